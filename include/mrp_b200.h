@@ -1,0 +1,193 @@
+/*
+ * mrp_b200.h — C ABI of the B200-native hot path of libMultiRobotPlanning.
+ *
+ * The reference is a header-only C++14 template library with NO plugin / FFI
+ * layer; its hot path is the duck-typed `Environment` concept that the
+ * CBS / ECBS / CBS-TA templates call back into.  This header is the boundary a
+ * maintainer binds instead: plain pointers and sizes, no C++ or torch types.
+ * Every entry point cites the reference code it replaces.  The C++ adapters in
+ * libmultirobotplanning_b200/host/ re-create the reference's `Environment`
+ * signatures on top of these calls.
+ *
+ * Conventions
+ *   - cell index = x + dimx*y (example/shortest_path_heuristic.hpp:65)
+ *   - all costs/distances are int32; MRP_INF = INT_MAX marks unreachable
+ *   - return value: 0 (or a non-negative answer) on success, negative
+ *     mrp_status on error; mrp_last_error() describes the last error of the
+ *     calling thread.  No exception crosses the ABI.
+ *   - "host" entry points take host pointers and do their own H2D/D2H copies;
+ *     `_dev` entry points take device pointers + a cudaStream_t (as void*) and
+ *     are asynchronous with respect to the host.
+ *   - there is NO CPU fallback: without a CUDA device every call fails with
+ *     MRP_ERR_NO_DEVICE.
+ */
+#ifndef MRP_B200_H
+#define MRP_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MRP_INF 2147483647
+
+typedef enum {
+  MRP_OK = 0,
+  MRP_ERR_NO_DEVICE = -1,
+  MRP_ERR_INVALID = -2,
+  MRP_ERR_CUDA = -3,
+  MRP_ERR_UNSUPPORTED = -4,
+  MRP_ERR_NOMEM = -5
+} mrp_status;
+
+/* ---- context --------------------------------------------------------- */
+/* Binds the calling process to CUDA device `device` (-1: keep the current
+ * one) and creates the library's streams.  Idempotent. */
+int mrp_init(int device);
+int mrp_shutdown(void);
+int mrp_device_count(void);
+const char* mrp_last_error(void);
+/* "major.minor name smcount" of the bound device, for logs */
+const char* mrp_device_info(void);
+
+/* ---- maps --------------------------------------------------------------
+ * A map handle owns the device-resident, bit-packed free-cell mask of one grid
+ * (1 bit per cell, 32x32-cell tiles).  Replaces the
+ * `std::unordered_set<Location> obstacles` every reference Environment keeps
+ * (example/cbs.cpp:561, example/cbs_ta.cpp:498). */
+typedef struct mrp_map_s* mrp_map;
+int mrp_map_create(int dimx, int dimy, const int32_t* obst_xy, int n_obst,
+                   mrp_map* out);
+int mrp_map_destroy(mrp_map map);
+
+/* ---- (1) distance fields -----------------------------------------------
+ * Replaces ShortestPathHeuristic::ShortestPathHeuristic (Floyd–Warshall over
+ * all cells, example/shortest_path_heuristic.hpp:12-54) and getValue (:58-62)
+ * by the goal rows only, i.e. the layout of the reference's disabled
+ * Environment::computeHeuristic (example/cbs.cpp:445-557):
+ *   out[g][x + dimx*y] = BFS distance from goal g, MRP_INF if unreachable or
+ *   obstacle; a goal that is itself an obstacle yields 0 at the goal and
+ *   MRP_INF elsewhere (the Floyd–Warshall row of an isolated vertex). */
+int mrp_bfs_fields(int dimx, int dimy, const int32_t* obst_xy, int n_obst,
+                   const int32_t* goal_xy, int n_goals, int32_t* out);
+/* Many small maps in one launch (configs C2/C4: every instance has its own
+ * obstacle layout).  dims[m] = (dimx, dimy); obstacles and goals are CSR over
+ * maps; fields are written back to back in goal order (field of goal k has
+ * dimx*dimy entries of its map). */
+int mrp_bfs_fields_batch(int n_maps, const int32_t* dims,
+                         const int32_t* obst_off, const int32_t* obst_xy,
+                         const int32_t* goal_off, const int32_t* goal_xy,
+                         int32_t* out);
+/* Device-resident variant: goals as cell indices, out = device int32
+ * [n_goals][dimx*dimy].  `workspace` must hold
+ * mrp_bfs_workspace_bytes(map, n_goals) bytes (may be 0). */
+size_t mrp_bfs_workspace_bytes(mrp_map map, int n_goals);
+int mrp_bfs_fields_dev(mrp_map map, const int32_t* d_goal_cell, int n_goals,
+                       int32_t* d_out, void* d_workspace, void* stream);
+
+/* ---- (2) conflicts over packed path tables -----------------------------
+ * Path table: cell[N][Tpad] int32 + len[N] (= PlanResult::states.size());
+ * positions past the end clamp to the last cell exactly like
+ * Environment::getState (example/cbs.cpp:420-429).  Entries with t >= len are
+ * never read.  mode 0: max_t = max(len)-1 (cbs/ecbs, example/cbs.cpp:338-341);
+ * mode 1: max_t = max(len) (cbs_ta, example/cbs_ta.cpp:372-375). */
+typedef struct {
+  int32_t time;
+  int32_t agent1;
+  int32_t agent2;
+  int32_t type; /* 0 Vertex, 1 Edge — Conflict::Type, example/cbs.cpp:81-84 */
+  int32_t x1, y1, x2, y2; /* x2,y2 = -1 for Vertex (unset in the reference) */
+} mrp_conflict;
+
+/* Environment::getFirstConflict (example/cbs.cpp:335-386,
+ * example/cbs_ta.cpp:369-420): returns 1 and fills *out with the first hit in
+ * the order (t, Vertex<Edge, agent1, agent2); 0 if conflict-free. */
+int mrp_first_conflict(const int32_t* cell, const int32_t* len, int N, int Tpad,
+                       int dimx, int mode, mrp_conflict* out);
+/* Environment::focalHeuristic (example/ecbs.cpp:315-350): number of vertex +
+ * edge conflicts over all agent pairs and timesteps, no early exit. */
+int mrp_count_conflicts(const int32_t* cell, const int32_t* len, int N,
+                        int Tpad, int mode, int32_t* count);
+/* Both answers for B tables of identical shape in one launch (one table per
+ * constraint-tree node): cell[B][N][Tpad], len[B][N]; found[B] (0/1),
+ * conflicts[B], counts[B] (counts may be NULL). */
+int mrp_conflicts_batch(const int32_t* cell, const int32_t* len, int B, int N,
+                        int Tpad, int dimx, int mode, int32_t* found,
+                        mrp_conflict* conflicts, int32_t* counts);
+/* Environment::focalStateHeuristic / focalTransitionHeuristic
+ * (example/ecbs.cpp:282-312) for n_cand candidate moves of agent `self`:
+ * candidate k leaves cand_from[k] at time cand_t[k] and arrives at cand_to[k]
+ * at cand_t[k]+1.  Agents with len == 0 are skipped (example/ecbs.cpp:287). */
+int mrp_focal_counts(const int32_t* cell, const int32_t* len, int N, int Tpad,
+                     int self, const int32_t* cand_t, const int32_t* cand_from,
+                     const int32_t* cand_to, int n_cand, int32_t* state_cnt,
+                     int32_t* trans_cnt);
+/* Device-resident variant of first-conflict + count.  d_result is 4 x int64:
+ * [0] packed first-conflict key (t<<41 | type<<40 | i<<20 | j), ~0 if none;
+ * [1] conflict count; [2],[3] scratch.  The call resets d_result itself. */
+int mrp_conflicts_dev(const int32_t* d_cell, const int32_t* d_len, int N,
+                      int Tpad, int mode, int want_first, int want_count,
+                      unsigned long long* d_result, void* stream);
+/* Decodes d_result[0] (copied to the host) into a conflict; returns 1/0.
+ * cell_i_t / cell_i_t1 are agent1's cells at `time` and `time+1`. */
+int mrp_decode_conflict(unsigned long long key, int dimx, int32_t cell_i_t,
+                        int32_t cell_i_t1, mrp_conflict* out);
+
+/* ---- (3) batched low-level replans --------------------------------------
+ * One job = one call of AStar::search (a_star.hpp:63-161) or
+ * AStarEpsilon::search (a_star_epsilon.hpp:86-285) for one agent under one
+ * constraint set, i.e. what CBS::search / ECBS::search / CBSTA::search issue
+ * at cbs.hpp:155-157, ecbs.hpp:265-268, cbs_ta.hpp:192-195.
+ * Constraints follow VertexConstraint(time,x,y) (arrival time) and
+ * EdgeConstraint(time,x1,y1,x2,y2) (departure time), example/cbs.cpp:108-163. */
+typedef struct {
+  int32_t map;        /* index into the maps[] array of the call */
+  int32_t start_cell; /* State(0, x, y) */
+  int32_t goal_cell;  /* -1: agent without task (cbs_ta, cbs_ta.cpp:283-319) */
+  int32_t field;      /* index into the fields of the call: distance field of
+                         goal_cell on that map (admissible heuristic) */
+  int32_t vc_begin, vc_end; /* range in vc[][2] = (time, cell) */
+  int32_t ec_begin, ec_end; /* range in ec[][3] = (time, from, to) */
+  int32_t table;  /* ECBS: index of the other agents' path table, -1: none */
+  int32_t self;   /* ECBS: this agent's row in that table (skipped) */
+} mrp_job;
+
+typedef struct {
+  int32_t status;   /* 0 solved, 1 no solution, 2 capped (horizon/expansions) */
+  int32_t cost;     /* PlanResult::cost */
+  int32_t fmin;     /* PlanResult::fmin */
+  int32_t length;   /* number of states (path rows written) */
+  int32_t expanded; /* low-level expansions (onExpandLowLevelNode) */
+} mrp_path_info;
+
+typedef struct {
+  int32_t variant;      /* 0: cbs/ecbs moves (all cost 1); 1: cbs_ta (waiting
+                           on the goal is free, example/cbs_ta.cpp:329-339) */
+  float w;              /* <= 0 or == 1.0: A*; > 1: A*-epsilon focal search */
+  int32_t max_expanded; /* per job cap (the reference has none) */
+  int32_t path_cap;     /* rows available per job in out_cells / out_g */
+} mrp_lowlevel_params;
+
+/* fields: [n_fields][cells] distance fields (e.g. from mrp_bfs_fields); all
+ * maps of one call must have the same dimensions.  tables: [n_tables][N][Tpad]
+ * + table_len[n_tables][N] (may be NULL when no job has table >= 0).
+ * out_cells/out_g: [n_jobs][path_cap] cell and g-score per state. */
+int mrp_lowlevel_batch(const mrp_map* maps, int n_maps, const int32_t* fields,
+                       int n_fields, const int32_t* vc, int n_vc,
+                       const int32_t* ec, int n_ec, const int32_t* tables,
+                       const int32_t* table_len, int n_tables, int N, int Tpad,
+                       const mrp_job* jobs, int n_jobs,
+                       const mrp_lowlevel_params* params, mrp_path_info* info,
+                       int32_t* out_cells, int32_t* out_g);
+
+/* ---- instrumentation ---------------------------------------------------- */
+/* number of kernel launches issued by this library since mrp_init (bench.py's
+ * `gpu_launches`) */
+long long mrp_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

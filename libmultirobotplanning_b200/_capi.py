@@ -1,0 +1,212 @@
+"""ctypes binding of libmrp_b200.so — the C ABI declared in include/mrp_b200.h.
+
+This is the only way Python code (tests, bench.py) reaches the CUDA path; the
+binding is a 1:1 mirror of the header.  There is no CPU fallback: if the
+shared library is missing or no CUDA device is present the calls raise.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG, "libmrp_b200.so")
+INF = 2147483647
+
+
+class MrpError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("mrp_b200 error %d: %s" % (code, msg))
+        self.code = code
+
+
+class Conflict(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in
+                ("time", "agent1", "agent2", "type", "x1", "y1", "x2", "y2")]
+
+    def astuple(self):
+        return (self.time, self.agent1, self.agent2, self.type,
+                self.x1, self.y1, self.x2, self.y2)
+
+
+class Job(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in
+                ("map", "start_cell", "goal_cell", "field", "vc_begin", "vc_end",
+                 "ec_begin", "ec_end", "table", "self_idx")]
+
+
+class PathInfo(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in
+                ("status", "cost", "fmin", "length", "expanded")]
+
+
+class LowLevelParams(C.Structure):
+    _fields_ = [("variant", C.c_int32), ("w", C.c_float),
+                ("max_expanded", C.c_int32), ("path_cap", C.c_int32)]
+
+
+EXPORTS = [
+    "mrp_init", "mrp_shutdown", "mrp_device_count", "mrp_last_error",
+    "mrp_device_info", "mrp_map_create", "mrp_map_destroy", "mrp_bfs_fields",
+    "mrp_bfs_fields_batch", "mrp_bfs_workspace_bytes", "mrp_bfs_fields_dev",
+    "mrp_first_conflict", "mrp_count_conflicts", "mrp_conflicts_batch",
+    "mrp_focal_counts", "mrp_conflicts_dev", "mrp_decode_conflict",
+    "mrp_lowlevel_batch", "mrp_launch_count",
+]
+
+_lib = None
+
+
+def lib():
+    """Loads the shared library (raises if it has not been built)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise MrpError(-1, "%s not found: build it with "
+                           "`python -c 'import __graft_entry__ as g; g.build()'` "
+                           "(there is no CPU fallback)" % LIB_PATH)
+        _lib = C.CDLL(LIB_PATH)
+        _lib.mrp_last_error.restype = C.c_char_p
+        _lib.mrp_device_info.restype = C.c_char_p
+        _lib.mrp_bfs_workspace_bytes.restype = C.c_size_t
+        _lib.mrp_bfs_workspace_bytes.argtypes = [C.c_void_p, C.c_int]
+        _lib.mrp_launch_count.restype = C.c_longlong
+        _lib.mrp_map_destroy.argtypes = [C.c_void_p]
+        _lib.mrp_bfs_fields_dev.argtypes = [C.c_void_p, C.c_void_p, C.c_int,
+                                            C.c_void_p, C.c_void_p, C.c_void_p]
+        _lib.mrp_conflicts_dev.argtypes = [C.c_void_p, C.c_void_p, C.c_int,
+                                           C.c_int, C.c_int, C.c_int, C.c_int,
+                                           C.c_void_p, C.c_void_p]
+        _lib.mrp_decode_conflict.argtypes = [C.c_ulonglong, C.c_int, C.c_int32,
+                                             C.c_int32, C.c_void_p]
+    return _lib
+
+
+def check(rc):
+    if rc < 0:
+        raise MrpError(rc, lib().mrp_last_error().decode())
+    return rc
+
+
+def _i32(a):
+    return np.ascontiguousarray(a, dtype=np.int32)
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+
+def init(device=-1):
+    check(lib().mrp_init(device))
+
+
+def device_info():
+    return lib().mrp_device_info().decode()
+
+
+def launch_count():
+    return int(lib().mrp_launch_count())
+
+
+class Map:
+    """Device-resident bit-packed map (mrp_map)."""
+
+    def __init__(self, dimx, dimy, obst_xy):
+        obst = _i32(obst_xy).reshape(-1, 2)
+        h = C.c_void_p()
+        check(lib().mrp_map_create(dimx, dimy, _p(obst), len(obst), C.byref(h)))
+        self.handle = h
+        self.dimx, self.dimy = dimx, dimy
+
+    def close(self):
+        if self.handle:
+            lib().mrp_map_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def workspace_bytes(self, n_goals):
+        return int(lib().mrp_bfs_workspace_bytes(self.handle, n_goals))
+
+    def bfs_fields_dev(self, d_goal_cell_ptr, n_goals, d_out_ptr, d_ws_ptr, stream=0):
+        check(lib().mrp_bfs_fields_dev(self.handle, d_goal_cell_ptr, n_goals,
+                                       d_out_ptr, d_ws_ptr, stream))
+
+
+def bfs_fields(dimx, dimy, obst_xy, goal_xy, out=None):
+    obst = _i32(obst_xy).reshape(-1, 2)
+    goals = _i32(goal_xy).reshape(-1, 2)
+    if out is None:
+        out = np.empty((len(goals), dimy * dimx), np.int32)
+    check(lib().mrp_bfs_fields(dimx, dimy, _p(obst), len(obst), _p(goals),
+                               len(goals), _p(out)))
+    return out
+
+
+def bfs_fields_batch(instances):
+    """instances: iterable of objects with dimx, dimy, obstacles, goals.
+    Returns a list of [n_goals, cells] int32 arrays (one per instance)."""
+    instances = list(instances)
+    dims = _i32([[i.dimx, i.dimy] for i in instances]).reshape(-1, 2)
+    ooff = np.zeros(len(instances) + 1, np.int32)
+    goff = np.zeros(len(instances) + 1, np.int32)
+    for k, i in enumerate(instances):
+        ooff[k + 1] = ooff[k] + len(i.obstacles)
+        goff[k + 1] = goff[k] + len(i.goals)
+    obst = _i32(np.concatenate([np.asarray(i.obstacles).reshape(-1, 2)
+                                for i in instances]) if instances else [])
+    goals = _i32(np.concatenate([np.asarray(i.goals).reshape(-1, 2)
+                                 for i in instances]) if instances else [])
+    sizes = [len(i.goals) * i.dimx * i.dimy for i in instances]
+    out = np.empty(int(sum(sizes)), np.int32)
+    check(lib().mrp_bfs_fields_batch(len(instances), _p(dims), _p(ooff), _p(obst),
+                                     _p(goff), _p(goals), _p(out)))
+    res, off = [], 0
+    for i, s in zip(instances, sizes):
+        res.append(out[off:off + s].reshape(len(i.goals), i.dimx * i.dimy))
+        off += s
+    return res
+
+
+def first_conflict(cell, length, dimx, mode):
+    cell, length = _i32(cell), _i32(length)
+    N, Tpad = cell.shape
+    c = Conflict()
+    found = check(lib().mrp_first_conflict(_p(cell), _p(length), N, Tpad, dimx,
+                                           mode, C.byref(c)))
+    return c.astuple() if found else None
+
+
+def count_conflicts(cell, length, mode=0):
+    cell, length = _i32(cell), _i32(length)
+    N, Tpad = cell.shape
+    n = C.c_int32(0)
+    check(lib().mrp_count_conflicts(_p(cell), _p(length), N, Tpad, mode,
+                                    C.byref(n)))
+    return n.value
+
+
+def conflicts_batch(cell, length, dimx, mode):
+    cell, length = _i32(cell), _i32(length)
+    B, N, Tpad = cell.shape
+    found = np.zeros(B, np.int32)
+    counts = np.zeros(B, np.int32)
+    confl = (Conflict * B)()
+    check(lib().mrp_conflicts_batch(_p(cell), _p(length), B, N, Tpad, dimx, mode,
+                                    _p(found), confl, _p(counts)))
+    return [confl[b].astuple() if found[b] else None for b in range(B)], counts
+
+
+def focal_counts(cell, length, self_idx, cand_t, cand_from, cand_to):
+    cell, length = _i32(cell), _i32(length)
+    N, Tpad = cell.shape
+    ct, cf, cto = _i32(cand_t), _i32(cand_from), _i32(cand_to)
+    s = np.zeros(len(ct), np.int32)
+    tr = np.zeros(len(ct), np.int32)
+    check(lib().mrp_focal_counts(_p(cell), _p(length), N, Tpad, self_idx, _p(ct),
+                                 _p(cf), _p(cto), len(ct), _p(s), _p(tr)))
+    return s, tr

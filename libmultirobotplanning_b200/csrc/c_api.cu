@@ -1,0 +1,582 @@
+// c_api.cu — the extern "C" surface declared in include/mrp_b200.h: context,
+// maps, and the host-pointer convenience entry points (they stage H2D/D2H
+// copies around the kernels of bfs_small.cu / bfs_large.cu / conflicts.cu /
+// lowlevel.cu).  No CPU fallback anywhere: without a device every call fails.
+#include <algorithm>
+#include <cstring>
+#include <mutex>
+#include <vector>
+
+#include "common.cuh"
+
+namespace mrp {
+
+std::atomic<long long> g_launches{0};
+
+std::string& lastErrorStorage() {
+  thread_local std::string s;
+  return s;
+}
+
+int fail(int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  lastErrorStorage() = buf;
+  return code;
+}
+
+Context& ctx() {
+  static Context c;
+  return c;
+}
+
+static std::mutex& apiMutex() {
+  static std::mutex m;
+  return m;
+}
+
+static int initLocked(int device) {
+  Context& c = ctx();
+  if (c.ready && (device < 0 || device == c.device)) return 0;
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0)
+    return fail(MRP_ERR_NO_DEVICE,
+                "no CUDA device available (%s); this library has no CPU fallback",
+                e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+  if (device < 0) {
+    if (cudaGetDevice(&device) != cudaSuccess) device = 0;
+  }
+  MRP_CHECK(device < n, MRP_ERR_INVALID, "device %d out of range (%d devices)",
+            device, n);
+  MRP_CUDA(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  MRP_CUDA(cudaGetDeviceProperties(&prop, device));
+  if (c.ready) {
+    cudaStreamDestroy(c.stream);
+    cudaStreamDestroy(c.copyStream);
+  }
+  c.device = device;
+  c.smCount = prop.multiProcessorCount;
+  c.smemOptin = prop.sharedMemPerBlockOptin;
+  MRP_CUDA(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
+  MRP_CUDA(cudaStreamCreateWithFlags(&c.copyStream, cudaStreamNonBlocking));
+  char buf[256];
+  snprintf(buf, sizeof buf, "%d.%d %s sm=%d smem_optin=%zu", prop.major, prop.minor,
+           prop.name, prop.multiProcessorCount, (size_t)prop.sharedMemPerBlockOptin);
+  c.info = buf;
+  c.ready = true;
+  return 0;
+}
+
+int ensureInit() {
+  if (ctx().ready) {
+    // other libraries (torch) may have changed the current device
+    cudaSetDevice(ctx().device);
+    return 0;
+  }
+  return initLocked(-1);
+}
+
+// grow-only device scratch slots for the host-pointer entry points
+struct Scratch {
+  void* p = nullptr;
+  size_t cap = 0;
+  int get(size_t bytes, void** out) {
+    if (bytes > cap) {
+      if (p) cudaFree(p);
+      p = nullptr;
+      cap = 0;
+      size_t want = std::max(bytes, (size_t)1 << 16);
+      want += want / 4;
+      cudaError_t e = cudaMalloc(&p, want);
+      if (e != cudaSuccess)
+        return fail(MRP_ERR_NOMEM, "cudaMalloc(%zu) failed: %s", want,
+                    cudaGetErrorString(e));
+      cap = want;
+    }
+    *out = p;
+    return 0;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+  }
+};
+static Scratch g_scratch[12];
+
+template <class T>
+static int scratch(int slot, size_t count, T** out) {
+  void* p = nullptr;
+  int rc = g_scratch[slot].get(count * sizeof(T), &p);
+  *out = static_cast<T*>(p);
+  return rc;
+}
+
+static void packMapBits(int dimx, int dimy, const int32_t* obst_xy, int n_obst,
+                        std::vector<uint32_t>& bits, int* Wout, int* Sout) {
+  const int W = (dimx + 31) / 32, S = (dimy + 31) / 32;
+  bits.assign((size_t)W * S * 32, 0u);
+  for (int y = 0; y < dimy; ++y) {
+    const int s = y >> 5, r = y & 31;
+    for (int tx = 0; tx < W; ++tx) {
+      const int n = std::min(32, dimx - tx * 32);
+      bits[((size_t)s * W + tx) * 32 + r] = n == 32 ? 0xffffffffu : ((1u << n) - 1u);
+    }
+  }
+  for (int k = 0; k < n_obst; ++k) {
+    const int x = obst_xy[2 * k], y = obst_xy[2 * k + 1];
+    // obstacles outside the map are never looked up by the reference
+    if (x < 0 || y < 0 || x >= dimx || y >= dimy) continue;
+    bits[((size_t)(y >> 5) * W + (x >> 5)) * 32 + (y & 31)] &= ~(1u << (x & 31));
+  }
+  *Wout = W;
+  *Sout = S;
+}
+
+static int validateGoals(int dimx, int dimy, const int32_t* goal_xy, int n_goals) {
+  for (int k = 0; k < n_goals; ++k) {
+    const int x = goal_xy[2 * k], y = goal_xy[2 * k + 1];
+    MRP_CHECK(x >= 0 && y >= 0 && x < dimx && y < dimy, MRP_ERR_INVALID,
+              "goal %d = (%d,%d) lies outside the %dx%d map", k, x, y, dimx, dimy);
+  }
+  return 0;
+}
+
+}  // namespace mrp
+
+using namespace mrp;
+
+extern "C" {
+
+int mrp_init(int device) {
+  std::lock_guard<std::mutex> lk(apiMutex());
+  return initLocked(device);
+}
+
+int mrp_shutdown(void) {
+  std::lock_guard<std::mutex> lk(apiMutex());
+  Context& c = ctx();
+  if (!c.ready) return 0;
+  cudaSetDevice(c.device);
+  cudaDeviceSynchronize();
+  for (auto& s : g_scratch) s.release();
+  cudaStreamDestroy(c.stream);
+  cudaStreamDestroy(c.copyStream);
+  c.ready = false;
+  return 0;
+}
+
+int mrp_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+  return n;
+}
+
+const char* mrp_last_error(void) { return lastErrorStorage().c_str(); }
+
+const char* mrp_device_info(void) {
+  std::lock_guard<std::mutex> lk(apiMutex());
+  if (ensureInit() != 0) return "";
+  return ctx().info.c_str();
+}
+
+long long mrp_launch_count(void) { return g_launches.load(); }
+
+// ---- maps ------------------------------------------------------------------
+int mrp_map_create(int dimx, int dimy, const int32_t* obst_xy, int n_obst,
+                   mrp_map* out) {
+  std::lock_guard<std::mutex> lk(apiMutex());
+  MRP_CHECK(out != nullptr, MRP_ERR_INVALID, "out is NULL");
+  *out = nullptr;
+  MRP_CHECK(dimx > 0 && dimy > 0, MRP_ERR_INVALID, "bad dimensions %dx%d", dimx, dimy);
+  MRP_CHECK((long long)dimx * dimy < (1ll << 30), MRP_ERR_UNSUPPORTED,
+            "map of %dx%d cells is too large", dimx, dimy);
+  MRP_CHECK(n_obst == 0 || obst_xy != nullptr, MRP_ERR_INVALID, "obst_xy is NULL");
+  if (int rc = ensureInit()) return rc;
+  std::vector<uint32_t> bits;
+  int W, S;
+  packMapBits(dimx, dimy, obst_xy, n_obst, bits, &W, &S);
+  mrp_map_s* m = new mrp_map_s();
+  m->dimx = dimx;
+  m->dimy = dimy;
+  m->W = W;
+  m->S = S;
+  m->h_bits = new uint32_t[bits.size()];
+  std::memcpy(m->h_bits, bits.data(), bits.size() * 4);
+  cudaError_t e = cudaMalloc(&m->d_bits, bits.size() * 4);
+  if (e == cudaSuccess)
+    e = cudaMemcpy(m->d_bits, bits.data(), bits.size() * 4, cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) {
+    delete[] m->h_bits;
+    delete m;
+    return fail(MRP_ERR_CUDA, "map upload failed: %s", cudaGetErrorString(e));
+  }
+  *out = m;
+  return 0;
+}
+
+int mrp_map_destroy(mrp_map map) {
+  std::lock_guard<std::mutex> lk(apiMutex());
+  if (!map) return 0;
+  if (ctx().ready) cudaSetDevice(ctx().device);
+  cudaFree(map->d_bits);
+  delete[] map->h_bits;
+  delete map;
+  return 0;
+}
+
+// ---- (1) distance fields -----------------------------------------------------
+size_t mrp_bfs_workspace_bytes(mrp_map map, int n_goals) {
+  std::lock_guard<std::mutex> lk(apiMutex());
+  if (!map || ensureInit() != 0) return 0;
+  if (map->W == 1 && map->S == 1) return 16 * (size_t)std::max(n_goals, 1) + 256;
+  return bfsLargeWorkspaceBytes(map, n_goals);
+}
+
+// jobs for the single-tile kernel, built on the device side of the ABI
+__global__ void make_small_jobs_kernel(const int32_t* goal_cell, int n, int cells,
+                                       int4* jobs) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  const long long off = (long long)k * cells;
+  jobs[k] = make_int4(0, goal_cell[k], (int)(off & 0xffffffffll), (int)(off >> 32));
+}
+
+static int bfsFieldsDevLocked(mrp_map map, const int32_t* d_goal_cell, int n_goals,
+                              int32_t* d_out, void* d_ws, cudaStream_t st) {
+  if (n_goals == 0) return 0;
+  if (map->W == 1 && map->S == 1) {
+    // workspace: [0,256) dims, then jobs
+    int32_t* d_dims = static_cast<int32_t*>(d_ws);
+    int4* d_jobs = reinterpret_cast<int4*>(static_cast<char*>(d_ws) + 256);
+    const int32_t dims[2] = {map->dimx, map->dimy};
+    MRP_CUDA(cudaMemcpyAsync(d_dims, dims, sizeof dims, cudaMemcpyHostToDevice, st));
+    make_small_jobs_kernel<<<(n_goals + 255) / 256, 256, 0, st>>>(
+        d_goal_cell, n_goals, map->dimx * map->dimy, d_jobs);
+    countLaunch();
+    return launchBfsSmall(map->d_bits, d_dims, d_jobs, n_goals, d_out, st);
+  }
+  return launchBfsLarge(map, d_goal_cell, n_goals, d_out, d_ws, st);
+}
+
+int mrp_bfs_fields_dev(mrp_map map, const int32_t* d_goal_cell, int n_goals,
+                       int32_t* d_out, void* d_workspace, void* stream) {
+  std::lock_guard<std::mutex> lk(apiMutex());
+  MRP_CHECK(map != nullptr, MRP_ERR_INVALID, "map is NULL");
+  MRP_CHECK(n_goals >= 0, MRP_ERR_INVALID, "n_goals < 0");
+  if (int rc = ensureInit()) return rc;
+  MRP_CHECK(n_goals == 0 || (d_goal_cell && d_out && d_workspace), MRP_ERR_INVALID,
+            "NULL device pointer");
+  return bfsFieldsDevLocked(map, d_goal_cell, n_goals, d_out, d_workspace,
+                            static_cast<cudaStream_t>(stream));
+}
+
+int mrp_bfs_fields(int dimx, int dimy, const int32_t* obst_xy, int n_obst,
+                   const int32_t* goal_xy, int n_goals, int32_t* out) {
+  MRP_CHECK(n_goals >= 0, MRP_ERR_INVALID, "n_goals < 0");
+  MRP_CHECK(n_goals == 0 || (goal_xy && out), MRP_ERR_INVALID, "NULL pointer");
+  if (int rc = validateGoals(dimx, dimy, goal_xy, n_goals)) return rc;
+  mrp_map map = nullptr;
+  if (int rc = mrp_map_create(dimx, dimy, obst_xy, n_obst, &map)) return rc;
+  int rc = 0;
+  {
+    std::lock_guard<std::mutex> lk(apiMutex());
+    Context& c = ctx();
+    const size_t cells = (size_t)dimx * dimy;
+    const size_t fieldBytes = cells * 4;
+    // goals are processed in batches; batch k+1 computes while batch k is
+    // copied back on the copy stream (double-buffered device output)
+    size_t batch = std::max<size_t>(4 * (size_t)c.smCount, ((size_t)1 << 30) / fieldBytes);
+    batch = std::min<size_t>(batch, (size_t)n_goals);
+    std::vector<int32_t> goalCell(n_goals);
+    for (int k = 0; k < n_goals; ++k)
+      goalCell[k] = goal_xy[2 * k] + dimx * goal_xy[2 * k + 1];
+    int32_t* d_goals = nullptr;
+    int32_t* d_out[2] = {nullptr, nullptr};
+    void* d_ws = nullptr;
+    const bool twoBuffers = (size_t)n_goals > batch;
+    size_t wsBytes = (map->W == 1 && map->S == 1) ? 16 * batch + 256
+                                                  : bfsLargeWorkspaceBytes(map, (int)batch);
+    cudaEvent_t done[2] = {nullptr, nullptr}, copied[2] = {nullptr, nullptr};
+    do {
+      if ((rc = scratch(0, (size_t)std::max(n_goals, 1), &d_goals))) break;
+      if ((rc = scratch(1, batch * cells, &d_out[0]))) break;
+      if (twoBuffers && (rc = scratch(2, batch * cells, &d_out[1]))) break;
+      char* wsp = nullptr;
+      if ((rc = scratch(3, wsBytes, &wsp))) break;
+      d_ws = wsp;
+      for (int b = 0; b < 2; ++b) {
+        cudaEventCreateWithFlags(&done[b], cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&copied[b], cudaEventDisableTiming);
+      }
+      cudaError_t e = cudaMemcpyAsync(d_goals, goalCell.data(), (size_t)n_goals * 4,
+                                      cudaMemcpyHostToDevice, c.stream);
+      if (e != cudaSuccess) {
+        rc = fail(MRP_ERR_CUDA, "H2D copy failed: %s", cudaGetErrorString(e));
+        break;
+      }
+      int b = 0;
+      for (size_t g0 = 0; g0 < (size_t)n_goals && rc == 0; g0 += batch, b ^= 1) {
+        const size_t n = std::min(batch, (size_t)n_goals - g0);
+        int32_t* dst = twoBuffers ? d_out[b] : d_out[0];
+        // the buffer must have been drained by its previous D2H copy
+        cudaStreamWaitEvent(c.stream, copied[b], 0);
+        rc = bfsFieldsDevLocked(map, d_goals + g0, (int)n, dst, d_ws, c.stream);
+        if (rc) break;
+        cudaEventRecord(done[b], c.stream);
+        cudaStreamWaitEvent(c.copyStream, done[b], 0);
+        e = cudaMemcpyAsync(out + g0 * cells, dst, n * fieldBytes,
+                            cudaMemcpyDeviceToHost, c.copyStream);
+        if (e != cudaSuccess) {
+          rc = fail(MRP_ERR_CUDA, "D2H copy failed: %s", cudaGetErrorString(e));
+          break;
+        }
+        cudaEventRecord(copied[b], c.copyStream);
+      }
+      cudaError_t e1 = cudaStreamSynchronize(c.stream);
+      cudaError_t e2 = cudaStreamSynchronize(c.copyStream);
+      if (rc == 0 && (e1 != cudaSuccess || e2 != cudaSuccess))
+        rc = fail(MRP_ERR_CUDA, "bfs fields failed: %s",
+                  cudaGetErrorString(e1 != cudaSuccess ? e1 : e2));
+    } while (0);
+    for (int b = 0; b < 2; ++b) {
+      if (done[b]) cudaEventDestroy(done[b]);
+      if (copied[b]) cudaEventDestroy(copied[b]);
+    }
+  }
+  mrp_map_destroy(map);
+  return rc;
+}
+
+int mrp_bfs_fields_batch(int n_maps, const int32_t* dims, const int32_t* obst_off,
+                         const int32_t* obst_xy, const int32_t* goal_off,
+                         const int32_t* goal_xy, int32_t* out) {
+  MRP_CHECK(n_maps >= 0, MRP_ERR_INVALID, "n_maps < 0");
+  if (n_maps == 0) return 0;
+  MRP_CHECK(dims && obst_off && goal_off, MRP_ERR_INVALID, "NULL pointer");
+  bool allSmall = true;
+  for (int m = 0; m < n_maps; ++m) {
+    MRP_CHECK(dims[2 * m] > 0 && dims[2 * m + 1] > 0, MRP_ERR_INVALID,
+              "map %d has bad dimensions", m);
+    if (dims[2 * m] > 32 || dims[2 * m + 1] > 32) allSmall = false;
+    if (int rc = validateGoals(dims[2 * m], dims[2 * m + 1], goal_xy + 2 * goal_off[m],
+                               goal_off[m + 1] - goal_off[m]))
+      return rc;
+  }
+  if (!allSmall) {
+    // large maps: one map at a time through the tiled kernel
+    size_t off = 0;
+    for (int m = 0; m < n_maps; ++m) {
+      const int ng = goal_off[m + 1] - goal_off[m];
+      int rc = mrp_bfs_fields(dims[2 * m], dims[2 * m + 1], obst_xy + 2 * obst_off[m],
+                              obst_off[m + 1] - obst_off[m], goal_xy + 2 * goal_off[m],
+                              ng, out + off);
+      if (rc) return rc;
+      off += (size_t)ng * dims[2 * m] * dims[2 * m + 1];
+    }
+    return 0;
+  }
+  std::lock_guard<std::mutex> lk(apiMutex());
+  if (int rc = ensureInit()) return rc;
+  Context& c = ctx();
+  const int n_goals = goal_off[n_maps];
+  if (n_goals == 0) return 0;
+  std::vector<uint32_t> rows((size_t)n_maps * 32);
+  std::vector<int4> jobs(n_goals);
+  long long off = 0;
+  for (int m = 0; m < n_maps; ++m) {
+    std::vector<uint32_t> bits;
+    int W, S;
+    packMapBits(dims[2 * m], dims[2 * m + 1], obst_xy + 2 * obst_off[m],
+                obst_off[m + 1] - obst_off[m], bits, &W, &S);
+    std::memcpy(&rows[(size_t)m * 32], bits.data(), 32 * 4);
+    const int cells = dims[2 * m] * dims[2 * m + 1];
+    for (int k = goal_off[m]; k < goal_off[m + 1]; ++k) {
+      jobs[k] = make_int4(m, goal_xy[2 * k] + dims[2 * m] * goal_xy[2 * k + 1],
+                          (int)(off & 0xffffffffll), (int)(off >> 32));
+      off += cells;
+    }
+  }
+  uint32_t* d_rows;
+  int32_t* d_dims;
+  int4* d_jobs;
+  int32_t* d_out;
+  if (int rc = scratch(4, rows.size(), &d_rows)) return rc;
+  if (int rc = scratch(5, (size_t)2 * n_maps, &d_dims)) return rc;
+  if (int rc = scratch(6, jobs.size(), &d_jobs)) return rc;
+  if (int rc = scratch(1, (size_t)off, &d_out)) return rc;
+  MRP_CUDA(cudaMemcpyAsync(d_rows, rows.data(), rows.size() * 4, cudaMemcpyHostToDevice, c.stream));
+  MRP_CUDA(cudaMemcpyAsync(d_dims, dims, (size_t)2 * n_maps * 4, cudaMemcpyHostToDevice, c.stream));
+  MRP_CUDA(cudaMemcpyAsync(d_jobs, jobs.data(), jobs.size() * sizeof(int4), cudaMemcpyHostToDevice, c.stream));
+  if (int rc = launchBfsSmall(d_rows, d_dims, d_jobs, n_goals, d_out, c.stream)) return rc;
+  MRP_CUDA(cudaMemcpyAsync(out, d_out, (size_t)off * 4, cudaMemcpyDeviceToHost, c.stream));
+  MRP_CUDA(cudaStreamSynchronize(c.stream));
+  return 0;
+}
+
+// ---- (2) conflicts -------------------------------------------------------------
+int mrp_decode_conflict(unsigned long long key, int dimx, int32_t cell_i_t,
+                        int32_t cell_i_t1, mrp_conflict* out) {
+  if (key == kNoConflict) return 0;
+  out->time = (int32_t)(key >> 41);
+  out->type = (int32_t)((key >> 40) & 1);
+  out->agent1 = (int32_t)((key >> 20) & 0xfffff);
+  out->agent2 = (int32_t)(key & 0xfffff);
+  out->x1 = cell_i_t % dimx;
+  out->y1 = cell_i_t / dimx;
+  if (out->type == 1) {
+    out->x2 = cell_i_t1 % dimx;
+    out->y2 = cell_i_t1 / dimx;
+  } else {
+    out->x2 = -1;
+    out->y2 = -1;
+  }
+  return 1;
+}
+
+static int checkTable(const int32_t* cell, const int32_t* len, int N, int Tpad) {
+  MRP_CHECK(N >= 0 && Tpad >= 0, MRP_ERR_INVALID, "negative table shape");
+  MRP_CHECK(N < kMaxAgents, MRP_ERR_UNSUPPORTED, "N=%d exceeds %d agents", N, kMaxAgents);
+  MRP_CHECK(Tpad < kMaxTime, MRP_ERR_UNSUPPORTED, "Tpad=%d exceeds %d", Tpad, kMaxTime);
+  MRP_CHECK(N == 0 || (cell && len), MRP_ERR_INVALID, "NULL table pointer");
+  for (int i = 0; i < N; ++i)
+    MRP_CHECK(len[i] >= 0 && len[i] <= Tpad, MRP_ERR_INVALID,
+              "len[%d]=%d outside [0,%d]", i, len[i], Tpad);
+  return 0;
+}
+
+static inline int32_t hostPos(const int32_t* cell, const int32_t* len, int Tpad, int i,
+                              int t) {
+  const int L = len[i];
+  return cell[(size_t)i * Tpad + (t < L ? t : L - 1)];
+}
+
+static int conflictsHost(const int32_t* cell, const int32_t* len, int B, int N, int Tpad,
+                         int dimx, int mode, bool wantFirst, bool wantCount,
+                         int32_t* found, mrp_conflict* conflicts, int32_t* counts) {
+  for (int b = 0; b < B; ++b)
+    if (int rc = checkTable(cell + (size_t)b * N * Tpad, len + (size_t)b * N, N, Tpad))
+      return rc;
+  MRP_CHECK(mode == 0 || mode == 1, MRP_ERR_INVALID, "mode must be 0 or 1");
+  for (int b = 0; b < B; ++b) {
+    if (found) found[b] = 0;
+    if (counts) counts[b] = 0;
+  }
+  if (N < 2 || Tpad == 0 || B == 0) return 0;
+  std::lock_guard<std::mutex> lk(apiMutex());
+  if (int rc = ensureInit()) return rc;
+  Context& c = ctx();
+  int32_t *d_cell, *d_len;
+  unsigned long long* d_res;
+  const size_t nCell = (size_t)B * N * Tpad;
+  if (int rc = scratch(7, nCell, &d_cell)) return rc;
+  if (int rc = scratch(8, (size_t)B * N, &d_len)) return rc;
+  if (int rc = scratch(9, (size_t)4 * B, &d_res)) return rc;
+  MRP_CUDA(cudaMemcpyAsync(d_cell, cell, nCell * 4, cudaMemcpyHostToDevice, c.stream));
+  MRP_CUDA(cudaMemcpyAsync(d_len, len, (size_t)B * N * 4, cudaMemcpyHostToDevice, c.stream));
+  int rc = (B == 1) ? launchConflicts(d_cell, d_len, N, Tpad, mode, wantFirst, wantCount,
+                                      d_res, c.stream)
+                    : launchConflictsBatch(d_cell, d_len, B, N, Tpad, mode, d_res, c.stream);
+  if (rc) return rc;
+  std::vector<unsigned long long> res((size_t)4 * B);
+  MRP_CUDA(cudaMemcpyAsync(res.data(), d_res, res.size() * 8, cudaMemcpyDeviceToHost, c.stream));
+  MRP_CUDA(cudaStreamSynchronize(c.stream));
+  for (int b = 0; b < B; ++b) {
+    const int32_t* tc = cell + (size_t)b * N * Tpad;
+    const int32_t* tl = len + (size_t)b * N;
+    if (counts) counts[b] = (int32_t)res[4 * b + 1];
+    if (found && conflicts) {
+      const unsigned long long key = res[4 * b];
+      if (key != kNoConflict) {
+        const int t = (int)(key >> 41), i = (int)((key >> 20) & 0xfffff);
+        found[b] = mrp_decode_conflict(key, dimx, hostPos(tc, tl, Tpad, i, t),
+                                       hostPos(tc, tl, Tpad, i, t + 1), &conflicts[b]);
+      }
+    }
+  }
+  return 0;
+}
+
+int mrp_first_conflict(const int32_t* cell, const int32_t* len, int N, int Tpad,
+                       int dimx, int mode, mrp_conflict* out) {
+  MRP_CHECK(out != nullptr && dimx > 0, MRP_ERR_INVALID, "bad arguments");
+  std::memset(out, 0xff, sizeof *out);
+  int32_t found = 0;
+  int rc = conflictsHost(cell, len, 1, N, Tpad, dimx, mode, true, false, &found, out,
+                         nullptr);
+  return rc ? rc : found;
+}
+
+int mrp_count_conflicts(const int32_t* cell, const int32_t* len, int N, int Tpad,
+                        int mode, int32_t* count) {
+  MRP_CHECK(count != nullptr, MRP_ERR_INVALID, "count is NULL");
+  return conflictsHost(cell, len, 1, N, Tpad, 1, mode, false, true, nullptr, nullptr,
+                       count);
+}
+
+int mrp_conflicts_batch(const int32_t* cell, const int32_t* len, int B, int N, int Tpad,
+                        int dimx, int mode, int32_t* found, mrp_conflict* conflicts,
+                        int32_t* counts) {
+  MRP_CHECK(B >= 0 && dimx > 0, MRP_ERR_INVALID, "bad arguments");
+  MRP_CHECK(B == 0 || (found && conflicts), MRP_ERR_INVALID, "NULL output");
+  for (int b = 0; b < B; ++b) std::memset(&conflicts[b], 0xff, sizeof(mrp_conflict));
+  return conflictsHost(cell, len, B, N, Tpad, dimx, mode, true, true, found, conflicts,
+                       counts);
+}
+
+int mrp_conflicts_dev(const int32_t* d_cell, const int32_t* d_len, int N, int Tpad,
+                      int mode, int want_first, int want_count,
+                      unsigned long long* d_result, void* stream) {
+  std::lock_guard<std::mutex> lk(apiMutex());
+  MRP_CHECK(d_cell && d_len && d_result, MRP_ERR_INVALID, "NULL device pointer");
+  MRP_CHECK(N >= 2 && N < kMaxAgents && Tpad > 0 && Tpad < kMaxTime, MRP_ERR_INVALID,
+            "bad table shape N=%d Tpad=%d", N, Tpad);
+  MRP_CHECK(want_first || want_count, MRP_ERR_INVALID, "nothing requested");
+  if (int rc = ensureInit()) return rc;
+  return launchConflicts(d_cell, d_len, N, Tpad, mode, want_first != 0, want_count != 0,
+                         d_result, static_cast<cudaStream_t>(stream));
+}
+
+int mrp_focal_counts(const int32_t* cell, const int32_t* len, int N, int Tpad, int self,
+                     const int32_t* cand_t, const int32_t* cand_from,
+                     const int32_t* cand_to, int n_cand, int32_t* state_cnt,
+                     int32_t* trans_cnt) {
+  if (int rc = checkTable(cell, len, N, Tpad)) return rc;
+  MRP_CHECK(n_cand >= 0, MRP_ERR_INVALID, "n_cand < 0");
+  if (n_cand == 0) return 0;
+  MRP_CHECK(cand_t && cand_from && cand_to && state_cnt && trans_cnt, MRP_ERR_INVALID,
+            "NULL pointer");
+  if (N == 0 || Tpad == 0) {
+    std::memset(state_cnt, 0, (size_t)n_cand * 4);
+    std::memset(trans_cnt, 0, (size_t)n_cand * 4);
+    return 0;
+  }
+  std::lock_guard<std::mutex> lk(apiMutex());
+  if (int rc = ensureInit()) return rc;
+  Context& c = ctx();
+  int32_t *d_cell, *d_len, *d_cand, *d_out;
+  if (int rc = scratch(7, (size_t)N * Tpad, &d_cell)) return rc;
+  if (int rc = scratch(8, (size_t)N, &d_len)) return rc;
+  if (int rc = scratch(10, (size_t)3 * n_cand, &d_cand)) return rc;
+  if (int rc = scratch(11, (size_t)2 * n_cand, &d_out)) return rc;
+  MRP_CUDA(cudaMemcpyAsync(d_cell, cell, (size_t)N * Tpad * 4, cudaMemcpyHostToDevice, c.stream));
+  MRP_CUDA(cudaMemcpyAsync(d_len, len, (size_t)N * 4, cudaMemcpyHostToDevice, c.stream));
+  MRP_CUDA(cudaMemcpyAsync(d_cand, cand_t, (size_t)n_cand * 4, cudaMemcpyHostToDevice, c.stream));
+  MRP_CUDA(cudaMemcpyAsync(d_cand + n_cand, cand_from, (size_t)n_cand * 4, cudaMemcpyHostToDevice, c.stream));
+  MRP_CUDA(cudaMemcpyAsync(d_cand + 2 * n_cand, cand_to, (size_t)n_cand * 4, cudaMemcpyHostToDevice, c.stream));
+  if (int rc = launchFocalCounts(d_cell, d_len, N, Tpad, self, d_cand, d_cand + n_cand,
+                                 d_cand + 2 * n_cand, n_cand, d_out, d_out + n_cand,
+                                 c.stream))
+    return rc;
+  MRP_CUDA(cudaMemcpyAsync(state_cnt, d_out, (size_t)n_cand * 4, cudaMemcpyDeviceToHost, c.stream));
+  MRP_CUDA(cudaMemcpyAsync(trans_cnt, d_out + n_cand, (size_t)n_cand * 4, cudaMemcpyDeviceToHost, c.stream));
+  MRP_CUDA(cudaStreamSynchronize(c.stream));
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,117 @@
+// common.cuh — shared helpers of the mrp_b200 CUDA library (sm_100a only).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <string>
+
+#include "../../include/mrp_b200.h"
+
+namespace mrp {
+
+constexpr int kTile = 32;  // maps are tiled in 32x32-cell tiles, one bit per cell
+
+// ---- error handling (thread-local message, never throws across the ABI) ----
+std::string& lastErrorStorage();
+int fail(int code, const char* fmt, ...);
+
+#define MRP_CUDA(expr)                                                     \
+  do {                                                                     \
+    cudaError_t _e = (expr);                                               \
+    if (_e != cudaSuccess)                                                 \
+      return ::mrp::fail(MRP_ERR_CUDA, "%s failed: %s (%s:%d)", #expr,     \
+                         cudaGetErrorString(_e), __FILE__, __LINE__);      \
+  } while (0)
+
+#define MRP_CHECK(cond, code, ...)                         \
+  do {                                                     \
+    if (!(cond)) return ::mrp::fail(code, __VA_ARGS__);    \
+  } while (0)
+
+// ---- context ----
+struct Context {
+  bool ready = false;
+  int device = -1;
+  int smCount = 0;
+  size_t smemOptin = 0;
+  cudaStream_t stream = nullptr;   // compute
+  cudaStream_t copyStream = nullptr;
+  std::string info;
+};
+Context& ctx();
+int ensureInit();
+extern std::atomic<long long> g_launches;
+inline void countLaunch(int n = 1) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+// ---- device map ----
+}  // namespace mrp
+
+struct mrp_map_s {
+  int dimx, dimy;
+  int W;   // tiles per row  = ceil(dimx/32)
+  int S;   // tile rows (stripes) = ceil(dimy/32)
+  // free mask, tile-major: bits[(s*W + tx)*32 + r] = row 32*s+r, word tx;
+  // bit b of that word = cell x = 32*tx + b.  Bits outside the map are 0.
+  uint32_t* d_bits;
+  uint32_t* h_bits;  // host copy (CLI / validation)
+};
+
+namespace mrp {
+
+// simple RAII device buffer for the host-pointer entry points
+struct DevBuf {
+  void* p = nullptr;
+  size_t bytes = 0;
+  ~DevBuf() {
+    if (p) cudaFree(p);
+  }
+  int alloc(size_t n) {
+    if (p) {
+      cudaFree(p);
+      p = nullptr;
+    }
+    bytes = n;
+    if (n == 0) return 0;
+    cudaError_t e = cudaMalloc(&p, n);
+    if (e != cudaSuccess)
+      return fail(MRP_ERR_NOMEM, "cudaMalloc(%zu) failed: %s", n,
+                  cudaGetErrorString(e));
+    return 0;
+  }
+  template <class T>
+  T* as() { return static_cast<T*>(p); }
+};
+
+// kernels launchers (defined in the .cu files)
+int launchBfsSmall(const uint32_t* d_rows, const int32_t* d_dims,
+                   const int4* d_jobs, int n_jobs, int32_t* d_out,
+                   cudaStream_t st);
+size_t bfsLargeWorkspaceBytes(const mrp_map_s* map, int n_goals);
+int launchBfsLarge(const mrp_map_s* map, const int32_t* d_goal_cell,
+                   int n_goals, int32_t* d_out, void* d_ws, cudaStream_t st);
+int launchConflicts(const int32_t* d_cell, const int32_t* d_len, int N,
+                    int Tpad, int mode, bool wantFirst, bool wantCount,
+                    unsigned long long* d_result, cudaStream_t st);
+int launchConflictsBatch(const int32_t* d_cell, const int32_t* d_len, int B,
+                         int N, int Tpad, int mode,
+                         unsigned long long* d_result, cudaStream_t st);
+int launchFocalCounts(const int32_t* d_cell, const int32_t* d_len, int N,
+                      int Tpad, int self, const int32_t* d_t,
+                      const int32_t* d_from, const int32_t* d_to, int n_cand,
+                      int32_t* d_state, int32_t* d_trans, cudaStream_t st);
+
+// packed first-conflict key: t<<41 | type<<40 | i<<20 | j   (min = first)
+__host__ __device__ inline unsigned long long conflictKey(int t, int type, int i,
+                                                         int j) {
+  return ((unsigned long long)t << 41) | ((unsigned long long)type << 40) |
+         ((unsigned long long)i << 20) | (unsigned long long)j;
+}
+constexpr unsigned long long kNoConflict = ~0ull;
+constexpr int kMaxAgents = 1 << 20;
+constexpr int kMaxTime = 1 << 22;
+
+}  // namespace mrp

@@ -1,0 +1,254 @@
+// conflicts.cu — vertex / edge-swap conflict detection and counting over packed
+// path tables cell[N][Tpad] (+ len[N]).
+//
+// Replaces, on the reference side,
+//   Environment::getFirstConflict   example/cbs.cpp:335-386 (bound size-1),
+//                                   example/cbs_ta.cpp:369-420 (bound size)
+//   Environment::focalHeuristic     example/ecbs.cpp:315-350
+//   Environment::focalStateHeuristic / focalTransitionHeuristic
+//                                   example/ecbs.cpp:282-312
+// with getState()'s clamp to the last state (example/cbs.cpp:420-429).
+//
+// all-pairs kernel: a CTA owns a 64x64 block of agent pairs (upper triangle
+// only) and a chunk of 64 timesteps.  Both 64-agent slabs of the table are
+// staged in shared memory ([agent][t], odd stride), every thread keeps a 4x4
+// register tile of pairs and walks the chunk in time, re-using the t+1 column
+// as the next t column.  Per pair-step: 1 vertex compare and 2 edge compares.
+// The first conflict is the minimum of the packed key (t, type, i, j) — the
+// exact iteration order of the reference loops — reduced with a 64-bit
+// atomicMin; counts are reduced per CTA and added with one atomic.
+#include "common.cuh"
+
+namespace mrp {
+
+constexpr int kPB = 64;        // agents per block side
+constexpr int kTC = 64;        // timesteps per chunk
+constexpr int kStride = kTC + 3;  // 67: odd => conflict-light column reads
+
+// result layout per table (4 x u64): [0] min key, [1] count, [2] max len, [3] -
+__global__ void conflict_prep_kernel(const int32_t* __restrict__ len, int N,
+                                     unsigned long long* __restrict__ result) {
+  const int b = blockIdx.x;
+  const int32_t* l = len + (size_t)b * N;
+  __shared__ int smax[32];
+  int m = 0;
+  for (int i = threadIdx.x; i < N; i += blockDim.x) m = max(m, l[i]);
+  for (int o = 16; o; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) smax[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    m = threadIdx.x < (blockDim.x >> 5) ? smax[threadIdx.x] : 0;
+    for (int o = 16; o; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if (threadIdx.x == 0) {
+      result[4 * b + 0] = kNoConflict;
+      result[4 * b + 1] = 0ull;
+      result[4 * b + 2] = (unsigned long long)m;
+      result[4 * b + 3] = 0ull;
+    }
+  }
+}
+
+template <bool kFirst, bool kCount>
+__global__ void __launch_bounds__(256)
+conflict_pairs_kernel(const int32_t* __restrict__ cellAll,
+                      const int32_t* __restrict__ lenAll, int N, int Tpad,
+                      int mode, int nb, unsigned long long* __restrict__ resultAll) {
+  __shared__ int32_t sA[kPB * kStride];
+  __shared__ int32_t sB[kPB * kStride];
+  __shared__ int sCount[8];
+
+  const int table = blockIdx.z;
+  const int32_t* cell = cellAll + (size_t)table * N * Tpad;
+  const int32_t* len = lenAll + (size_t)table * N;
+  unsigned long long* result = resultAll + 4 * (size_t)table;
+
+  const int maxLen = (int)result[2];
+  const int max_t = maxLen - (mode == 0 ? 1 : 0);
+  const int t0 = blockIdx.y * kTC;
+  if (t0 >= max_t) return;
+  if (kFirst && !kCount) {
+    // a conflict at an earlier chunk makes this chunk irrelevant
+    const unsigned long long best = *(volatile unsigned long long*)&result[0];
+    if (best != kNoConflict && (int)(best >> 41) < t0) return;
+  }
+  const int tEnd = min(t0 + kTC, max_t);  // timesteps [t0, tEnd)
+
+  // upper-triangular block index -> (bi, bj), bi <= bj
+  int bi = 0, rem = blockIdx.x;
+  while (rem >= nb - bi) {
+    rem -= nb - bi;
+    ++bi;
+  }
+  const int bj = bi + rem;
+
+  // stage positions t0 .. tEnd (inclusive: the edge test needs t+1)
+  const int nT = tEnd - t0 + 1;
+  for (int idx = threadIdx.x; idx < kPB * (kTC + 1); idx += blockDim.x) {
+    const int a = idx / (kTC + 1), k = idx - a * (kTC + 1);
+    if (k >= nT) continue;
+    const int t = t0 + k;
+    int ia = bi * kPB + a, ib = bj * kPB + a;
+    int va = -2 - a, vb = -2 - kPB - a;  // padding agents never match anything
+    if (ia < N) {
+      const int L = len[ia];
+      if (L > 0) va = cell[(size_t)ia * Tpad + min(t, L - 1)];
+    }
+    if (ib < N) {
+      const int L = len[ib];
+      if (L > 0) vb = cell[(size_t)ib * Tpad + min(t, L - 1)];
+    }
+    sA[a * kStride + k] = va;
+    sB[a * kStride + k] = vb;
+  }
+  __syncthreads();
+
+  const int ti = threadIdx.x >> 4, tj = threadIdx.x & 15;
+  const int i0 = bi * kPB + ti * 4, j0 = bj * kPB + tj * 4;
+  const int32_t* pa = sA + (ti * 4) * kStride;
+  const int32_t* pb = sB + (tj * 4) * kStride;
+
+  // pair (k,l) is live iff i < j (only matters on diagonal blocks) and in range
+  unsigned live = 0;
+#pragma unroll
+  for (int k = 0; k < 4; ++k)
+#pragma unroll
+    for (int l = 0; l < 4; ++l)
+      if (i0 + k < j0 + l && i0 + k < N && j0 + l < N) live |= 1u << (k * 4 + l);
+
+  int cnt = 0;
+  unsigned long long best = kNoConflict;
+  if (live) {
+    int a0[4], b0[4], a1[4], b1[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      a0[k] = pa[k * kStride];
+      b0[k] = pb[k * kStride];
+    }
+    for (int k = 0; k < tEnd - t0; ++k) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        a1[q] = pa[q * kStride + k + 1];
+        b1[q] = pb[q * kStride + k + 1];
+      }
+      unsigned vhit = 0, ehit = 0;
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+#pragma unroll
+        for (int l = 0; l < 4; ++l) {
+          const unsigned bit = 1u << (q * 4 + l);
+          if (a0[q] == b0[l]) vhit |= bit;
+          if (a0[q] == b1[l] && a1[q] == b0[l]) ehit |= bit;
+        }
+      vhit &= live;
+      ehit &= live;
+      if (kCount) cnt += __popc(vhit) + __popc(ehit);
+      if (kFirst && (vhit | ehit) && best == kNoConflict) {
+        // first hit of this thread in time; vertex before edge, then (i, j)
+        const unsigned hit = vhit ? vhit : ehit;
+        const int p = __ffs(hit) - 1;  // bit order q*4+l == (i, j) ascending
+        best = conflictKey(t0 + k, vhit ? 0 : 1, i0 + (p >> 2), j0 + (p & 3));
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        a0[q] = a1[q];
+        b0[q] = b1[q];
+      }
+    }
+  }
+  if (kFirst && best != kNoConflict) atomicMin(&result[0], best);
+  if (kCount) {
+    for (int o = 16; o; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    if ((threadIdx.x & 31) == 0) sCount[threadIdx.x >> 5] = cnt;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      int tot = 0;
+      for (int w = 0; w < 8; ++w) tot += sCount[w];
+      if (tot) atomicAdd(&result[1], (unsigned long long)tot);
+    }
+  }
+}
+
+// focal counts: one warp per candidate move, lanes stride over the agents
+__global__ void focal_counts_kernel(const int32_t* __restrict__ cell,
+                                    const int32_t* __restrict__ len, int N,
+                                    int Tpad, int self,
+                                    const int32_t* __restrict__ ct,
+                                    const int32_t* __restrict__ cfrom,
+                                    const int32_t* __restrict__ cto, int n_cand,
+                                    int32_t* __restrict__ stateCnt,
+                                    int32_t* __restrict__ transCnt) {
+  const int k = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (k >= n_cand) return;
+  const int t = ct[k], from = cfrom[k], to = cto[k];
+  int s = 0, tr = 0;
+  for (int i = lane; i < N; i += 32) {
+    const int L = len[i];
+    if (i == self || L <= 0) continue;
+    const int pa = cell[(size_t)i * Tpad + min(t, L - 1)];
+    const int pb = cell[(size_t)i * Tpad + min(t + 1, L - 1)];
+    s += (pb == to);
+    tr += (from == pb && to == pa);
+  }
+  for (int o = 16; o; o >>= 1) {
+    s += __shfl_xor_sync(0xffffffffu, s, o);
+    tr += __shfl_xor_sync(0xffffffffu, tr, o);
+  }
+  if (lane == 0) {
+    stateCnt[k] = s;
+    transCnt[k] = tr;
+  }
+}
+
+static int launchPairs(const int32_t* d_cell, const int32_t* d_len, int B, int N,
+                       int Tpad, int mode, bool wantFirst, bool wantCount,
+                       unsigned long long* d_result, cudaStream_t st) {
+  conflict_prep_kernel<<<B, 256, 0, st>>>(d_len, N, d_result);
+  countLaunch();
+  const int nb = (N + kPB - 1) / kPB;
+  const int nPairBlocks = nb * (nb + 1) / 2;
+  const int chunks = (Tpad + kTC - 1) / kTC;
+  dim3 grid(nPairBlocks, chunks, B);
+  if (wantFirst && wantCount)
+    conflict_pairs_kernel<true, true><<<grid, 256, 0, st>>>(d_cell, d_len, N, Tpad,
+                                                            mode, nb, d_result);
+  else if (wantFirst)
+    conflict_pairs_kernel<true, false><<<grid, 256, 0, st>>>(d_cell, d_len, N, Tpad,
+                                                             mode, nb, d_result);
+  else
+    conflict_pairs_kernel<false, true><<<grid, 256, 0, st>>>(d_cell, d_len, N, Tpad,
+                                                             mode, nb, d_result);
+  countLaunch();
+  MRP_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int launchConflicts(const int32_t* d_cell, const int32_t* d_len, int N, int Tpad,
+                    int mode, bool wantFirst, bool wantCount,
+                    unsigned long long* d_result, cudaStream_t st) {
+  return launchPairs(d_cell, d_len, 1, N, Tpad, mode, wantFirst, wantCount,
+                     d_result, st);
+}
+
+int launchConflictsBatch(const int32_t* d_cell, const int32_t* d_len, int B,
+                         int N, int Tpad, int mode,
+                         unsigned long long* d_result, cudaStream_t st) {
+  return launchPairs(d_cell, d_len, B, N, Tpad, mode, true, true, d_result, st);
+}
+
+int launchFocalCounts(const int32_t* d_cell, const int32_t* d_len, int N,
+                      int Tpad, int self, const int32_t* d_t,
+                      const int32_t* d_from, const int32_t* d_to, int n_cand,
+                      int32_t* d_state, int32_t* d_trans, cudaStream_t st) {
+  if (n_cand <= 0) return 0;
+  const int threads = 256;
+  const int blocks = (n_cand * 32 + threads - 1) / threads;
+  focal_counts_kernel<<<blocks, threads, 0, st>>>(d_cell, d_len, N, Tpad, self,
+                                                  d_t, d_from, d_to, n_cand,
+                                                  d_state, d_trans);
+  countLaunch();
+  MRP_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace mrp

@@ -1,0 +1,133 @@
+"""GPU parity: distance fields through the C ABI vs the CPU oracle (bit-exact)."""
+import zlib
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _rand_map(rng, dimx, dimy, density):
+    blocked = rng.random((dimy, dimx)) < density
+    ys, xs = np.nonzero(blocked)
+    return np.stack([xs, ys], 1).astype(np.int32)
+
+
+def test_anchor_field(capi, set32):
+    inst = next(i for i in set32 if i.name == "map_32by32_obst204_agents10_ex1")
+    f = capi.bfs_fields(32, 32, inst.obstacles, inst.goals)
+    assert zlib.crc32(f[0].astype("<i4").tobytes()) == 0x2C73F098
+
+
+def test_all_benchmark_instances_batch(capi, orc, set8, set32):
+    for sset in (set8, set32):
+        got = capi.bfs_fields_batch(sset)
+        for inst, g in zip(sset, got):
+            want = orc.bfs_fields(inst.dimx, inst.dimy, inst.obstacles, inst.goals)
+            assert np.array_equal(g, want), inst.name
+
+
+def test_golden_crcs(capi, set8, set32, oracle_golden):
+    by = {i.name: i for i in set8 + set32}
+    for name, g in oracle_golden["bfs_fields"].items():
+        i = by[name]
+        f = capi.bfs_fields(i.dimx, i.dimy, i.obstacles, i.goals)
+        assert zlib.crc32(np.ascontiguousarray(f, "<i4").tobytes()) == g["crc32"], name
+
+
+@pytest.mark.parametrize("dimx,dimy,density", [
+    (1, 1, 0.0), (1, 7, 0.0), (9, 1, 0.2), (5, 2, 0.3), (8, 8, 0.2), (31, 17, 0.25),
+    (32, 32, 0.2), (33, 32, 0.2), (32, 33, 0.2), (40, 50, 0.3), (64, 64, 0.2),
+    (100, 37, 0.35), (129, 65, 0.2), (257, 300, 0.25), (1100, 70, 0.2),
+    (70, 1100, 0.2)])
+def test_random_maps(capi, orc, dimx, dimy, density):
+    rng = np.random.default_rng(dimx * 1000 + dimy)
+    obst = _rand_map(rng, dimx, dimy, density)
+    n = min(dimx * dimy, 12)
+    cells = rng.choice(dimx * dimy, n, replace=False)
+    goals = np.stack([cells % dimx, cells // dimx], 1)  # may sit on obstacles
+    got = capi.bfs_fields(dimx, dimy, obst, goals)
+    want = orc.bfs_fields(dimx, dimy, obst, goals)
+    assert np.array_equal(got, want)
+
+
+def test_empty_and_errors(capi):
+    assert capi.bfs_fields(8, 8, [], np.zeros((0, 2))).shape == (0, 64)
+    with pytest.raises(capi.MrpError):
+        capi.bfs_fields(8, 8, [], [[8, 0]])
+    with pytest.raises(capi.MrpError):
+        capi.bfs_fields(0, 8, [], [[0, 0]])
+    # obstacles outside the map are ignored like in the reference
+    f = capi.bfs_fields(3, 1, [[5, 5], [-1, 0]], [[0, 0]])
+    assert list(f[0]) == [0, 1, 2]
+
+
+def test_maze_deep(capi, orc):
+    # serpentine corridor: BFS depth ~ cells/2, exercises long wavefronts
+    dimx, dimy = 96, 67
+    obst = []
+    for y in range(1, dimy, 2):
+        gap = dimx - 1 if (y // 2) % 2 == 0 else 0
+        obst += [[x, y] for x in range(dimx) if x != gap]
+    goals = [[0, 0], [dimx - 1, dimy - 1], [40, 20]]
+    got = capi.bfs_fields(dimx, dimy, obst, goals)
+    want = orc.bfs_fields(dimx, dimy, obst, goals)
+    assert np.array_equal(got, want)
+    assert got[0][got[0] != capi.INF].max() > 2000
+
+
+def test_c5_map_sample(capi, orc):
+    from libmultirobotplanning_b200 import instances
+    inst = instances.synthetic_c5()
+    assert len(inst.obstacles) == 209448
+    goals = inst.goals[:6]
+    got = capi.bfs_fields(1024, 1024, inst.obstacles, goals)
+    want = orc.bfs_fields(1024, 1024, inst.obstacles, goals)
+    assert np.array_equal(got, want)
+
+
+def test_c5_properties_many_goals(capi):
+    """Full-size properties that need no oracle: 0 exactly at the goal, MRP_INF
+    exactly on obstacles/other components, neighbouring free cells differ by
+    exactly 1 (bipartite grid), symmetry d(a,b) == d(b,a)."""
+    from libmultirobotplanning_b200 import instances
+    inst = instances.synthetic_c5()
+    G = 300
+    goals = inst.goals[:G]
+    f = capi.bfs_fields(1024, 1024, inst.obstacles, goals).reshape(G, 1024, 1024)
+    free = np.ones((1024, 1024), bool)
+    free[inst.obstacles[:, 1], inst.obstacles[:, 0]] = False
+    reach = f[0] != capi.INF
+    assert reach.sum() == 837416
+    for g in range(G):
+        fg = f[g]
+        assert fg[goals[g, 1], goals[g, 0]] == 0
+        assert ((fg != capi.INF) == reach).all()
+        assert (fg == 0).sum() == 1
+    for g in range(0, G, 37):
+        fg = f[g].astype(np.int64)
+        both = reach[:, 1:] & reach[:, :-1]
+        assert (np.abs(fg[:, 1:] - fg[:, :-1])[both] == 1).all()
+        both = reach[1:, :] & reach[:-1, :]
+        assert (np.abs(fg[1:, :] - fg[:-1, :])[both] == 1).all()
+    for a in range(0, 40, 7):
+        for b in range(1, 40, 11):
+            assert f[a][goals[b, 1], goals[b, 0]] == f[b][goals[a, 1], goals[a, 0]]
+
+
+def test_device_entry_point(capi, orc):
+    import torch
+    dimx, dimy = 200, 150
+    rng = np.random.default_rng(5)
+    obst = _rand_map(rng, dimx, dimy, 0.2)
+    cells = rng.choice(dimx * dimy, 40, replace=False).astype(np.int32)
+    m = capi.Map(dimx, dimy, obst)
+    d_goals = torch.from_numpy(cells).cuda()
+    d_out = torch.empty((40, dimx * dimy), dtype=torch.int32, device="cuda")
+    ws = torch.empty(max(m.workspace_bytes(40), 256), dtype=torch.uint8, device="cuda")
+    s = torch.cuda.current_stream()
+    m.bfs_fields_dev(d_goals.data_ptr(), 40, d_out.data_ptr(), ws.data_ptr(), s.cuda_stream)
+    s.synchronize()
+    goals = np.stack([cells % dimx, cells // dimx], 1)
+    assert np.array_equal(d_out.cpu().numpy(), orc.bfs_fields(dimx, dimy, obst, goals))
+    m.close()

@@ -1,0 +1,218 @@
+"""CPU tests: the oracle against the reference's own known answers
+(test/test_cbs.py:24-34, test_ecbs.py:25-35, test_cbs_ta.py:24-38,
+test_assignment.py:19-63, test_next_best_assignment.py:19-110 of the reference)
+and against the implementation-independent anchors of BASELINE.md."""
+import re
+import zlib
+
+import numpy as np
+import pytest
+
+CAPS = (20000, 2_000_000, 30.0)
+
+
+def test_cbs_ecbs_fixture_costs(orc, ref_fixtures):
+    for name, d in ref_fixtures.items():
+        exp = d["expected"]
+        if "cbs_cost" not in exp:
+            continue
+        r = orc.cbs(d["dimx"], d["dimy"], d["obstacles"], d["starts"], d["goals"], CAPS)
+        assert r["status"] == orc.SOLVED and r["cost"] == exp["cbs_cost"], name
+        r = orc.ecbs(d["dimx"], d["dimy"], d["obstacles"], d["starts"], d["goals"],
+                     1.0, CAPS)
+        assert r["status"] == orc.SOLVED and r["cost"] == exp["ecbs_w1_cost"], name
+
+
+def test_cbs_ta_fixtures(orc, ref_fixtures):
+    for name, d in ref_fixtures.items():
+        exp = d["expected"]
+        if "cbs_ta_cost" not in exp:
+            continue
+        r = orc.cbs_ta(d["dimx"], d["dimy"], d["obstacles"], d["starts"],
+                       d["potentialGoals"], caps=CAPS)
+        assert r["status"] == orc.SOLVED and r["cost"] == exp["cbs_ta_cost"], name
+        if "agent0_last" in exp:
+            x, y, t = r["paths"][0][-1]
+            assert {"x": x, "y": y, "t": t} == exp["agent0_last"], name
+        if "agent1_last_xy" in exp:
+            assert list(r["paths"][1][-1][:2]) == exp["agent1_last_xy"], name
+
+
+def test_extra_cbs_anchors(orc, ref_fixtures):
+    # swap2 12/6, swap4 28/8 (edge conflicts)
+    for name, cost, makespan in (("mapf_swap2", 12, 6), ("mapf_swap4", 28, 8)):
+        d = ref_fixtures[name]
+        r = orc.cbs(d["dimx"], d["dimy"], d["obstacles"], d["starts"], d["goals"], CAPS)
+        assert (r["cost"], r["makespan"]) == (cost, makespan)
+
+
+def test_assignment_vectors(orc):
+    assert orc.assignment([], 0, 0)[0] == 0
+    c, s = orc.assignment([[0, 0, 2], [0, 1, 1]], 1, 2)
+    assert c == 1 and s[0] == 1
+    c, s = orc.assignment([[0, 0, 2], [1, 0, 1]], 2, 1)
+    assert c == 1 and list(s) == [-1, 0]
+    M = [[90, 76, 75, 80], [35, 85, 55, 65], [125, 95, 90, 105], [45, 110, 95, 115]]
+    E = [[i, j, M[i][j]] for i in range(4) for j in range(4)]
+    c, s = orc.assignment(E, 4, 4)
+    assert c == 275 and list(s) == [3, 2, 1, 0]
+
+
+def test_next_best_assignment_vectors(orc):
+    c, s = orc.next_best_assignments([], 0, 0)
+    assert len(c) == 0
+    c, s = orc.next_best_assignments([[0, 0, 2], [0, 1, 1]], 1, 2)
+    assert list(c) == [1, 2] and s[0][0] == 1 and s[1][0] == 0
+    c, s = orc.next_best_assignments([[0, 0, 2], [1, 0, 1]], 2, 1)
+    assert list(c) == [1, 2] and list(s[0]) == [-1, 0] and list(s[1]) == [0, -1]
+    c, s = orc.next_best_assignments([[0, 0, 90], [0, 1, 76], [1, 0, 35], [1, 1, 85]], 2, 2)
+    assert list(c) == [111, 175] and list(s[0]) == [1, 0] and list(s[1]) == [0, 1]
+    M = [[90, 76, 75, 80], [35, 85, 55, 65], [125, 95, 90, 105], [45, 110, 95, 115]]
+    E = [[i, j, M[i][j]] for i in range(4) for j in range(4)]
+    c, s = orc.next_best_assignments(E, 4, 4)
+    assert len(c) == 24 and c[0] == 275 and c[-1] == 400
+    assert list(s[0]) == [3, 2, 1, 0] and list(s[-1]) == [2, 1, 0, 3]
+    assert all(c[k] <= c[k + 1] for k in range(len(c) - 1))
+    assert len({tuple(r) for r in s}) == 24
+
+
+def test_floyd_warshall_equals_bfs(orc, set8, set32):
+    # the reference algorithm (FW, shortest_path_heuristic.hpp:47-53) and the
+    # per-goal BFS (cbs.cpp:445-557) must agree on every goal row
+    for inst in set8[::211] + set32[::499]:
+        fw = orc.floyd_warshall(inst.dimx, inst.dimy, inst.obstacles)
+        bf = orc.bfs_fields(inst.dimx, inst.dimy, inst.obstacles, inst.goals)
+        cells = inst.cell(inst.goals)
+        assert np.array_equal(fw[cells], bf), inst.name
+        assert np.array_equal(fw, fw.T)
+    # a goal on an obstacle: FW row of an isolated vertex
+    fw = orc.floyd_warshall(4, 3, [[1, 1]])
+    bf = orc.bfs_fields(4, 3, [[1, 1]], [[1, 1]])
+    assert np.array_equal(fw[1 + 4 * 1], bf[0])
+    assert bf[0][5] == 0 and (np.delete(bf[0], 5) == orc.INF).all()
+
+
+def test_field_anchor_crc(orc, set32):
+    inst = next(i for i in set32 if i.name == "map_32by32_obst204_agents10_ex1")
+    f = orc.bfs_fields(32, 32, inst.obstacles, inst.goals)
+    assert tuple(inst.goals[0]) == (29, 10)
+    assert zlib.crc32(f[0].astype("<i4").tobytes()) == 0x2C73F098
+    fin = f[0][f[0] != orc.INF]
+    assert (len(fin), fin.max(), fin.sum()) == (815, 50, 19746)
+    per_agent = [int(f[k][inst.cell(inst.starts[k])]) for k in range(10)]
+    assert per_agent == [15, 34, 24, 30, 44, 20, 15, 14, 31, 9]
+
+
+def test_cbs_anchor_sums(orc, set8, set32, oracle_golden):
+    sums = {}
+    for inst in set8:
+        n = inst.n_agents
+        if n > 3:
+            continue
+        r = orc.cbs(inst.dimx, inst.dimy, inst.obstacles, inst.starts, inst.goals, CAPS)
+        assert r["status"] == orc.SOLVED
+        sums[n] = sums.get(n, 0) + r["cost"]
+        g = oracle_golden["cbs"][inst.name]
+        assert (g["cost"], g["makespan"]) == (r["cost"], r["makespan"])
+    assert sums == {1: 599, 2: 1167, 3: 1765}
+    by = {i.name: i for i in set32}
+    for name, cost, mk in (("map_32by32_obst204_agents10_ex1", 236, 44),
+                           ("map_32by32_obst204_agents10_ex0", 252, 37)):
+        i = by[name]
+        r = orc.cbs(32, 32, i.obstacles, i.starts, i.goals, CAPS)
+        assert (r["cost"], r["makespan"]) == (cost, mk)
+
+
+def test_golden_sums(oracle_golden):
+    sums = {}
+    for name, r in oracle_golden["cbs"].items():
+        m = re.match(r"map_8by8_obst12_agents(\d+)_ex", name)
+        if m and int(m.group(1)) <= 5:
+            assert r["status"] == 0
+            sums[int(m.group(1))] = sums.get(int(m.group(1)), 0) + r["cost"]
+    assert sums == {1: 599, 2: 1167, 3: 1765, 4: 2418, 5: 2979}
+
+
+def test_ecbs_within_bound(orc, set32):
+    by = {i.name: i for i in set32}
+    i = by["map_32by32_obst204_agents10_ex1"]
+    r = orc.ecbs(32, 32, i.obstacles, i.starts, i.goals, 1.3, CAPS)
+    assert r["status"] == orc.SOLVED and 236 <= r["cost"] <= 306
+    assert r["cost"] <= 1.3 * r["lower_bound"] + 1e-6
+
+
+def _table(paths):
+    T = max(len(p) for p in paths)
+    cell = np.zeros((len(paths), T), np.int32)
+    ln = np.array([len(p) for p in paths], np.int32)
+    for k, p in enumerate(paths):
+        cell[k, :len(p)] = p
+        cell[k, len(p):] = -7  # padding must never be read
+    return cell, ln
+
+
+def test_conflict_semantics(orc):
+    # vertex before edge at the same t; smallest (i, j) first (cbs.cpp:343-383)
+    cell, ln = _table([[0, 1, 2], [5, 1, 9], [7, 1, 8]])
+    assert orc.first_conflict(cell, ln, 10, 0) == (1, 0, 1, 0, 1, 0, -1, -1)
+    assert orc.count_conflicts(cell, ln) == 3
+    # swap: agent0 0->1, agent1 1->0
+    cell, ln = _table([[0, 1], [1, 0]])
+    assert orc.first_conflict(cell, ln, 10, 0) == (0, 0, 1, 1, 0, 0, 1, 0)
+    assert orc.count_conflicts(cell, ln) == 1
+    # mode 0 never tests the final timestep, mode 1 does (cbs_ta.cpp:372-375)
+    cell, ln = _table([[0, 4], [1, 4]])
+    assert orc.first_conflict(cell, ln, 10, 0) is None
+    assert orc.first_conflict(cell, ln, 10, 1) == (1, 0, 1, 0, 4, 0, -1, -1)
+    # clamp to the last state (cbs.cpp:420-429): agent1 parks on 3
+    cell, ln = _table([[0, 1, 2, 3], [3]])
+    assert orc.first_conflict(cell, ln, 10, 0) is None
+    assert orc.first_conflict(cell, ln, 10, 1) == (3, 0, 1, 0, 3, 0, -1, -1)
+    cell, ln = _table([[0, 1, 2, 3, 4], [3]])
+    assert orc.first_conflict(cell, ln, 10, 0) == (3, 0, 1, 0, 3, 0, -1, -1)
+    # two agents resting on one cell count as a vertex AND an "edge" conflict
+    cell, ln = _table([[2, 2, 2], [2, 2, 2]])
+    assert orc.count_conflicts(cell, ln) == 4
+
+
+def test_focal_counts(orc):
+    cell, ln = _table([[0, 1, 2], [5, 1, 9], [2, 1, 0], []])
+    s, tr = orc.focal_counts(cell, ln, 0, [0, 1], [0, 1], [1, 2])
+    # candidate 0: arrive at cell 1 at t=1 -> agents 1 and 2 are there
+    assert list(s) == [2, 0]
+    s, tr = orc.focal_counts(cell, ln, 1, [0], [1], [2])
+    # move 1->2 at t=0: agent 2 moves 2->1: swap
+    assert list(tr) == [1]
+
+
+def test_fp32_focal_bound_vectors():
+    # a_star_epsilon.hpp:240 evaluates `f <= best * w` with w stored as float
+    w = np.float32(1.3)
+
+    def bound(best):
+        lim = np.float32(best) * w
+        f = int(best * 1.3) + 2
+        while not np.float32(f) <= lim:
+            f -= 1
+        return f
+
+    assert [bound(b) for b in (90, 170, 180, 190, 236)] == [116, 220, 233, 246, 306]
+
+
+def test_lowlevel_oracle_constraints(orc):
+    # 5x1 corridor, start 0 goal 4: plain cost 4; a vertex constraint on the
+    # goal at t=4 forces arrival at t>=5 (isSolution needs time > last goal
+    # constraint, cbs.cpp:286-289)
+    r = orc.lowlevel(5, 1, [], 0, 0, 4)
+    assert r["status"] == 0 and r["cost"] == 4 and len(r["path"]) == 5
+    r = orc.lowlevel(5, 1, [], 0, 0, 4, vc=[[4, 4]])
+    assert r["cost"] == 5
+    r = orc.lowlevel(5, 1, [], 0, 0, 4, vc=[[9, 4]])
+    assert r["cost"] == 10
+    # edge constraint on the first move (departure time 0)
+    r = orc.lowlevel(5, 1, [], 0, 0, 4, ec=[[0, 0, 1]])
+    assert r["cost"] == 5
+    # cbs_ta: waiting on the goal is free (cbs_ta.cpp:329-339)
+    r = orc.lowlevel(5, 1, [], 1, 0, 4, vc=[[9, 4]])
+    # reach the goal (4), rest for free until t=8, step off at t=9 and back
+    assert r["cost"] == 6
