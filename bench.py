@@ -1,0 +1,395 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the B200 hot path.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+Headline metric (BASELINE.json): BFS heuristic cells/s on config C5 — the
+synthetic 1024x1024 grid with 20 % obstacles and 4096 goals;
+one "step" = one pass of the distance-field kernel over all goals of the rank
+(4096 fields = 17.2 GB of int32 per GPU).  The JSON line also carries the
+conflict pair-steps/s of the same config (`also`), the HBM roofline of the
+dominant kernel, the CPU baseline (oracle port on the host cores) and the
+end-to-end number through the host-pointer C-ABI call.
+
+Multi-GPU: one process per GPU (torchrun); goals are sharded by rank, no
+data-path collective (weak scaling: 4096 goals per GPU); the optional NCCL
+all-gather that makes every field resident on every GPU is timed separately
+(`also.allgather_*`).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+DIM = 1024
+GOALS_PER_GPU = 4096
+E2E_GOALS = 1024
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows = []
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q,
+                 "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), line.strip()))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ts, line in self.rows:
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                mx = float(f[1])
+                if t0 - 0.05 <= ts <= t1 + 0.15:
+                    sm.append(float(f[0]))
+                    for n, v in zip(names, f[3:7]):
+                        if v.lower().startswith("active"):
+                            reasons.add(n)
+            except ValueError:
+                continue
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def c5_instance(n_ranks):
+    from libmultirobotplanning_b200 import instances
+    return instances.synthetic_c5(dim=DIM, n_agents=GOALS_PER_GPU * n_ranks)
+
+
+def cpu_bfs_rate(inst, goals, threads):
+    """Oracle BFS on the host cores (the checker, here as the CPU baseline)."""
+    from concurrent.futures import ThreadPoolExecutor
+    from oracle import orc
+    orc.build()
+    orc.bfs_fields(inst.dimx, inst.dimy, inst.obstacles, goals[:1])  # warm
+    chunks = [goals[i::threads] for i in range(threads) if len(goals[i::threads])]
+    t0 = time.perf_counter()
+    if threads == 1:
+        orc.bfs_fields(inst.dimx, inst.dimy, inst.obstacles, goals)
+    else:
+        with ThreadPoolExecutor(threads) as ex:  # ctypes releases the GIL
+            list(ex.map(lambda g: orc.bfs_fields(inst.dimx, inst.dimy, inst.obstacles, g),
+                        chunks))
+    dt = time.perf_counter() - t0
+    return len(goals) * inst.dimx * inst.dimy / dt, dt
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU path for this metric.  The
+    reference itself cannot be built here (Boost / yaml-cpp absent) and its own
+    algorithm (Floyd–Warshall over all V = 2^20 cells) is infeasible at this
+    size, so the timed code is the oracle's per-goal queue BFS (identical
+    output), on all host cores."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    inst = c5_instance(1)
+    per_step = max(cores * 2, 8)
+    goals = inst.goals[:per_step]
+    for _ in range(min(args.warmup, 1)):
+        cpu_bfs_rate(inst, goals[:cores], cores)
+    rates, times = [], []
+    for _ in range(args.steps):
+        r, dt = cpu_bfs_rate(inst, goals, cores)
+        rates.append(r)
+        times.append(dt)
+    value = per_step * DIM * DIM * len(times) / sum(times)
+    line = {
+        "impl": "reference", "metric": "BFS heuristic cells/s", "value": value,
+        "unit": "cells/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * sum(times) / len(times), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
+        "config": {"workload": "C5 synthetic 1024x1024, 20% obstacles, distance fields by goal",
+                   "dim": DIM, "goals_per_step": per_step},
+        "cpu_baseline": {"value": value, "unit": "cells/s", "cores": cores, "kind": "port",
+                         "sample": "%d goals per step, oracle queue BFS, one thread per core"
+                                   % per_step},
+        "e2e": {"value": value, "unit": "cells/s", "h2d_bytes_per_step": 0,
+                "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+def descend_paths(torch, fields, inst, starts_cell, n_agents, max_t):
+    """Steepest descent on each agent's goal field with neighbour preference
+    Left, Right, Up, Down: the path table of the conflict
+    sweep.  fields: device int32 [G][cells], agent i follows field i."""
+    dev = fields.device
+    cur = torch.as_tensor(starts_cell[:n_agents], device=dev, dtype=torch.int64)
+    idx = torch.arange(n_agents, device=dev)
+    dist0 = fields[idx, cur].to(torch.int64)
+    T = int(dist0.max().item()) + 1
+    T = min(T, max_t)
+    table = torch.empty((n_agents, T), dtype=torch.int32, device=dev)
+    length = (dist0 + 1).clamp(max=T).to(torch.int32)
+    x = cur % DIM
+    y = cur // DIM
+    big = torch.iinfo(torch.int32).max
+    for t in range(T):
+        table[:, t] = cur.to(torch.int32)
+        d = fields[idx, cur]
+        nxt = cur.clone()
+        done = d == 0
+        for dx, dy in ((-1, 0), (1, 0), (0, 1), (0, -1))[::-1]:
+            nx, ny = x + dx, y + dy
+            ok = (nx >= 0) & (nx < DIM) & (ny >= 0) & (ny < DIM)
+            nc = (nx.clamp(0, DIM - 1) + DIM * ny.clamp(0, DIM - 1))
+            nd = torch.where(ok, fields[idx, nc], torch.full_like(d, big))
+            take = (nd == d - 1) & ~done
+            nxt = torch.where(take, nc, nxt)
+        cur = nxt
+        x = cur % DIM
+        y = cur // DIM
+    return table.contiguous(), length.contiguous()
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    import libmultirobotplanning_b200 as pkg
+    capi = pkg.capi
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    else:
+        torch.cuda.set_device(0)
+    dev = torch.device("cuda", local if world > 1 else 0)
+    capi.init(dev.index)
+
+    inst = c5_instance(world)
+    cells = DIM * DIM
+    G = GOALS_PER_GPU
+    goals_xy = inst.goals[rank * G:(rank + 1) * G]
+    goal_cells = (goals_xy[:, 0] + DIM * goals_xy[:, 1]).astype(np.int32)
+    mp = capi.Map(DIM, DIM, inst.obstacles)
+    d_goals = torch.from_numpy(goal_cells).to(dev)
+    d_out = torch.empty((G, cells), dtype=torch.int32, device=dev)
+    d_ws = torch.empty(max(mp.workspace_bytes(G), 256), dtype=torch.uint8, device=dev)
+    stream = torch.cuda.current_stream()
+
+    def step():
+        mp.bfs_fields_dev(d_goals.data_ptr(), G, d_out.data_ptr(), d_ws.data_ptr(),
+                          stream.cuda_stream)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    sampler = ClockSampler(dev.index)
+    launches0 = capi.launch_count()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    barrier()
+    t0 = time.time()
+    ev[0].record(stream)
+    for k in range(args.steps):
+        step()
+        ev[k + 1].record(stream)
+    barrier()
+    t1 = time.time()
+    launches = capi.launch_count() - launches0
+    clocks = sampler.stop(t0, t1)
+    total_ms = ev[0].elapsed_time(ev[-1])
+    step_ms = [ev[k].elapsed_time(ev[k + 1]) for k in range(args.steps)]
+    t = torch.tensor([total_ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms_max = float(t.item())
+    ms_per_step = total_ms_max / args.steps
+    value = world * G * cells / (ms_per_step * 1e-3)
+
+    # ---- roofline of the dominant kernel (bfs_large_kernel) -------------------
+    peak, peak_src = measured_peaks()
+    alg_bytes = G * cells * 4 + cells // 8       # 4 B per (goal, cell) + bitmap
+    kern_ms = float(np.mean(step_ms))            # one launch per step
+    achieved = alg_bytes / (kern_ms * 1e-3) / 1e9
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tp):
+        with open(tp) as f:
+            tj = json.load(f)
+        # dram bytes per launch measured by ncu at tj["goals"] goals, scaled per goal
+        traffic = tj["dram_bytes_per_goal"] * G
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                "kernel": "bfs_large_kernel<true>", "algorithmic_bytes_per_launch": alg_bytes,
+                "kernel_ms": kern_ms}
+
+    # ---- also: conflict sweep of C5 (N = 4096 agents on their goal fields) ----
+    also = {}
+    if rank == 0 and not args.skip_conflicts:
+        starts_cell = (inst.starts[:, 0] + DIM * inst.starts[:, 1]).astype(np.int64)
+        N = G
+        table, length = descend_paths(torch, d_out, inst, starts_cell[rank * G:], N, 4096)
+        Tpad = table.shape[1]
+        d_res = torch.zeros(4, dtype=torch.int64, device=dev)
+        lib = capi.lib()
+
+        def cstep():
+            capi.check(lib.mrp_conflicts_dev(table.data_ptr(), length.data_ptr(), N, Tpad,
+                                             0, 1, 1, d_res.data_ptr(), stream.cuda_stream))
+        for _ in range(3):
+            cstep()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = 5
+        e0.record(stream)
+        for _ in range(reps):
+            cstep()
+        e1.record(stream)
+        torch.cuda.synchronize()
+        cms = e0.elapsed_time(e1) / reps
+        max_t = int(length.max().item()) - 1
+        pair_steps = N * (N - 1) // 2 * max_t
+        res = d_res.cpu().numpy()
+        also.update({
+            "conflict_pair_steps_per_s": pair_steps / (cms * 1e-3),
+            "conflict_ms": cms, "conflict_agents": N, "conflict_max_t": max_t,
+            "conflict_count": int(res[1]),
+            "conflict_first_key": int(np.uint64(res[0])) if res[0] != -1 else None,
+            "conflict_table_gbps": N * Tpad * 4 / (cms * 1e-3) / 1e9,
+        })
+        del table, length
+
+    # ---- optional all-gather of the fields over NVLink (north_star) -----------
+    if world > 1 and args.allgather:
+        Gg = 256  # fields per rank in the gathered sample
+        gathered = torch.empty((world * Gg, cells), dtype=torch.int32, device=dev)
+        for _ in range(2):
+            dist.all_gather_into_tensor(gathered, d_out[:Gg])
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        dist.all_gather_into_tensor(gathered, d_out[:Gg])
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        also["allgather_ms_per_%d_fields_per_rank" % Gg] = ms
+        also["allgather_gbps_in_per_gpu"] = (world - 1) * Gg * cells * 4 / (ms * 1e-3) / 1e9
+        del gathered
+
+    # ---- e2e: host buffers through the C-ABI call (H2D + kernel + D2H) -------
+    del d_out
+    torch.cuda.empty_cache()
+    Ge = min(E2E_GOALS, G)
+    h_out = torch.empty((Ge, cells), dtype=torch.int32).pin_memory()
+    h_np = h_out.numpy()
+    obst = np.ascontiguousarray(inst.obstacles, np.int32)
+    gxy = np.ascontiguousarray(goals_xy[:Ge], np.int32)
+    capi.bfs_fields(DIM, DIM, obst, gxy, out=h_np)  # warm (allocates scratch)
+    barrier()
+    te0 = time.perf_counter()
+    e2e_steps = max(1, min(args.steps, 3))
+    for _ in range(e2e_steps):
+        capi.bfs_fields(DIM, DIM, obst, gxy, out=h_np)
+    torch.cuda.synchronize()
+    te = (time.perf_counter() - te0) / e2e_steps
+    t = torch.tensor([te], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    te = float(t.item())
+    e2e = {"value": world * Ge * cells / te, "unit": "cells/s",
+           "h2d_bytes_per_step": int(obst.nbytes + gxy.nbytes),
+           "d2h_bytes_per_step": int(Ge * cells * 4), "goals_per_step": Ge,
+           "ms_per_step": te * 1e3,
+           "api": "mrp_bfs_fields (host pointers, pinned output)"}
+    # spot-check the e2e output against the oracle (checker only, 2 goals)
+    if rank == 0:
+        from oracle import orc
+        want = orc.bfs_fields(DIM, DIM, inst.obstacles, gxy[:2])
+        assert np.array_equal(h_np[:2], want), "e2e output differs from the oracle"
+
+    # ---- CPU baseline: oracle port, one core, bounded sample -------------------
+    cpu = None
+    if rank == 0:
+        sample = 16
+        r, dt = cpu_bfs_rate(inst, inst.goals[:sample], 1)
+        cpu = {"value": r, "unit": "cells/s", "cores": 1, "kind": "port",
+               "sample": "%d goals of the same map, oracle queue BFS (the reference's "
+                         "Floyd-Warshall is infeasible at V=2^20), %.1f s" % (sample, dt)}
+
+    if rank == 0:
+        line = {
+            "metric": "BFS heuristic cells/s", "value": value, "unit": "cells/s",
+            "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "int32", "data": "synthetic",
+            "config": {"workload": "C5 synthetic 1024x1024 grid, 20% obstacles, "
+                                   "4096 goals per GPU: one BFS distance field per goal",
+                       "dim": DIM, "goals_per_gpu": G, "obstacles": int(len(inst.obstacles)),
+                       "l2": "no flush: each step writes 17.2 GB >> 126 MB L2; the 128 KB "
+                             "map bitmap is cache-resident by design"},
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks,
+            "gpu_launches": int(launches), "also": also,
+            "device": capi.device_info(),
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--skip-conflicts", action="store_true")
+    ap.add_argument("--allgather", action="store_true", default=True)
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -208,10 +208,24 @@ int mrp_map_create(int dimx, int dimy, const int32_t* obst_xy, int n_obst,
   m->S = S;
   m->h_bits = new uint32_t[bits.size()];
   std::memcpy(m->h_bits, bits.data(), bits.size() * 4);
+  // second layout: 8x4-cell tiles for the tiled BFS kernel
+  const int TW8 = (dimx + 7) / 8, TH4 = (dimy + 3) / 4;
+  std::vector<uint32_t> bits84((size_t)TW8 * TH4, 0u);
+  for (int y = 0; y < dimy; ++y)
+    for (int x = 0; x < dimx; ++x)
+      if ((bits[((size_t)(y >> 5) * W + (x >> 5)) * 32 + (y & 31)] >> (x & 31)) & 1u)
+        bits84[(size_t)(y >> 2) * TW8 + (x >> 3)] |= 1u << (((y & 3) << 3) | (x & 7));
+  m->d_bits = nullptr;
+  m->d_bits84 = nullptr;
   cudaError_t e = cudaMalloc(&m->d_bits, bits.size() * 4);
   if (e == cudaSuccess)
     e = cudaMemcpy(m->d_bits, bits.data(), bits.size() * 4, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMalloc(&m->d_bits84, bits84.size() * 4);
+  if (e == cudaSuccess)
+    e = cudaMemcpy(m->d_bits84, bits84.data(), bits84.size() * 4, cudaMemcpyHostToDevice);
   if (e != cudaSuccess) {
+    cudaFree(m->d_bits);
+    cudaFree(m->d_bits84);
     delete[] m->h_bits;
     delete m;
     return fail(MRP_ERR_CUDA, "map upload failed: %s", cudaGetErrorString(e));
@@ -225,6 +239,7 @@ int mrp_map_destroy(mrp_map map) {
   if (!map) return 0;
   if (ctx().ready) cudaSetDevice(ctx().device);
   cudaFree(map->d_bits);
+  cudaFree(map->d_bits84);
   delete[] map->h_bits;
   delete map;
   return 0;

@@ -58,6 +58,9 @@ struct mrp_map_s {
   // bit b of that word = cell x = 32*tx + b.  Bits outside the map are 0.
   uint32_t* d_bits;
   uint32_t* h_bits;  // host copy (CLI / validation)
+  // free mask in 8x4-cell tiles (bfs_large.cu): bits84[ty*TW8 + tx], bit
+  // 8*(y&3) + (x&7), TW8 = ceil(dimx/8), TH4 = ceil(dimy/4)
+  uint32_t* d_bits84;
 };
 
 namespace mrp {
