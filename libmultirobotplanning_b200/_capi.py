@@ -210,3 +210,54 @@ def focal_counts(cell, length, self_idx, cand_t, cand_from, cand_to):
     check(lib().mrp_focal_counts(_p(cell), _p(length), N, Tpad, self_idx, _p(ct),
                                  _p(cf), _p(cto), len(ct), _p(s), _p(tr)))
     return s, tr
+
+
+def lowlevel_batch(maps, fields, jobs, variant=0, w=0.0, max_expanded=4000,
+                   path_cap=512, tables=None, table_len=None):
+    """jobs: list of dicts with keys map, start, goal, field (-1: Manhattan),
+    vc [(t, cell)...], ec [(t, from, to)...], table (-1), self.  Returns a list
+    of dicts(status, cost, fmin, expanded, cells, g)."""
+    n = len(jobs)
+    arr = (Job * max(n, 1))()
+    vc, ec = [], []
+    for k, j in enumerate(jobs):
+        a = arr[k]
+        a.map, a.start_cell, a.goal_cell = j.get("map", 0), j["start"], j["goal"]
+        a.field = j.get("field", -1)
+        a.vc_begin = len(vc)
+        vc += [list(x) for x in j.get("vc", [])]
+        a.vc_end = len(vc)
+        a.ec_begin = len(ec)
+        ec += [list(x) for x in j.get("ec", [])]
+        a.ec_end = len(ec)
+        a.table, a.self_idx = j.get("table", -1), j.get("self", 0)
+    vc = _i32(vc).reshape(-1, 2)
+    ec = _i32(ec).reshape(-1, 3)
+    handles = (C.c_void_p * len(maps))(*[m.handle for m in maps])
+    nf = 0
+    fptr = None
+    if fields is not None:
+        fields = _i32(fields)
+        nf = fields.shape[0]
+        fptr = _p(fields)
+    nt = N = Tpad = 0
+    tptr = lptr = None
+    if tables is not None:
+        tables, table_len = _i32(tables), _i32(table_len)
+        nt, N, Tpad = tables.shape
+        tptr, lptr = _p(tables), _p(table_len)
+    params = LowLevelParams(variant, w, max_expanded, path_cap)
+    info = (PathInfo * max(n, 1))()
+    cells = np.zeros((max(n, 1), path_cap), np.int32)
+    g = np.zeros((max(n, 1), path_cap), np.int32)
+    check(lib().mrp_lowlevel_batch(handles, len(maps), fptr, nf, _p(vc), len(vc),
+                                   _p(ec), len(ec), tptr, lptr, nt, N, Tpad, arr, n,
+                                   C.byref(params), info, _p(cells), _p(g)))
+    out = []
+    for k in range(n):
+        i = info[k]
+        L = i.length if i.status == 0 else 0
+        out.append({"status": i.status, "cost": i.cost, "fmin": i.fmin,
+                    "expanded": i.expanded, "cells": cells[k, :L].copy(),
+                    "g": g[k, :L].copy()})
+    return out
