@@ -182,6 +182,25 @@ int mrp_lowlevel_batch(const mrp_map* maps, int n_maps, const int32_t* fields,
                        const mrp_lowlevel_params* params, mrp_path_info* info,
                        int32_t* out_cells, int32_t* out_g);
 
+/* Device-resident distance fields ("field set"): computed once per instance
+ * batch and kept in HBM so that the replans of every constraint-tree node read
+ * them in place — the role ShortestPathHeuristic::m_shortestDistance plays for
+ * the lifetime of a reference Environment (example/cbs_ta.cpp:511).  All maps
+ * must share their dimensions; goal k lives on map goal_map[k]. */
+typedef struct mrp_fieldset_s* mrp_fieldset;
+int mrp_fieldset_create(const mrp_map* maps, int n_maps, const int32_t* goal_map,
+                        const int32_t* goal_cell, int n_goals, mrp_fieldset* out);
+int mrp_fieldset_read(mrp_fieldset fs, int first, int count, int32_t* out);
+int mrp_fieldset_destroy(mrp_fieldset fs);
+/* mrp_lowlevel_batch with job.field indexing a field set instead of a host
+ * array. */
+int mrp_lowlevel_batch_fs(const mrp_map* maps, int n_maps, mrp_fieldset fs,
+                          const int32_t* vc, int n_vc, const int32_t* ec, int n_ec,
+                          const int32_t* tables, const int32_t* table_len,
+                          int n_tables, int N, int Tpad, const mrp_job* jobs,
+                          int n_jobs, const mrp_lowlevel_params* params,
+                          mrp_path_info* info, int32_t* out_cells, int32_t* out_g);
+
 /* ---- instrumentation ---------------------------------------------------- */
 /* number of kernel launches issued by this library since mrp_init (bench.py's
  * `gpu_launches`) */

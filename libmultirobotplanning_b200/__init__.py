@@ -5,3 +5,4 @@ mirror used by the tests and the benchmark; the C++ host adapters and the
 cbs / ecbs / cbs_ta command lines live in host/."""
 from . import _capi as capi  # noqa: F401
 from . import instances  # noqa: F401
+from . import solver  # noqa: F401

@@ -51,7 +51,8 @@ EXPORTS = [
     "mrp_bfs_fields_batch", "mrp_bfs_workspace_bytes", "mrp_bfs_fields_dev",
     "mrp_first_conflict", "mrp_count_conflicts", "mrp_conflicts_batch",
     "mrp_focal_counts", "mrp_conflicts_dev", "mrp_decode_conflict",
-    "mrp_lowlevel_batch", "mrp_launch_count",
+    "mrp_lowlevel_batch", "mrp_launch_count", "mrp_fieldset_create",
+    "mrp_fieldset_read", "mrp_fieldset_destroy", "mrp_lowlevel_batch_fs",
 ]
 
 _lib = None

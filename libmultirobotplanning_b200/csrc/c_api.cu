@@ -33,7 +33,7 @@ Context& ctx() {
   return c;
 }
 
-static std::mutex& apiMutex() {
+std::mutex& apiMutex() {
   static std::mutex m;
   return m;
 }
@@ -431,6 +431,131 @@ int mrp_bfs_fields_batch(int n_maps, const int32_t* dims, const int32_t* obst_of
   if (int rc = launchBfsSmall(d_rows, d_dims, d_jobs, n_goals, d_out, c.stream)) return rc;
   MRP_CUDA(cudaMemcpyAsync(out, d_out, (size_t)off * 4, cudaMemcpyDeviceToHost, c.stream));
   MRP_CUDA(cudaStreamSynchronize(c.stream));
+  return 0;
+}
+
+// ---- field sets ---------------------------------------------------------------
+__global__ void gather_rows_kernel(const uint32_t* const* mapBits, int n_maps,
+                                   uint32_t* rows) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n_maps * 32) rows[i] = mapBits[i >> 5][i & 31];
+}
+__global__ void make_fs_jobs_kernel(const int32_t* goal_map, const int32_t* goal_cell, int n,
+                                    int cells, int4* jobs) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  const long long off = (long long)k * cells;
+  jobs[k] = make_int4(goal_map[k], goal_cell[k], (int)(off & 0xffffffffll), (int)(off >> 32));
+}
+
+int mrp_fieldset_create(const mrp_map* maps, int n_maps, const int32_t* goal_map,
+                        const int32_t* goal_cell, int n_goals, mrp_fieldset* out) {
+  std::lock_guard<std::mutex> lk(apiMutex());
+  MRP_CHECK(out != nullptr, MRP_ERR_INVALID, "out is NULL");
+  *out = nullptr;
+  MRP_CHECK(maps && n_maps > 0 && n_goals >= 0, MRP_ERR_INVALID, "bad arguments");
+  MRP_CHECK(n_goals == 0 || (goal_map && goal_cell), MRP_ERR_INVALID, "NULL goal arrays");
+  if (int rc = ensureInit()) return rc;
+  Context& c = ctx();
+  const int dimx = maps[0]->dimx, dimy = maps[0]->dimy, cells = dimx * dimy;
+  for (int m = 0; m < n_maps; ++m)
+    MRP_CHECK(maps[m] && maps[m]->dimx == dimx && maps[m]->dimy == dimy, MRP_ERR_INVALID,
+              "all maps of a field set must share their dimensions");
+  for (int k = 0; k < n_goals; ++k) {
+    MRP_CHECK(goal_map[k] >= 0 && goal_map[k] < n_maps, MRP_ERR_INVALID, "goal %d: bad map", k);
+    MRP_CHECK(goal_cell[k] >= 0 && goal_cell[k] < cells, MRP_ERR_INVALID,
+              "goal %d: cell outside the map", k);
+  }
+  mrp_fieldset_s* fs = new mrp_fieldset_s();
+  fs->dimx = dimx;
+  fs->dimy = dimy;
+  fs->n_fields = n_goals;
+  fs->d_fields = nullptr;
+  if (n_goals == 0) {
+    *out = fs;
+    return 0;
+  }
+  cudaError_t e = cudaMalloc(&fs->d_fields, (size_t)n_goals * cells * 4);
+  if (e != cudaSuccess) {
+    delete fs;
+    return fail(MRP_ERR_NOMEM, "cudaMalloc failed: %s", cudaGetErrorString(e));
+  }
+  int rc = 0;
+  int32_t *d_gm = nullptr, *d_gc = nullptr;
+  do {
+    if ((rc = scratch(5, (size_t)n_goals, &d_gm))) break;
+    if ((rc = scratch(0, (size_t)n_goals, &d_gc))) break;
+    cudaMemcpyAsync(d_gm, goal_map, (size_t)n_goals * 4, cudaMemcpyHostToDevice, c.stream);
+    cudaMemcpyAsync(d_gc, goal_cell, (size_t)n_goals * 4, cudaMemcpyHostToDevice, c.stream);
+    if (maps[0]->W == 1 && maps[0]->S == 1) {
+      // single-tile maps: one launch over all (map, goal) jobs
+      const uint32_t** d_ptrs = nullptr;
+      uint32_t* d_rows = nullptr;
+      int32_t* d_dims = nullptr;
+      int4* d_jobs = nullptr;
+      if ((rc = scratch(3, (size_t)n_maps, &d_ptrs))) break;
+      if ((rc = scratch(4, (size_t)n_maps * 32, &d_rows))) break;
+      if ((rc = scratch(2, (size_t)n_maps * 2, &d_dims))) break;
+      if ((rc = scratch(6, (size_t)n_goals, &d_jobs))) break;
+      std::vector<const uint32_t*> ptrs(n_maps);
+      std::vector<int32_t> dims(2 * (size_t)n_maps);
+      for (int m = 0; m < n_maps; ++m) {
+        ptrs[m] = maps[m]->d_bits;
+        dims[2 * m] = dimx;
+        dims[2 * m + 1] = dimy;
+      }
+      cudaMemcpyAsync(d_ptrs, ptrs.data(), sizeof(void*) * n_maps, cudaMemcpyHostToDevice, c.stream);
+      cudaMemcpyAsync(d_dims, dims.data(), dims.size() * 4, cudaMemcpyHostToDevice, c.stream);
+      gather_rows_kernel<<<(n_maps * 32 + 255) / 256, 256, 0, c.stream>>>(d_ptrs, n_maps, d_rows);
+      make_fs_jobs_kernel<<<(n_goals + 255) / 256, 256, 0, c.stream>>>(d_gm, d_gc, n_goals, cells, d_jobs);
+      countLaunch(2);
+      rc = launchBfsSmall(d_rows, d_dims, d_jobs, n_goals, fs->d_fields, c.stream);
+      if (rc) break;
+      cudaStreamSynchronize(c.stream);  // host staging vectors go out of scope
+    } else {
+      // tiled kernel: goals grouped by map (consecutive runs)
+      char* ws = nullptr;
+      if ((rc = scratch(3, bfsLargeWorkspaceBytes(maps[0], n_goals), &ws))) break;
+      int k = 0;
+      while (k < n_goals && rc == 0) {
+        int k1 = k;
+        while (k1 < n_goals && goal_map[k1] == goal_map[k]) ++k1;
+        rc = launchBfsLarge(maps[goal_map[k]], d_gc + k, k1 - k,
+                            fs->d_fields + (size_t)k * cells, ws, c.stream);
+        k = k1;
+      }
+      if (rc) break;
+    }
+    e = cudaStreamSynchronize(c.stream);
+    if (e != cudaSuccess) rc = fail(MRP_ERR_CUDA, "field set failed: %s", cudaGetErrorString(e));
+  } while (0);
+  if (rc) {
+    cudaFree(fs->d_fields);
+    delete fs;
+    return rc;
+  }
+  *out = fs;
+  return 0;
+}
+
+int mrp_fieldset_read(mrp_fieldset fs, int first, int count, int32_t* out) {
+  std::lock_guard<std::mutex> lk(apiMutex());
+  MRP_CHECK(fs && out && first >= 0 && count >= 0 && first + count <= fs->n_fields,
+            MRP_ERR_INVALID, "bad field range");
+  if (count == 0) return 0;
+  if (int rc = ensureInit()) return rc;
+  const size_t cells = (size_t)fs->dimx * fs->dimy;
+  MRP_CUDA(cudaMemcpy(out, fs->d_fields + (size_t)first * cells, (size_t)count * cells * 4,
+                      cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+int mrp_fieldset_destroy(mrp_fieldset fs) {
+  std::lock_guard<std::mutex> lk(apiMutex());
+  if (!fs) return 0;
+  if (ctx().ready) cudaSetDevice(ctx().device);
+  cudaFree(fs->d_fields);
+  delete fs;
   return 0;
 }
 

@@ -7,6 +7,7 @@
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
+#include <mutex>
 #include <string>
 
 #include "../../include/mrp_b200.h"
@@ -63,7 +64,14 @@ struct mrp_map_s {
   uint32_t* d_bits84;
 };
 
+struct mrp_fieldset_s {
+  int dimx, dimy, n_fields;
+  int32_t* d_fields;  // [n_fields][dimx*dimy]
+};
+
 namespace mrp {
+
+std::mutex& apiMutex();
 
 // simple RAII device buffer for the host-pointer entry points
 struct DevBuf {

@@ -1,0 +1,595 @@
+// hl_search.hpp — batched high-level searches on top of the CUDA hot path.
+//
+// The high-level loops of the reference stay on the host, as sequential
+// best-first searches per instance:
+//   CBS::search    include/libMultiRobotPlanning/cbs.hpp:85-172
+//   ECBS::search   include/libMultiRobotPlanning/ecbs.hpp:109-288
+//   CBSTA::search  include/libMultiRobotPlanning/cbs_ta.hpp:87-214
+// What changes is the granularity of their callees.  Many instances advance in
+// lock-step; per step ALL constraint-tree nodes that were just created are
+// checked for conflicts in one launch (mrp_conflicts_batch: getFirstConflict +
+// focalHeuristic), and ALL low-level replans they trigger run in one launch
+// (mrp_lowlevel_batch_fs: AStar / AStarEpsilon).  The per-goal distance fields
+// are computed once per batch and stay resident in HBM (mrp_fieldset).
+//
+// Deviations from the reference, all result-preserving:
+//   * cbs/ecbs use the exact BFS distance field instead of the Manhattan
+//     distance as admissible heuristic: same optimal costs.
+//   * ECBS admits a node to FOCAL iff cost <= w * min LB over OPEN (LB = sum of
+//     fmin), which implies the reference's rule cost <= w * min cost
+//     (ecbs.hpp:171-189) and additionally guarantees cost <= w * optimum.
+//   * expansion / wall-clock caps (the reference has none and may not return).
+//   * ties among equal-cost nodes break by node id (reference: Boost.Heap
+//     internals, not pinned by any of its tests).
+#pragma once
+
+#include <algorithm>
+#include <array>
+#include <chrono>
+#include <cstdint>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <set>
+#include <stdexcept>
+#include <string>
+#include <tuple>
+#include <vector>
+
+#include "../../include/mrp_b200.h"
+#include "assignment.hpp"
+
+namespace mrp_host {
+
+struct MapfInstance {
+  int dimx = 0, dimy = 0;
+  std::vector<int32_t> obstXY;                     // x0, y0, x1, y1, ...
+  std::vector<int> starts;                         // cell = x + dimx*y
+  std::vector<int> goals;                          // cbs / ecbs
+  std::vector<std::vector<int> > potentialGoals;   // cbs_ta (lists may be empty)
+  size_t numAgents() const { return starts.size(); }
+};
+
+struct AgentPath {
+  std::vector<int> cells;
+  std::vector<int> g;  // g-score per state: the "t" of output.yaml (cbs.cpp:659)
+  int cost = 0;
+  int fmin = 0;
+};
+
+enum SolveStatus { kSolved = 0, kNoSolution = 1, kCapped = 2 };
+
+struct SolveResult {
+  int status = kNoSolution;
+  long cost = 0, makespan = 0, lowerBound = 0;
+  long hlExpanded = 0, llExpanded = 0, numTaskAssignments = 0;
+  double runtime = 0;
+  std::vector<AgentPath> paths;
+};
+
+struct SolveOptions {
+  float w = 1.0f;
+  long maxHlExpanded = 0;  // per instance; 0 = unlimited
+  int maxLlExpanded = 8000;  // per low-level search (GPU workspace is sized by it)
+  double maxSeconds = 0;     // whole batch; 0 = unlimited
+  long maxTaskAssignments = 1000000000L;
+};
+
+enum class Algo { CBS = 0, ECBS = 1, CBSTA = 2 };
+
+inline void gpuCheck(int rc) {
+  if (rc < 0) throw std::runtime_error(std::string("mrp_b200: ") + mrp_last_error());
+}
+
+class BatchSolver {
+ public:
+  BatchSolver(Algo algo, const std::vector<MapfInstance>& instances, const SolveOptions& opt)
+      : m_algo(algo), m_opt(opt) {
+    if (instances.empty()) return;
+    m_dimx = instances[0].dimx;
+    m_dimy = instances[0].dimy;
+    m_cells = m_dimx * m_dimy;
+    m_pathCap = std::max(128, 4 * (m_dimx + m_dimy));
+    m_inst.resize(instances.size());
+    for (size_t k = 0; k < instances.size(); ++k) {
+      if (instances[k].dimx != m_dimx || instances[k].dimy != m_dimy)
+        throw std::runtime_error("all instances of one batch must share their map dimensions");
+      m_inst[k].in = &instances[k];
+    }
+  }
+  ~BatchSolver() {
+    if (m_fields) mrp_fieldset_destroy(m_fields);
+    for (mrp_map m : m_maps) mrp_map_destroy(m);
+  }
+  BatchSolver(const BatchSolver&) = delete;
+  BatchSolver& operator=(const BatchSolver&) = delete;
+
+  std::vector<SolveResult> run() {
+    std::vector<SolveResult> out(m_inst.size());
+    if (m_inst.empty()) return out;
+    setup();
+    const auto t0 = std::chrono::steady_clock::now();
+    auto elapsed = [&t0]() {
+      return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    };
+    std::vector<Node*> fresh;
+    buildRoots(fresh);
+    while (true) {
+      evaluate(fresh);
+      for (Node* n : fresh) m_inst[n->inst].open.emplace_back(n);
+      fresh.clear();
+      // one expansion per running instance
+      std::vector<Pending> pending;
+      bool anyRunning = false;
+      const bool timeUp = m_opt.maxSeconds > 0 && elapsed() > m_opt.maxSeconds;
+      for (size_t k = 0; k < m_inst.size(); ++k) {
+        Inst& I = m_inst[k];
+        if (I.done) continue;
+        if (I.open.empty()) {
+          finish(I, kNoSolution, nullptr, elapsed());
+          continue;
+        }
+        if (timeUp || (m_opt.maxHlExpanded > 0 && I.res.hlExpanded >= m_opt.maxHlExpanded)) {
+          finish(I, kCapped, nullptr, elapsed());
+          continue;
+        }
+        std::unique_ptr<Node> P = popBest(I);
+        ++I.res.hlExpanded;  // onExpandHighLevelNode, cbs.hpp:121
+        if (!P->found) {
+          finish(I, kSolved, P.get(), elapsed());
+          continue;
+        }
+        anyRunning = true;
+        Pending pd;
+        pd.inst = (int)k;
+        pd.parent = std::move(P);
+        pending.push_back(std::move(pd));
+      }
+      if (!anyRunning) break;
+      expand(pending, fresh);
+    }
+    for (size_t k = 0; k < m_inst.size(); ++k) out[k] = std::move(m_inst[k].res);
+    return out;
+  }
+
+ private:
+  struct ConsList {
+    std::vector<int32_t> vc;  // (time, cell) pairs
+    std::vector<int32_t> ec;  // (time, from, to) triples
+  };
+  struct Node {
+    int inst = 0;
+    std::vector<AgentPath> paths;
+    std::vector<ConsList> cons;
+    std::vector<int> task;  // goal cell per agent (-1: none)
+    long cost = 0, LB = 0;
+    int focal = 0;
+    int id = 0;
+    bool isRoot = false;
+    int found = 0;
+    mrp_conflict conflict;
+  };
+  struct Inst {
+    const MapfInstance* in = nullptr;
+    std::vector<std::unique_ptr<Node> > open;
+    int nextId = 0;
+    bool done = false;
+    int mapIdx = 0;
+    int fieldBase = 0;                 // first field of this instance in the set
+    std::map<int, int> fieldOfGoal;    // goal cell -> field index (cbs_ta)
+    std::unique_ptr<NextBestAssignment<int, int> > assignment;
+    SolveResult res;
+  };
+  struct Pending {
+    int inst = 0;
+    std::unique_ptr<Node> parent;
+  };
+  struct JobSpec {
+    int inst, agent, goal, field;
+    const ConsList* cons;
+    int table, self;
+  };
+  struct JobOut {
+    int status;
+    long expanded;
+    AgentPath path;
+  };
+
+  // ---------------------------------------------------------------------
+  void setup() {
+    std::vector<int32_t> goalMap, goalCell;
+    for (size_t k = 0; k < m_inst.size(); ++k) {
+      Inst& I = m_inst[k];
+      const MapfInstance& in = *I.in;
+      mrp_map m = nullptr;
+      gpuCheck(mrp_map_create(in.dimx, in.dimy, in.obstXY.data(), (int)in.obstXY.size() / 2, &m));
+      I.mapIdx = (int)m_maps.size();
+      m_maps.push_back(m);
+      I.fieldBase = (int)goalCell.size();
+      if (m_algo == Algo::CBSTA) {
+        for (const auto& pg : in.potentialGoals)
+          for (int g : pg)
+            if (!I.fieldOfGoal.count(g)) {
+              I.fieldOfGoal[g] = (int)goalCell.size();
+              goalMap.push_back(I.mapIdx);
+              goalCell.push_back(g);
+            }
+      } else {
+        for (int g : in.goals) {
+          goalMap.push_back(I.mapIdx);
+          goalCell.push_back(g);
+        }
+      }
+    }
+    // the heuristic precompute sits outside the reference's timer as well
+    // (Environment ctor, example/cbs_ta.cpp:254-281,570-578)
+    gpuCheck(mrp_fieldset_create(m_maps.data(), (int)m_maps.size(), goalMap.data(),
+                                 goalCell.data(), (int)goalCell.size(), &m_fields));
+    if (m_algo == Algo::CBSTA) {
+      for (Inst& I : m_inst) {
+        const MapfInstance& in = *I.in;
+        const int nf = (int)I.fieldOfGoal.size();
+        std::vector<int32_t> f((size_t)nf * m_cells);
+        if (nf) gpuCheck(mrp_fieldset_read(m_fields, I.fieldBase, nf, f.data()));
+        I.assignment.reset(new NextBestAssignment<int, int>());
+        for (size_t a = 0; a < in.numAgents(); ++a)
+          for (int g : in.potentialGoals[a]) {
+            const int fi = I.fieldOfGoal[g] - I.fieldBase;
+            I.assignment->setCost((int)a, g, f[(size_t)fi * m_cells + in.starts[a]]);
+          }
+        I.assignment->solve();
+      }
+    }
+  }
+
+  // nextTaskAssignment, example/cbs_ta.cpp:442-456
+  bool nextTasks(Inst& I, std::vector<int>& task) {
+    task.assign(I.in->numAgents(), -1);
+    if ((unsigned long)I.res.numTaskAssignments > (unsigned long)m_opt.maxTaskAssignments)
+      return false;
+    std::map<int, int> sol;
+    I.assignment->nextSolution(sol);
+    if (sol.empty()) return false;
+    ++I.res.numTaskAssignments;
+    for (const auto& e : sol) task[e.first] = e.second;
+    return true;
+  }
+
+  int fieldFor(const Inst& I, int agent, int goalCell) const {
+    if (goalCell < 0) return -1;
+    if (m_algo == Algo::CBSTA) return I.fieldOfGoal.at(goalCell);
+    return I.fieldBase + agent;
+  }
+
+  void finish(Inst& I, int status, const Node* n, double t) {
+    I.done = true;
+    I.res.status = status;
+    I.res.runtime = t;
+    if (n) {
+      I.res.paths = n->paths;
+      for (const auto& p : n->paths) {  // example/cbs.cpp:630-635
+        I.res.cost += p.cost;
+        I.res.makespan = std::max<long>(I.res.makespan, p.cost);
+        I.res.lowerBound += p.fmin;
+      }
+    }
+    I.open.clear();
+  }
+
+  std::unique_ptr<Node> popBest(Inst& I) {
+    size_t best = 0;
+    if (m_algo == Algo::ECBS) {
+      long minLB = I.open[0]->LB;
+      for (const auto& n : I.open) minLB = std::min(minLB, n->LB);
+      const float bound = (float)minLB * m_opt.w;  // fp32 like ecbs.hpp:181
+      bool have = false;
+      for (size_t k = 0; k < I.open.size(); ++k) {
+        const Node& n = *I.open[k];
+        if (!((float)n.cost <= bound)) continue;
+        // FOCAL order: focalHeuristic, then cost (ecbs.hpp:344-352), then id
+        if (!have || std::make_tuple(n.focal, n.cost, n.id) <
+                         std::make_tuple(I.open[best]->focal, I.open[best]->cost,
+                                         I.open[best]->id)) {
+          best = k;
+          have = true;
+        }
+      }
+      if (!have) {  // cannot happen (the min-LB node always qualifies); stay safe
+        for (size_t k = 1; k < I.open.size(); ++k)
+          if (I.open[k]->LB < I.open[best]->LB) best = k;
+      }
+    } else {
+      for (size_t k = 1; k < I.open.size(); ++k)  // lowest cost (cbs.hpp:187-191), then id
+        if (std::make_pair(I.open[k]->cost, I.open[k]->id) <
+            std::make_pair(I.open[best]->cost, I.open[best]->id))
+          best = k;
+    }
+    std::unique_ptr<Node> n = std::move(I.open[best]);
+    I.open[best] = std::move(I.open.back());
+    I.open.pop_back();
+    return n;
+  }
+
+  // ---- low-level batch ---------------------------------------------------
+  void runLowLevel(const std::vector<JobSpec>& specs, const std::vector<const Node*>& tableNodes,
+                   std::vector<JobOut>& out) {
+    out.assign(specs.size(), JobOut());
+    if (specs.empty()) return;
+    std::vector<mrp_job> jobs(specs.size());
+    std::vector<int32_t> vc, ec;
+    for (size_t k = 0; k < specs.size(); ++k) {
+      const JobSpec& s = specs[k];
+      mrp_job& j = jobs[k];
+      j.map = m_inst[s.inst].mapIdx;
+      j.start_cell = m_inst[s.inst].in->starts[s.agent];
+      j.goal_cell = s.goal;
+      j.field = s.field;
+      j.vc_begin = (int)vc.size() / 2;
+      if (s.cons) vc.insert(vc.end(), s.cons->vc.begin(), s.cons->vc.end());
+      j.vc_end = (int)vc.size() / 2;
+      j.ec_begin = (int)ec.size() / 3;
+      if (s.cons) ec.insert(ec.end(), s.cons->ec.begin(), s.cons->ec.end());
+      j.ec_end = (int)ec.size() / 3;
+      j.table = s.table;
+      j.self = s.self;
+    }
+    // path tables of the other agents (ECBS focal heuristics)
+    std::vector<int32_t> tables, tlen;
+    int N = 0, Tpad = 0;
+    if (!tableNodes.empty()) packTables(tableNodes, tables, tlen, N, Tpad);
+    mrp_lowlevel_params prm;
+    prm.variant = m_algo == Algo::CBSTA ? 1 : 0;
+    prm.w = m_algo == Algo::ECBS ? m_opt.w : 0.0f;
+    prm.max_expanded = m_opt.maxLlExpanded;
+    prm.path_cap = m_pathCap;
+    std::vector<mrp_path_info> info(specs.size());
+    std::vector<int32_t> cells(specs.size() * (size_t)m_pathCap), gs(cells.size());
+    gpuCheck(mrp_lowlevel_batch_fs(m_maps.data(), (int)m_maps.size(), m_fields, vc.data(),
+                                   (int)vc.size() / 2, ec.data(), (int)ec.size() / 3,
+                                   tables.empty() ? nullptr : tables.data(),
+                                   tlen.empty() ? nullptr : tlen.data(), (int)tableNodes.size(), N,
+                                   Tpad, jobs.data(), (int)jobs.size(), &prm, info.data(),
+                                   cells.data(), gs.data()));
+    for (size_t k = 0; k < specs.size(); ++k) {
+      JobOut& o = out[k];
+      o.status = info[k].status;
+      o.expanded = info[k].expanded;
+      m_inst[specs[k].inst].res.llExpanded += info[k].expanded;
+      if (o.status == 0) {
+        const int L = info[k].length;
+        o.path.cells.assign(cells.begin() + k * m_pathCap, cells.begin() + k * m_pathCap + L);
+        o.path.g.assign(gs.begin() + k * m_pathCap, gs.begin() + k * m_pathCap + L);
+        o.path.cost = info[k].cost;
+        o.path.fmin = info[k].fmin;
+      }
+    }
+  }
+
+  void packTables(const std::vector<const Node*>& nodes, std::vector<int32_t>& tables,
+                  std::vector<int32_t>& tlen, int& N, int& Tpad) const {
+    N = 0;
+    Tpad = 1;
+    for (const Node* n : nodes) {
+      N = std::max(N, (int)n->paths.size());
+      for (const auto& p : n->paths) Tpad = std::max(Tpad, (int)p.cells.size());
+    }
+    tables.assign(nodes.size() * (size_t)N * Tpad, 0);
+    tlen.assign(nodes.size() * (size_t)N, 0);
+    for (size_t b = 0; b < nodes.size(); ++b)
+      for (size_t a = 0; a < nodes[b]->paths.size(); ++a) {
+        const auto& c = nodes[b]->paths[a].cells;
+        std::copy(c.begin(), c.end(), tables.begin() + (b * N + a) * (size_t)Tpad);
+        tlen[b * N + a] = (int)c.size();
+      }
+  }
+
+  // ---- conflicts of freshly created nodes ----------------------------------
+  void evaluate(std::vector<Node*>& fresh) {
+    if (fresh.empty()) return;
+    std::vector<const Node*> nodes(fresh.begin(), fresh.end());
+    std::vector<int32_t> tables, tlen;
+    int N = 0, Tpad = 0;
+    packTables(nodes, tables, tlen, N, Tpad);
+    const int B = (int)fresh.size();
+    std::vector<int32_t> found(B), counts(B);
+    std::vector<mrp_conflict> confl(B);
+    // getFirstConflict bound: size-1 for cbs/ecbs (cbs.cpp:338-341), size for
+    // cbs_ta (cbs_ta.cpp:372-375); focalHeuristic counts with the same table
+    const int mode = m_algo == Algo::CBSTA ? 1 : 0;
+    gpuCheck(mrp_conflicts_batch(tables.data(), tlen.data(), B, N, Tpad, m_dimx, mode,
+                                 found.data(), confl.data(), counts.data()));
+    for (int b = 0; b < B; ++b) {
+      fresh[b]->found = found[b];
+      fresh[b]->conflict = confl[b];
+      fresh[b]->focal = counts[b];
+    }
+  }
+
+  // ---- roots -----------------------------------------------------------------
+  void buildRoots(std::vector<Node*>& fresh) {
+    std::vector<std::unique_ptr<Node> > roots(m_inst.size());
+    for (size_t k = 0; k < m_inst.size(); ++k) {
+      Inst& I = m_inst[k];
+      std::unique_ptr<Node> n(new Node());
+      n->inst = (int)k;
+      n->paths.resize(I.in->numAgents());
+      n->cons.resize(I.in->numAgents());
+      n->id = I.nextId++;
+      n->isRoot = true;
+      if (m_algo == Algo::CBSTA) {
+        if (!nextTasks(I, n->task)) {  // cbs_ta.hpp:96-103: no assignment, no search
+          finish(I, kNoSolution, nullptr, 0);
+          continue;
+        }
+      } else {
+        n->task.assign(I.in->goals.begin(), I.in->goals.end());
+      }
+      roots[k] = std::move(n);
+    }
+    if (m_algo == Algo::ECBS) {
+      // agents one after the other, each seeing the already planned ones
+      // through the focal heuristics (ecbs.hpp:118-136)
+      size_t maxN = 0;
+      for (const Inst& I : m_inst) maxN = std::max(maxN, I.in->numAgents());
+      for (size_t a = 0; a < maxN; ++a) {
+        std::vector<JobSpec> specs;
+        std::vector<const Node*> tabs;
+        for (size_t k = 0; k < m_inst.size(); ++k) {
+          if (!roots[k] || a >= m_inst[k].in->numAgents()) continue;
+          const int goal = roots[k]->task[a];
+          specs.push_back({(int)k, (int)a, goal, fieldFor(m_inst[k], (int)a, goal),
+                           &roots[k]->cons[a], (int)tabs.size(), (int)a});
+          tabs.push_back(roots[k].get());
+        }
+        std::vector<JobOut> outs;
+        runLowLevel(specs, tabs, outs);
+        for (size_t j = 0; j < specs.size(); ++j) absorbRoot(roots, specs[j], outs[j]);
+      }
+    } else {
+      std::vector<JobSpec> specs;
+      for (size_t k = 0; k < m_inst.size(); ++k) {
+        if (!roots[k]) continue;
+        for (size_t a = 0; a < m_inst[k].in->numAgents(); ++a) {
+          const int goal = roots[k]->task[a];
+          specs.push_back({(int)k, (int)a, goal, fieldFor(m_inst[k], (int)a, goal),
+                           &roots[k]->cons[a], -1, (int)a});
+        }
+      }
+      std::vector<JobOut> outs;
+      runLowLevel(specs, std::vector<const Node*>(), outs);
+      for (size_t j = 0; j < specs.size(); ++j) absorbRoot(roots, specs[j], outs[j]);
+    }
+    for (size_t k = 0; k < m_inst.size(); ++k)
+      if (roots[k]) fresh.push_back(roots[k].release());
+  }
+
+  void absorbRoot(std::vector<std::unique_ptr<Node> >& roots, const JobSpec& s, JobOut& o) {
+    if (!roots[s.inst]) return;
+    if (o.status != 0) {  // cbs.hpp:96-100: a failing root search ends the search
+      finish(m_inst[s.inst], o.status == 2 ? kCapped : kNoSolution, nullptr, 0);
+      roots[s.inst].reset();
+      return;
+    }
+    Node& n = *roots[s.inst];
+    n.cost += o.path.cost;
+    n.LB += o.path.fmin;
+    n.paths[s.agent] = std::move(o.path);
+  }
+
+  // ---- one expansion step for every pending parent -----------------------------
+  void expand(std::vector<Pending>& pending, std::vector<Node*>& fresh) {
+    struct ChildPlan {
+      int pendingIdx;
+      int agent;        // replanned agent; -1: a whole new root (cbs_ta)
+      std::unique_ptr<Node> node;
+      size_t firstJob, nJobs;
+      bool failed = false;
+    };
+    std::vector<ChildPlan> plans;
+    std::vector<JobSpec> specs;
+    std::vector<const Node*> tabs;
+    for (size_t pi = 0; pi < pending.size(); ++pi) {
+      Inst& I = m_inst[pending[pi].inst];
+      const Node& P = *pending[pi].parent;
+      int tableIdx = -1;
+      if (m_algo == Algo::ECBS) {
+        tableIdx = (int)tabs.size();
+        tabs.push_back(&P);
+      }
+      if (m_algo == Algo::CBSTA && P.isRoot) {
+        // an expanded root with a conflict spawns the next-best assignment as
+        // a new root (cbs_ta.hpp:142-172).  The reference copies isRoot into
+        // every child (cbs_ta.hpp:180), so this fires on every expansion.
+        std::unique_ptr<Node> r(new Node());
+        if (nextTasks(I, r->task)) {
+          r->inst = pending[pi].inst;
+          r->paths.resize(I.in->numAgents());
+          r->cons.resize(I.in->numAgents());
+          r->isRoot = true;
+          ChildPlan cp;
+          cp.pendingIdx = (int)pi;
+          cp.agent = -1;
+          cp.firstJob = specs.size();
+          cp.nJobs = I.in->numAgents();
+          for (size_t a = 0; a < I.in->numAgents(); ++a)
+            specs.push_back({pending[pi].inst, (int)a, r->task[a],
+                             fieldFor(I, (int)a, r->task[a]), &r->cons[a], -1, (int)a});
+          cp.node = std::move(r);
+          plans.push_back(std::move(cp));
+        }
+      }
+      // createConstraintsFromConflict, example/cbs.cpp:388-406: children in
+      // ascending agent order (agent1 < agent2)
+      const mrp_conflict& c = P.conflict;
+      const int c1 = c.x1 + m_dimx * c.y1;
+      const int c2 = c.type == 1 ? c.x2 + m_dimx * c.y2 : -1;
+      for (int side = 0; side < 2; ++side) {
+        const int agent = side == 0 ? c.agent1 : c.agent2;
+        std::unique_ptr<Node> n(new Node(P));
+        n->isRoot = P.isRoot;
+        if (c.type == 0) {
+          n->cons[agent].vc.push_back(c.time);
+          n->cons[agent].vc.push_back(c1);
+        } else {
+          n->cons[agent].ec.push_back(c.time);
+          n->cons[agent].ec.push_back(side == 0 ? c1 : c2);
+          n->cons[agent].ec.push_back(side == 0 ? c2 : c1);
+        }
+        n->cost -= n->paths[agent].cost;
+        n->LB -= n->paths[agent].fmin;
+        ChildPlan cp;
+        cp.pendingIdx = (int)pi;
+        cp.agent = agent;
+        cp.firstJob = specs.size();
+        cp.nJobs = 1;
+        specs.push_back({pending[pi].inst, agent, n->task[agent],
+                         fieldFor(I, agent, n->task[agent]), &n->cons[agent], tableIdx, agent});
+        cp.node = std::move(n);
+        plans.push_back(std::move(cp));
+      }
+    }
+    std::vector<JobOut> outs;
+    runLowLevel(specs, tabs, outs);
+    for (ChildPlan& cp : plans) {
+      Inst& I = m_inst[pending[cp.pendingIdx].inst];
+      if (I.done) continue;
+      Node& n = *cp.node;
+      bool ok = true, capped = false;
+      for (size_t j = cp.firstJob; j < cp.firstJob + cp.nJobs; ++j) {
+        if (outs[j].status == 2) capped = true;
+        if (outs[j].status != 0) ok = false;
+      }
+      if (capped) {  // a capped replan could hide the optimum: give up honestly
+        finish(I, kCapped, nullptr, 0);
+        continue;
+      }
+      if (!ok) continue;  // no path under these constraints: the child is dropped
+      for (size_t j = cp.firstJob; j < cp.firstJob + cp.nJobs; ++j) {
+        const int a = specs[j].agent;
+        n.cost += outs[j].path.cost;
+        n.LB += outs[j].path.fmin;
+        n.paths[a] = std::move(outs[j].path);
+      }
+      n.id = I.nextId++;
+      fresh.push_back(cp.node.release());
+    }
+    // children of instances that were finished meanwhile must not leak
+    for (auto it = fresh.begin(); it != fresh.end();) {
+      if (m_inst[(*it)->inst].done) {
+        delete *it;
+        it = fresh.erase(it);
+      } else {
+        ++it;
+      }
+    }
+  }
+
+  Algo m_algo;
+  SolveOptions m_opt;
+  int m_dimx = 0, m_dimy = 0, m_cells = 0, m_pathCap = 128;
+  std::vector<Inst> m_inst;
+  std::vector<mrp_map> m_maps;
+  mrp_fieldset m_fields = nullptr;
+};
+
+}  // namespace mrp_host

@@ -1,0 +1,170 @@
+// host_capi.cpp — C entry point of the batched high-level drivers
+// (libmrp_host.so), used by the Python tests and bench.py.
+#include <cstdint>
+#include <map>
+#include <string>
+#include <utility>
+#include <vector>
+
+#include "cli.hpp"
+#include "gpu_environment.hpp"
+#include "hl_search.hpp"
+
+using namespace mrp_host;
+
+static thread_local std::string g_err;
+
+extern "C" {
+
+const char* mrph_last_error(void) { return g_err.c_str(); }
+
+// algo: 0 cbs, 1 ecbs, 2 cbs_ta.  Instances are CSR-flattened:
+// dims[n][2]; obst_off[n+1] into obst_xy[][2]; agent_off[n+1] into
+// start_cell[] / goal_cell[]; cbs_ta: pg_off[total_agents+1] into pg_cell[].
+// Outputs per instance; paths: path_off[total_agents+1] into path_cell/path_g.
+int mrph_solve_batch(int algo, int n_inst, const int32_t* dims, const int32_t* obst_off,
+                     const int32_t* obst_xy, const int32_t* agent_off,
+                     const int32_t* start_cell, const int32_t* goal_cell,
+                     const int32_t* pg_off, const int32_t* pg_cell, float w, int64_t max_hl,
+                     int32_t max_ll, double max_seconds, int64_t max_ta, int32_t* status,
+                     int64_t* cost, int64_t* makespan, int64_t* lower_bound, int64_t* hl,
+                     int64_t* ll, int64_t* nta, double* runtime, int32_t* path_off,
+                     int32_t* path_cell, int32_t* path_g, int64_t path_cap) {
+  try {
+    std::vector<MapfInstance> insts(n_inst);
+    for (int k = 0; k < n_inst; ++k) {
+      MapfInstance& in = insts[k];
+      in.dimx = dims[2 * k];
+      in.dimy = dims[2 * k + 1];
+      in.obstXY.assign(obst_xy + 2 * obst_off[k], obst_xy + 2 * obst_off[k + 1]);
+      for (int a = agent_off[k]; a < agent_off[k + 1]; ++a) {
+        in.starts.push_back(start_cell[a]);
+        if (algo == 2)
+          in.potentialGoals.emplace_back(pg_cell + pg_off[a], pg_cell + pg_off[a + 1]);
+        else
+          in.goals.push_back(goal_cell[a]);
+      }
+    }
+    SolveOptions opt;
+    opt.w = w;
+    opt.maxHlExpanded = max_hl;
+    opt.maxLlExpanded = max_ll;
+    opt.maxSeconds = max_seconds;
+    opt.maxTaskAssignments = max_ta;
+    // one lock-step batch per map size
+    std::map<std::pair<int, int>, std::vector<int> > groups;
+    for (int k = 0; k < n_inst; ++k) groups[{insts[k].dimx, insts[k].dimy}].push_back(k);
+    std::vector<SolveResult> results(n_inst);
+    for (const auto& g : groups) {
+      std::vector<MapfInstance> sub;
+      for (int k : g.second) sub.push_back(insts[k]);
+      BatchSolver solver(static_cast<Algo>(algo), sub, opt);
+      std::vector<SolveResult> r = solver.run();
+      for (size_t j = 0; j < g.second.size(); ++j) results[g.second[j]] = std::move(r[j]);
+    }
+    int64_t off = 0;
+    for (int k = 0; k < n_inst; ++k) {
+      const SolveResult& r = results[k];
+      status[k] = r.status;
+      cost[k] = r.cost;
+      makespan[k] = r.makespan;
+      lower_bound[k] = r.lowerBound;
+      hl[k] = r.hlExpanded;
+      ll[k] = r.llExpanded;
+      nta[k] = r.numTaskAssignments;
+      runtime[k] = r.runtime;
+      for (int a = agent_off[k]; a < agent_off[k + 1]; ++a) {
+        path_off[a] = (int32_t)off;
+        if (r.status != kSolved) continue;
+        const AgentPath& p = r.paths[a - agent_off[k]];
+        for (size_t t = 0; t < p.cells.size(); ++t) {
+          if (off < path_cap) {
+            path_cell[off] = p.cells[t];
+            path_g[off] = p.g[t];
+          }
+          ++off;
+        }
+      }
+    }
+    path_off[agent_off[n_inst]] = (int32_t)off;
+    return off > path_cap ? -2 : 0;
+  } catch (const std::exception& e) {
+    g_err = e.what();
+    return -1;
+  }
+}
+
+// Smoke test of the concept adapter (gpu_environment.hpp): builds an
+// Environment, exercises every callback once and returns the first-conflict
+// time of two straight-line plans (-1: none).  Keeps the adapter compiled and
+// linked even though the CLIs use the batched path.
+int mrph_environment_selftest(void) {
+  try {
+    std::unordered_set<Location> obstacles;
+    std::vector<Location> goals = {Location(2, 0), Location(0, 0)};
+    Environment env(3, 1, obstacles, goals);
+    Constraints none;
+    env.setLowLevelContext(0, &none);
+    if (env.admissibleHeuristic(State(0, 0, 0)) != 2) return -10;
+    if (env.isSolution(State(0, 0, 0)) || !env.isSolution(State(2, 2, 0))) return -11;
+    std::vector<Neighbor<State, Action, int> > nb;
+    env.getNeighbors(State(0, 1, 0), nb);
+    if (nb.size() != 3) return -12;
+    std::vector<Environment::Plan> sol(2);
+    for (int t = 0; t < 3; ++t) {
+      sol[0].states.push_back({State(t, t, 0), t});
+      sol[1].states.push_back({State(t, 2 - t, 0), t});
+    }
+    Conflict c;
+    if (!env.getFirstConflict(sol, c)) return -13;
+    std::map<size_t, Constraints> cons;
+    env.createConstraintsFromConflict(c, cons);
+    if (cons.size() != 2) return -14;
+    if (env.focalHeuristic(sol) < 1) return -15;
+    if (env.focalStateHeuristic(State(1, 1, 0), 1, sol) != 1) return -16;
+    env.onExpandHighLevelNode(0);
+    env.onExpandLowLevelNode(State(0, 0, 0), 0, 0);
+    return c.time * 10 + (c.type == Conflict::Vertex ? 0 : 1);
+  } catch (const std::exception& e) {
+    g_err = e.what();
+    return -1;
+  }
+}
+
+}  // extern "C"
+
+// Parses an input YAML with the CLI's reader (CPU only; used by the tests).
+// Returns the number of agents, or -1.  Arrays must hold `cap` entries.
+extern "C" int mrph_load_instance(const char* path, int ta, int32_t* dims, int32_t* n_obst,
+                                  int32_t* obst_xy, int32_t* start_cell, int32_t* goal_cell,
+                                  int32_t* pg_off, int32_t* pg_cell, int cap) {
+  try {
+    const MapfInstance in = loadInstance(path, ta != 0);
+    if ((int)in.obstXY.size() > cap || (int)in.numAgents() >= cap) {
+      g_err = "instance exceeds the buffers";
+      return -1;
+    }
+    dims[0] = in.dimx;
+    dims[1] = in.dimy;
+    *n_obst = (int)in.obstXY.size() / 2;
+    for (size_t k = 0; k < in.obstXY.size(); ++k) obst_xy[k] = in.obstXY[k];
+    int off = 0;
+    for (size_t a = 0; a < in.numAgents(); ++a) {
+      start_cell[a] = in.starts[a];
+      if (ta) {
+        pg_off[a] = off;
+        for (int g : in.potentialGoals[a]) {
+          if (off >= cap) return -1;
+          pg_cell[off++] = g;
+        }
+      } else {
+        goal_cell[a] = in.goals[a];
+      }
+    }
+    if (ta) pg_off[in.numAgents()] = off;
+    return (int)in.numAgents();
+  } catch (const std::exception& e) {
+    g_err = e.what();
+    return -1;
+  }
+}

@@ -1,0 +1,188 @@
+"""GPU parity of the end-to-end searches (batched drivers + drop-in binaries):
+optimal sums-of-costs of CBS / CBS-TA bit-exact against the reference's pinned
+answers and the oracle; ECBS within the w bound."""
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+import yaml
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+BIN = os.path.join(ROOT, "bin")
+
+
+class Inst:
+    def __init__(self, d):
+        self.dimx, self.dimy = d["dimx"], d["dimy"]
+        self.obstacles = np.array(d["obstacles"], np.int32).reshape(-1, 2)
+        self.starts = np.array(d["starts"], np.int32).reshape(-1, 2)
+        if "goals" in d:
+            self.goals = np.array(d["goals"], np.int32).reshape(-1, 2)
+        else:
+            self.potential_goals = [np.array(g, np.int32).reshape(-1, 2)
+                                    for g in d["potentialGoals"]]
+
+    def cell(self, xy):
+        xy = np.asarray(xy)
+        return xy[..., 0] + self.dimx * xy[..., 1]
+
+
+def check_solution(inst, paths, mode):
+    """Validity under the reference's own conflict semantics (same loop bound)."""
+    free = np.ones((inst.dimy, inst.dimx), bool)
+    if len(inst.obstacles):
+        free[inst.obstacles[:, 1], inst.obstacles[:, 0]] = False
+    for a, p in enumerate(paths):
+        assert tuple(p[0][:2]) == tuple(inst.starts[a]) and p[0][2] == 0
+        for t in range(len(p)):
+            assert free[p[t][1], p[t][0]]
+            if t:
+                assert abs(p[t][0] - p[t - 1][0]) + abs(p[t][1] - p[t - 1][1]) <= 1
+    T = max(len(p) for p in paths) - (1 if mode == 0 else 0)
+    pos = lambda a, t: tuple(paths[a][min(t, len(paths[a]) - 1)][:2])
+    for t in range(T):
+        for a in range(len(paths)):
+            for b in range(a + 1, len(paths)):
+                assert pos(a, t) != pos(b, t)
+                assert not (pos(a, t) == pos(b, t + 1) and pos(a, t + 1) == pos(b, t))
+
+
+def test_reference_fixtures_batched(capi, ref_fixtures):
+    from libmultirobotplanning_b200 import solver
+    for name, d in ref_fixtures.items():
+        exp = d["expected"]
+        inst = Inst(d)
+        if "cbs_cost" in exp:
+            r = solver.solve_batch(solver.CBS, [inst], max_hl=5000)[0]
+            assert r["status"] == 0 and r["cost"] == exp["cbs_cost"], name
+            check_solution(inst, r["paths"], 0)
+            r = solver.solve_batch(solver.ECBS, [inst], w=1.0, max_hl=5000)[0]
+            assert r["status"] == 0 and r["cost"] == exp["ecbs_w1_cost"], name
+        if "cbs_ta_cost" in exp:
+            r = solver.solve_batch(solver.CBS_TA, [inst], max_hl=5000)[0]
+            assert r["status"] == 0 and r["cost"] == exp["cbs_ta_cost"], name
+            if "agent0_last" in exp:
+                x, y, g = r["paths"][0][-1]
+                assert {"x": x, "y": y, "t": g} == exp["agent0_last"]
+            if "agent1_last_xy" in exp:
+                assert list(r["paths"][1][-1][:2]) == exp["agent1_last_xy"]
+
+
+def test_swap_fixtures(capi, ref_fixtures):
+    from libmultirobotplanning_b200 import solver
+    for name, cost, mk in (("mapf_swap2", 12, 6), ("mapf_swap4", 28, 8), ("mapf_simple1b", 8, 4)):
+        r = solver.solve_batch(solver.CBS, [Inst(ref_fixtures[name])], max_hl=5000)[0]
+        assert (r["status"], r["cost"], r["makespan"]) == (0, cost, mk), name
+
+
+def test_cbs_8x8_set_matches_oracle_golden(capi, set8, oracle_golden):
+    """Config C2: CBS over the 8x8 benchmark set, all instances in one lock-step
+    batch; sums of costs bit-exact on every instance of the golden file."""
+    from libmultirobotplanning_b200 import solver
+    names = [n for n in oracle_golden["cbs"] if n.startswith("map_8by8")]
+    by = {i.name: i for i in set8}
+    insts = [by[n] for n in names]
+    res = solver.solve_batch(solver.CBS, insts, max_hl=20000, max_seconds=240)
+    sums = {}
+    for n, i, r in zip(names, insts, res):
+        g = oracle_golden["cbs"][n]
+        if g["status"] != 0 or r["status"] != 0:
+            continue  # capped on one side: nothing to compare
+        assert r["cost"] == g["cost"], n
+        k = i.n_agents
+        sums[k] = sums.get(k, 0) + r["cost"]
+    assert [sums[k] for k in (1, 2, 3, 4, 5)] == [599, 1167, 1765, 2418, 2979]
+    for i, r in list(zip(insts, res))[::23]:
+        if r["status"] == 0:
+            check_solution(i, r["paths"], 0)
+
+
+def test_cbs_32x32_and_ecbs_bound(capi, set32, oracle_golden):
+    from libmultirobotplanning_b200 import solver
+    names = [n for n in oracle_golden["cbs"] if n.startswith("map_32by32")]
+    by = {i.name: i for i in set32}
+    insts = [by[n] for n in names]
+    res = solver.solve_batch(solver.CBS, insts, max_hl=3000, max_seconds=240)
+    n_cmp = 0
+    for n, r in zip(names, res):
+        g = oracle_golden["cbs"][n]
+        if g["status"] == 0 and r["status"] == 0:
+            assert (r["cost"]) == (g["cost"]), n
+            n_cmp += 1
+    assert n_cmp >= 15
+    # config C1: ECBS w=1.3 on agents10_ex1; optimal SOC 236 => cost in [236, 306]
+    i = by["map_32by32_obst204_agents10_ex1"]
+    for w in (1.0, 1.3):
+        r = solver.solve_batch(solver.ECBS, [i], w=w, max_hl=3000)[0]
+        assert r["status"] == 0 and 236 <= r["cost"] <= 306
+        assert np.float32(r["cost"]) <= np.float32(r["lower_bound"]) * np.float32(w)
+        assert r["lower_bound"] <= 236
+        if w == 1.0:
+            assert r["cost"] == 236
+        check_solution(i, r["paths"], 0)
+    # ECBS on crowded instances (C3 regime): 50 agents, w = 1.3
+    crowd = [x for x in set32 if x.n_agents == 50][:8]
+    res = solver.solve_batch(solver.ECBS, crowd, w=1.3, max_hl=2000, max_seconds=120)
+    solved = 0
+    for i, r in zip(crowd, res):
+        if r["status"] == 0:
+            solved += 1
+            assert np.float32(r["cost"]) <= np.float32(r["lower_bound"]) * np.float32(1.3)
+            check_solution(i, r["paths"], 0)
+    assert solved >= 6
+
+
+def test_cbs_ta_c4_like(capi, orc, set32):
+    """Config C4 shape at a size the oracle finishes quickly: every agent may
+    take any goal of the instance; optimal cost equals the oracle's."""
+    from libmultirobotplanning_b200 import solver
+    base = next(i for i in set32 if i.name == "map_32by32_obst204_agents10_ex3")
+    inst = base.with_all_goals_potential()
+    r = solver.solve_batch(solver.CBS_TA, [inst], max_hl=3000)[0]
+    o = orc.cbs_ta(inst.dimx, inst.dimy, inst.obstacles, inst.starts,
+                   [g.tolist() for g in inst.potential_goals], caps=(3000, 0, 60.0))
+    assert r["status"] == 0 and o["status"] == 0
+    assert r["cost"] == o["cost"]
+    check_solution(inst, r["paths"], 1)
+
+
+def test_cli_binaries(capi, ref_fixtures, tmp_path):
+    from libmultirobotplanning_b200 import instances as I
+    for name, tool, extra, key in (("mapf_simple1", "cbs", [], "cbs_cost"),
+                                   ("mapf_circle", "cbs", [], "cbs_cost"),
+                                   ("mapf_atGoal", "ecbs", ["-w", "1.0"], "ecbs_w1_cost"),
+                                   ("mapf_simple1", "ecbs", ["--suboptimality=1.0"], "ecbs_w1_cost"),
+                                   ("mapfta_simple1_a2", "cbs_ta", [], "cbs_ta_cost"),
+                                   ("mapfta_simple1_a3", "cbs_ta", ["--maxTaskAssignments", "5"],
+                                    "cbs_ta_cost")):
+        d = ref_fixtures[name]
+        x = Inst(d)
+        inst = I.Instance(name, x.dimx, x.dimy, x.obstacles, x.starts,
+                          getattr(x, "goals", None), getattr(x, "potential_goals", None))
+        inp, out = str(tmp_path / "in.yaml"), str(tmp_path / "out.yaml")
+        if os.path.exists(out):
+            os.remove(out)
+        I.save_yaml(inst, inp)
+        r = subprocess.run([os.path.join(BIN, tool), "-i", inp, "-o", out] + extra,
+                           capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+        assert "Planning successful!" in r.stdout and "done; cost:" in r.stdout
+        text = open(out).read()
+        y = yaml.safe_load(text)
+        assert y["statistics"]["cost"] == d["expected"][key]
+        assert list(y["statistics"].keys())[:5] == ["cost", "makespan", "runtime",
+                                                    "highLevelExpanded", "lowLevelExpanded"]
+        assert ("numTaskAssignments" in y["statistics"]) == (tool == "cbs_ta")
+        assert re.search(r"^schedule:\n  agent0:\n    - x: \d+\n      y: \d+\n      t: 0\n", text, re.M)
+        assert sorted(y["schedule"]) == ["agent%d" % a for a in range(len(x.starts))]
+        if "agent0_last" in d["expected"]:
+            assert y["schedule"]["agent0"][-1] == d["expected"]["agent0_last"]
+
+
+def test_environment_adapter(capi):
+    from libmultirobotplanning_b200 import solver
+    # two agents walking into each other on a 3x1 corridor: vertex conflict at t=1
+    assert solver.lib().mrph_environment_selftest() == 10
