@@ -47,6 +47,7 @@ struct BfsTileParams {
   int TWc;  // row stride of the byte claims (TWc/4 == 1 mod 32)
   int cap;  // list entries kept in shared memory (multiple of the block size)
   int spillCap;  // capacity of the global fallback lists (same multiple)
+  int nCompute;  // threads that run the level logic; the rest only store
   int dbg;  // debug: bit0 = skip level stores, bit1 = skip obstacle stores
 };
 
@@ -86,6 +87,9 @@ bfs_tiles_kernel(BfsTileParams p) {
   const int TW = p.TW, TH = p.TH, dimx = p.dimx, TWv = p.TWv, TWc = p.TWc;
   const int nVis = TH * TWv, nClaimWords = (TH * TWc + 3) / 4;
   const int nThreads = blockDim.x;
+  // role split: the upper half of the block only issues the field stores
+  const int nCompute = p.nCompute;
+  const bool isStore = tid >= nCompute;
 
   // ---- storage ----
   // lists live in shared memory (capacity p.cap).  If a level ever needs more
@@ -162,7 +166,7 @@ bfs_tiles_kernel(BfsTileParams p) {
         uint2* lnxt = list0 + nxt * cap;
         TICK(0);
         // ---------------- phase A: read-only, shared memory only ----------------
-        for (int idx = tid; idx < count; idx += nThreads) {
+        for (int idx = tid; idx < (isStore ? 0 : count); idx += nCompute) {
           const uint2 ent = lcur[idx];  // x = ty<<16 | tx, y = free word of the tile
           const int ty = (int)(ent.x >> 16), tx = (int)(ent.x & 0xffffu);
           const int V = ty * TWv + tx, C = ty * TWc + tx;
@@ -206,58 +210,16 @@ bfs_tiles_kernel(BfsTileParams p) {
         __syncthreads();
         TICK(2);
         // ---------------- phase B: commit + next list + field stores ----------------
-        const int rounds = (count + nThreads - 1) / nThreads;
-        for (int r = 0; r < rounds; ++r) {
-          const int idx = r * nThreads + tid;
-          if (idx - lane >= count) break;  // warp-uniform: nothing left for this warp
-          const bool valid = idx < count;
-          const uint32_t cand = valid ? candArr[idx] : 0u;
-          const uint32_t pm = valid ? pmArr[idx] : 0u;
-          const uint2 ent = lcur[valid ? idx : 0];
-          const uint32_t e = ent.x;
-          const int ty = (int)(e >> 16), tx = (int)(e & 0xffffu);
-          const int C = ty * TWc + tx;
-          const int F = ty * TW + tx;
-          uint32_t wmask = 0;  // bit k: this entry appends neighbour k (0 = itself)
-          if (cand) {
-            const uint8_t id = (uint8_t)idx;
-            if (claim[C] == id) wmask |= 1;
-            if ((pm & 2) && claim[C - TWc] == id) wmask |= 2;
-            if ((pm & 4) && claim[C + TWc] == id) wmask |= 4;
-            if ((pm & 8) && claim[C - 1] == id) wmask |= 8;
-            if ((pm & 16) && claim[C + 1] == id) wmask |= 16;
-            vis[ty * TWv + tx] |= cand;
-          }
-          // free words of the tiles this entry appends (the next level then
-          // runs out of shared memory only); the loads complete behind the
-          // slot allocation and the field stores
-          uint32_t f1 = 0, f2 = 0, f3 = 0, f4 = 0;
-          if (wmask & 2u) f1 = __ldg(&p.free84[F - TW]);
-          if (wmask & 4u) f2 = __ldg(&p.free84[F + TW]);
-          if (wmask & 8u) f3 = __ldg(&p.free84[F - 1]);
-          if (wmask & 16u) f4 = __ldg(&p.free84[F + 1]);
-          TICK(6);
-          // slot allocation: ballots rank the winners, one atomic per warp
-          const uint32_t b0 = __ballot_sync(0xffffffffu, wmask & 1u);
-          const uint32_t b1 = __ballot_sync(0xffffffffu, wmask & 2u);
-          const uint32_t b2 = __ballot_sync(0xffffffffu, wmask & 4u);
-          const uint32_t b3 = __ballot_sync(0xffffffffu, wmask & 8u);
-          const uint32_t b4 = __ballot_sync(0xffffffffu, wmask & 16u);
-          const int n0 = __popc(b0), n1 = __popc(b1), n2 = __popc(b2), n3 = __popc(b3);
-          const int total = n0 + n1 + n2 + n3 + __popc(b4);
-          int base = 0;
-          if (total) {
-            if (lane == 0) base = atomicAdd(&sCount[nxt], total);
-            base = __shfl_sync(0xffffffffu, base, 0);
-            if (base + total > cap) {
-              if (lane == 0) sOverflow = 1;
-              wmask = 0;
-            }
-          }
-          TICK(7);
-          // field stores: every new cell gets its level; the obstacle cells of
-          // a tile that gains its first cell get MRP_INF at the same time
-          if (cand) {
+        // the field stores of this level: every new cell gets its level; the
+        // obstacle cells of a tile that gains its first cell get MRP_INF at
+        // the same time
+        auto fieldStores = [&](int first, int stride) {
+          for (int idx = first; idx < count; idx += stride) {
+            const uint32_t cand = candArr[idx];
+            if (!cand) continue;
+            const uint32_t pm = pmArr[idx];
+            const uint2 ent = lcur[idx];
+            const int ty = (int)(ent.x >> 16), tx = (int)(ent.x & 0xffffu);
             int32_t* obase = out + (4 * ty) * dimx + 8 * tx;
             uint32_t inf = 0;
             if ((pm & 0x20u) && !(p.dbg & 2)) inf = ~ent.y & tileInBounds(tx, ty, dimx, p.dimy);
@@ -265,15 +227,76 @@ bfs_tiles_kernel(BfsTileParams p) {
             while (m) {
               const int b = __ffs(m) - 1;
               m &= m - 1;
-              obase[(b >> 3) * dimx + (b & 7)] = ((inf >> b) & 1u) ? MRP_INF : level;
+              if (p.dbg & 4)
+                out[(idx & 31)] = level;  // debug: same store count, one line per warp
+              else
+                obase[(b >> 3) * dimx + (b & 7)] = ((inf >> b) & 1u) ? MRP_INF : level;
             }
           }
-          if (wmask & 1u) lnxt[base + __popc(b0 & ltMask)] = make_uint2(e, ent.y);
-          if (wmask & 2u) lnxt[base + n0 + __popc(b1 & ltMask)] = make_uint2(e - 0x10000u, f1);
-          if (wmask & 4u) lnxt[base + n0 + n1 + __popc(b2 & ltMask)] = make_uint2(e + 0x10000u, f2);
-          if (wmask & 8u) lnxt[base + n0 + n1 + n2 + __popc(b3 & ltMask)] = make_uint2(e - 1u, f3);
-          if (wmask & 16u)
-            lnxt[base + n0 + n1 + n2 + n3 + __popc(b4 & ltMask)] = make_uint2(e + 1u, f4);
+        };
+        if (isStore) {
+          // store warps run concurrently with the compute warps' commit
+          fieldStores(tid - nCompute, nThreads - nCompute);
+        } else {
+          const int rounds = (count + nCompute - 1) / nCompute;
+          for (int r = 0; r < rounds; ++r) {
+            const int idx = r * nCompute + tid;
+            if (idx - lane >= count) break;  // warp-uniform: nothing left for this warp
+            const bool valid = idx < count;
+            const uint32_t cand = valid ? candArr[idx] : 0u;
+            const uint32_t pm = valid ? pmArr[idx] : 0u;
+            const uint2 ent = lcur[valid ? idx : 0];
+            const uint32_t e = ent.x;
+            const int ty = (int)(e >> 16), tx = (int)(e & 0xffffu);
+            const int C = ty * TWc + tx;
+            const int F = ty * TW + tx;
+            uint32_t wmask = 0;  // bit k: this entry appends neighbour k (0 = itself)
+            if (cand) {
+              const uint8_t id = (uint8_t)idx;
+              if (claim[C] == id) wmask |= 1;
+              if ((pm & 2) && claim[C - TWc] == id) wmask |= 2;
+              if ((pm & 4) && claim[C + TWc] == id) wmask |= 4;
+              if ((pm & 8) && claim[C - 1] == id) wmask |= 8;
+              if ((pm & 16) && claim[C + 1] == id) wmask |= 16;
+              vis[ty * TWv + tx] |= cand;
+            }
+            // free words of the tiles this entry appends (the next level then
+            // runs out of shared memory only); the loads complete behind the
+            // slot allocation
+            uint32_t f1 = 0, f2 = 0, f3 = 0, f4 = 0;
+            if (wmask & 2u) f1 = __ldg(&p.free84[F - TW]);
+            if (wmask & 4u) f2 = __ldg(&p.free84[F + TW]);
+            if (wmask & 8u) f3 = __ldg(&p.free84[F - 1]);
+            if (wmask & 16u) f4 = __ldg(&p.free84[F + 1]);
+            TICK(6);
+            // slot allocation: ballots rank the winners, one atomic per warp
+            const uint32_t b0 = __ballot_sync(0xffffffffu, wmask & 1u);
+            const uint32_t b1 = __ballot_sync(0xffffffffu, wmask & 2u);
+            const uint32_t b2 = __ballot_sync(0xffffffffu, wmask & 4u);
+            const uint32_t b3 = __ballot_sync(0xffffffffu, wmask & 8u);
+            const uint32_t b4 = __ballot_sync(0xffffffffu, wmask & 16u);
+            const int n0 = __popc(b0), n1 = __popc(b1), n2 = __popc(b2), n3 = __popc(b3);
+            const int total = n0 + n1 + n2 + n3 + __popc(b4);
+            int base = 0;
+            if (total) {
+              if (lane == 0) base = atomicAdd(&sCount[nxt], total);
+              base = __shfl_sync(0xffffffffu, base, 0);
+              if (base + total > cap) {
+                if (lane == 0) sOverflow = 1;
+                wmask = 0;
+              }
+            }
+            TICK(7);
+            if (wmask & 1u) lnxt[base + __popc(b0 & ltMask)] = make_uint2(e, ent.y);
+            if (wmask & 2u) lnxt[base + n0 + __popc(b1 & ltMask)] = make_uint2(e - 0x10000u, f1);
+            if (wmask & 4u)
+              lnxt[base + n0 + n1 + __popc(b2 & ltMask)] = make_uint2(e + 0x10000u, f2);
+            if (wmask & 8u)
+              lnxt[base + n0 + n1 + n2 + __popc(b3 & ltMask)] = make_uint2(e - 1u, f3);
+            if (wmask & 16u)
+              lnxt[base + n0 + n1 + n2 + n3 + __popc(b4 & ltMask)] = make_uint2(e + 1u, f4);
+          }
+          if (nCompute == nThreads) fieldStores(tid, nThreads);  // small blocks: no split
         }
         TICK(8);
         TICK(3);
@@ -341,7 +364,7 @@ static TileGeom tileGeometry(const mrp_map_s* map) {
   if (t.TW < 124) t.TWc = (t.TW + 3) & ~3;
   // block size: a power of two (the striped list addressing uses shifts)
   int th = 128;
-  while (th < 512 && th * 32 < t.nTiles) th <<= 1;
+  while (th < 1024 && th * 32 < t.nTiles) th <<= 1;
   if (const char* e = getenv("MRP_BFS_THREADS")) th = atoi(e);
   t.threads = th;
   auto roundUp = [th](size_t n) { return (n + th - 1) / th * th; };
@@ -403,6 +426,8 @@ int launchBfsLarge(const mrp_map_s* map, const int32_t* d_goal_cell, int n_goals
   p.TWc = t.TWc;
   p.cap = t.cap;
   p.spillCap = t.spillCap;
+  p.nCompute = t.threads >= 256 ? t.threads / 2 : t.threads;
+  if (const char* e = getenv("MRP_BFS_COMPUTE")) p.nCompute = atoi(e);
   p.dbg = getenv("MRP_BFS_DBG") ? atoi(getenv("MRP_BFS_DBG")) : 0;
   MRP_CUDA(cudaMemsetAsync(d_ws, 0, kWsHeaderWords * 4, st));
   int blocks = tileBlocks(t, t.smemState);
