@@ -27,6 +27,8 @@
 #include <array>
 #include <chrono>
 #include <cstdint>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <memory>
@@ -77,6 +79,16 @@ struct SolveOptions {
 
 enum class Algo { CBS = 0, ECBS = 1, CBSTA = 2 };
 
+// wall-clock split of a batch run, printed when MRP_HOST_PROFILE is set
+struct HostProfile {
+  double gpuConflicts = 0, gpuLowLevel = 0, total = 0;
+  long iterations = 0, nodes = 0, jobs = 0;
+};
+inline double nowSeconds() {
+  return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch())
+      .count();
+}
+
 inline void gpuCheck(int rc) {
   if (rc < 0) throw std::runtime_error(std::string("mrp_b200: ") + mrp_last_error());
 }
@@ -98,6 +110,8 @@ class BatchSolver {
     }
   }
   ~BatchSolver() {
+    for (Inst& I : m_inst)
+      for (Node* n : I.open) delete n;
     if (m_fields) mrp_fieldset_destroy(m_fields);
     for (mrp_map m : m_maps) mrp_map_destroy(m);
   }
@@ -113,10 +127,12 @@ class BatchSolver {
       return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
     };
     std::vector<Node*> fresh;
+    const double tRun = nowSeconds();
     buildRoots(fresh);
     while (true) {
+      ++m_prof.iterations;
       evaluate(fresh);
-      for (Node* n : fresh) m_inst[n->inst].open.emplace_back(n);
+      for (Node* n : fresh) m_inst[n->inst].open.insert(n);
       fresh.clear();
       // one expansion per running instance
       std::vector<Pending> pending;
@@ -149,6 +165,14 @@ class BatchSolver {
       expand(pending, fresh);
     }
     for (size_t k = 0; k < m_inst.size(); ++k) out[k] = std::move(m_inst[k].res);
+    m_prof.total = nowSeconds() - tRun;
+    if (getenv("MRP_HOST_PROFILE"))
+      fprintf(stderr,
+              "[mrp_host] %zu instances, %ld lock-step iterations, %ld nodes, %ld replans: "
+              "total %.3fs = conflicts(gpu call) %.3fs + replans(gpu call) %.3fs + host %.3fs\n",
+              m_inst.size(), m_prof.iterations, m_prof.nodes, m_prof.jobs, m_prof.total,
+              m_prof.gpuConflicts, m_prof.gpuLowLevel,
+              m_prof.total - m_prof.gpuConflicts - m_prof.gpuLowLevel);
     return out;
   }
 
@@ -157,10 +181,15 @@ class BatchSolver {
     std::vector<int32_t> vc;  // (time, cell) pairs
     std::vector<int32_t> ec;  // (time, from, to) triples
   };
+  // Children share every path / constraint list they do not change (the
+  // reference deep-copies the whole node, cbs.hpp:144; sharing is invisible in
+  // the results and removes the O(N*T) copy per child).
+  typedef std::shared_ptr<const AgentPath> PathPtr;
+  typedef std::shared_ptr<const ConsList> ConsPtr;
   struct Node {
     int inst = 0;
-    std::vector<AgentPath> paths;
-    std::vector<ConsList> cons;
+    std::vector<PathPtr> paths;
+    std::vector<ConsPtr> cons;
     std::vector<int> task;  // goal cell per agent (-1: none)
     long cost = 0, LB = 0;
     int focal = 0;
@@ -169,9 +198,14 @@ class BatchSolver {
     int found = 0;
     mrp_conflict conflict;
   };
+  struct OpenOrder {  // lowest cost (cbs.hpp:187-191), then lowest id
+    bool operator()(const Node* a, const Node* b) const {
+      return std::make_pair(a->cost, a->id) < std::make_pair(b->cost, b->id);
+    }
+  };
   struct Inst {
     const MapfInstance* in = nullptr;
-    std::vector<std::unique_ptr<Node> > open;
+    std::set<Node*, OpenOrder> open;  // owning
     int nextId = 0;
     bool done = false;
     int mapIdx = 0;
@@ -266,47 +300,44 @@ class BatchSolver {
     I.res.status = status;
     I.res.runtime = t;
     if (n) {
-      I.res.paths = n->paths;
       for (const auto& p : n->paths) {  // example/cbs.cpp:630-635
-        I.res.cost += p.cost;
-        I.res.makespan = std::max<long>(I.res.makespan, p.cost);
-        I.res.lowerBound += p.fmin;
+        I.res.paths.push_back(*p);
+        I.res.cost += p->cost;
+        I.res.makespan = std::max<long>(I.res.makespan, p->cost);
+        I.res.lowerBound += p->fmin;
       }
     }
+    for (Node* o : I.open) delete o;
     I.open.clear();
   }
 
   std::unique_ptr<Node> popBest(Inst& I) {
-    size_t best = 0;
+    auto best = I.open.begin();
     if (m_algo == Algo::ECBS) {
-      long minLB = I.open[0]->LB;
-      for (const auto& n : I.open) minLB = std::min(minLB, n->LB);
+      long minLB = (*best)->LB;
+      for (const Node* n : I.open) minLB = std::min(minLB, n->LB);
       const float bound = (float)minLB * m_opt.w;  // fp32 like ecbs.hpp:181
       bool have = false;
-      for (size_t k = 0; k < I.open.size(); ++k) {
-        const Node& n = *I.open[k];
-        if (!((float)n.cost <= bound)) continue;
+      for (auto it = I.open.begin(); it != I.open.end(); ++it) {
+        const Node& n = **it;
+        if (!((float)n.cost <= bound)) break;  // the set is ordered by cost
         // FOCAL order: focalHeuristic, then cost (ecbs.hpp:344-352), then id
         if (!have || std::make_tuple(n.focal, n.cost, n.id) <
-                         std::make_tuple(I.open[best]->focal, I.open[best]->cost,
-                                         I.open[best]->id)) {
-          best = k;
+                         std::make_tuple((*best)->focal, (*best)->cost, (*best)->id)) {
+          best = it;
           have = true;
         }
       }
       if (!have) {  // cannot happen (the min-LB node always qualifies); stay safe
-        for (size_t k = 1; k < I.open.size(); ++k)
-          if (I.open[k]->LB < I.open[best]->LB) best = k;
+        for (auto it = I.open.begin(); it != I.open.end(); ++it)
+          if ((*it)->LB == minLB) {
+            best = it;
+            break;
+          }
       }
-    } else {
-      for (size_t k = 1; k < I.open.size(); ++k)  // lowest cost (cbs.hpp:187-191), then id
-        if (std::make_pair(I.open[k]->cost, I.open[k]->id) <
-            std::make_pair(I.open[best]->cost, I.open[best]->id))
-          best = k;
     }
-    std::unique_ptr<Node> n = std::move(I.open[best]);
-    I.open[best] = std::move(I.open.back());
-    I.open.pop_back();
+    std::unique_ptr<Node> n(*best);
+    I.open.erase(best);
     return n;
   }
 
@@ -344,12 +375,15 @@ class BatchSolver {
     prm.path_cap = m_pathCap;
     std::vector<mrp_path_info> info(specs.size());
     std::vector<int32_t> cells(specs.size() * (size_t)m_pathCap), gs(cells.size());
+    const double tg = nowSeconds();
+    m_prof.jobs += (long)specs.size();
     gpuCheck(mrp_lowlevel_batch_fs(m_maps.data(), (int)m_maps.size(), m_fields, vc.data(),
                                    (int)vc.size() / 2, ec.data(), (int)ec.size() / 3,
                                    tables.empty() ? nullptr : tables.data(),
                                    tlen.empty() ? nullptr : tlen.data(), (int)tableNodes.size(), N,
                                    Tpad, jobs.data(), (int)jobs.size(), &prm, info.data(),
                                    cells.data(), gs.data()));
+    m_prof.gpuLowLevel += nowSeconds() - tg;
     for (size_t k = 0; k < specs.size(); ++k) {
       JobOut& o = out[k];
       o.status = info[k].status;
@@ -371,13 +405,15 @@ class BatchSolver {
     Tpad = 1;
     for (const Node* n : nodes) {
       N = std::max(N, (int)n->paths.size());
-      for (const auto& p : n->paths) Tpad = std::max(Tpad, (int)p.cells.size());
+      for (const auto& p : n->paths)
+        if (p) Tpad = std::max(Tpad, (int)p->cells.size());
     }
     tables.assign(nodes.size() * (size_t)N * Tpad, 0);
     tlen.assign(nodes.size() * (size_t)N, 0);
     for (size_t b = 0; b < nodes.size(); ++b)
       for (size_t a = 0; a < nodes[b]->paths.size(); ++a) {
-        const auto& c = nodes[b]->paths[a].cells;
+        if (!nodes[b]->paths[a]) continue;  // not planned yet (ECBS root construction)
+        const auto& c = nodes[b]->paths[a]->cells;
         std::copy(c.begin(), c.end(), tables.begin() + (b * N + a) * (size_t)Tpad);
         tlen[b * N + a] = (int)c.size();
       }
@@ -396,8 +432,11 @@ class BatchSolver {
     // getFirstConflict bound: size-1 for cbs/ecbs (cbs.cpp:338-341), size for
     // cbs_ta (cbs_ta.cpp:372-375); focalHeuristic counts with the same table
     const int mode = m_algo == Algo::CBSTA ? 1 : 0;
+    const double tg = nowSeconds();
+    m_prof.nodes += B;
     gpuCheck(mrp_conflicts_batch(tables.data(), tlen.data(), B, N, Tpad, m_dimx, mode,
                                  found.data(), confl.data(), counts.data()));
+    m_prof.gpuConflicts += nowSeconds() - tg;
     for (int b = 0; b < B; ++b) {
       fresh[b]->found = found[b];
       fresh[b]->conflict = confl[b];
@@ -413,7 +452,7 @@ class BatchSolver {
       std::unique_ptr<Node> n(new Node());
       n->inst = (int)k;
       n->paths.resize(I.in->numAgents());
-      n->cons.resize(I.in->numAgents());
+      n->cons.assign(I.in->numAgents(), m_noCons);
       n->id = I.nextId++;
       n->isRoot = true;
       if (m_algo == Algo::CBSTA) {
@@ -438,7 +477,7 @@ class BatchSolver {
           if (!roots[k] || a >= m_inst[k].in->numAgents()) continue;
           const int goal = roots[k]->task[a];
           specs.push_back({(int)k, (int)a, goal, fieldFor(m_inst[k], (int)a, goal),
-                           &roots[k]->cons[a], (int)tabs.size(), (int)a});
+                           roots[k]->cons[a].get(), (int)tabs.size(), (int)a});
           tabs.push_back(roots[k].get());
         }
         std::vector<JobOut> outs;
@@ -452,7 +491,7 @@ class BatchSolver {
         for (size_t a = 0; a < m_inst[k].in->numAgents(); ++a) {
           const int goal = roots[k]->task[a];
           specs.push_back({(int)k, (int)a, goal, fieldFor(m_inst[k], (int)a, goal),
-                           &roots[k]->cons[a], -1, (int)a});
+                           roots[k]->cons[a].get(), -1, (int)a});
         }
       }
       std::vector<JobOut> outs;
@@ -473,7 +512,7 @@ class BatchSolver {
     Node& n = *roots[s.inst];
     n.cost += o.path.cost;
     n.LB += o.path.fmin;
-    n.paths[s.agent] = std::move(o.path);
+    n.paths[s.agent] = std::make_shared<const AgentPath>(std::move(o.path));
   }
 
   // ---- one expansion step for every pending parent -----------------------------
@@ -504,7 +543,7 @@ class BatchSolver {
         if (nextTasks(I, r->task)) {
           r->inst = pending[pi].inst;
           r->paths.resize(I.in->numAgents());
-          r->cons.resize(I.in->numAgents());
+          r->cons.assign(I.in->numAgents(), m_noCons);
           r->isRoot = true;
           ChildPlan cp;
           cp.pendingIdx = (int)pi;
@@ -513,7 +552,7 @@ class BatchSolver {
           cp.nJobs = I.in->numAgents();
           for (size_t a = 0; a < I.in->numAgents(); ++a)
             specs.push_back({pending[pi].inst, (int)a, r->task[a],
-                             fieldFor(I, (int)a, r->task[a]), &r->cons[a], -1, (int)a});
+                             fieldFor(I, (int)a, r->task[a]), r->cons[a].get(), -1, (int)a});
           cp.node = std::move(r);
           plans.push_back(std::move(cp));
         }
@@ -525,25 +564,27 @@ class BatchSolver {
       const int c2 = c.type == 1 ? c.x2 + m_dimx * c.y2 : -1;
       for (int side = 0; side < 2; ++side) {
         const int agent = side == 0 ? c.agent1 : c.agent2;
-        std::unique_ptr<Node> n(new Node(P));
+        std::unique_ptr<Node> n(new Node(P));  // shares paths / constraint lists
         n->isRoot = P.isRoot;
+        std::shared_ptr<ConsList> cl = std::make_shared<ConsList>(*P.cons[agent]);
         if (c.type == 0) {
-          n->cons[agent].vc.push_back(c.time);
-          n->cons[agent].vc.push_back(c1);
+          cl->vc.push_back(c.time);
+          cl->vc.push_back(c1);
         } else {
-          n->cons[agent].ec.push_back(c.time);
-          n->cons[agent].ec.push_back(side == 0 ? c1 : c2);
-          n->cons[agent].ec.push_back(side == 0 ? c2 : c1);
+          cl->ec.push_back(c.time);
+          cl->ec.push_back(side == 0 ? c1 : c2);
+          cl->ec.push_back(side == 0 ? c2 : c1);
         }
-        n->cost -= n->paths[agent].cost;
-        n->LB -= n->paths[agent].fmin;
+        n->cons[agent] = cl;
+        n->cost -= n->paths[agent]->cost;
+        n->LB -= n->paths[agent]->fmin;
         ChildPlan cp;
         cp.pendingIdx = (int)pi;
         cp.agent = agent;
         cp.firstJob = specs.size();
         cp.nJobs = 1;
         specs.push_back({pending[pi].inst, agent, n->task[agent],
-                         fieldFor(I, agent, n->task[agent]), &n->cons[agent], tableIdx, agent});
+                         fieldFor(I, agent, n->task[agent]), n->cons[agent].get(), tableIdx, agent});
         cp.node = std::move(n);
         plans.push_back(std::move(cp));
       }
@@ -568,7 +609,7 @@ class BatchSolver {
         const int a = specs[j].agent;
         n.cost += outs[j].path.cost;
         n.LB += outs[j].path.fmin;
-        n.paths[a] = std::move(outs[j].path);
+        n.paths[a] = std::make_shared<const AgentPath>(std::move(outs[j].path));
       }
       n.id = I.nextId++;
       fresh.push_back(cp.node.release());
@@ -590,6 +631,8 @@ class BatchSolver {
   std::vector<Inst> m_inst;
   std::vector<mrp_map> m_maps;
   mrp_fieldset m_fields = nullptr;
+  const ConsPtr m_noCons = std::make_shared<const ConsList>();
+  HostProfile m_prof;
 };
 
 }  // namespace mrp_host
