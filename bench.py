@@ -183,6 +183,55 @@ def descend_paths(torch, fields, inst, starts_cell, n_agents, max_t):
     return table.contiguous(), length.contiguous()
 
 
+def search_metrics(pkg):
+    """Instance throughput of the batched searches next to the oracle on one
+    host core (same caps).  ECBS: the 100-agent 32x32 files (config C3's base
+    case), w = 1.3.  CBS: the full 8x8 set (config C2) under an expansion cap."""
+    from oracle import orc
+    out = {}
+    g = os.path.join(ROOT, "tests", "golden")
+    s32 = pkg.instances.load_set(os.path.join(g, "bench_32x32.npz"))
+    s8 = pkg.instances.load_set(os.path.join(g, "bench_8x8.npz"))
+    insts = [i for i in s32 if i.n_agents == 100]
+    cap_hl = 2000
+    pkg.solver.solve_batch(pkg.solver.ECBS, insts[:2], w=1.3, max_hl=50)  # warm
+    t0 = time.perf_counter()
+    res = pkg.solver.solve_batch(pkg.solver.ECBS, insts, w=1.3, max_hl=cap_hl, max_seconds=120)
+    dt = time.perf_counter() - t0
+    ok = [r for r in res if r["status"] == 0]
+    out["ecbs_w1.3_instances_per_s"] = len(ok) / dt
+    out["ecbs_config"] = "32x32_obst204, 100 agents, %d instances in one lock-step batch, " \
+                         "cap %d high-level expansions" % (len(insts), cap_hl)
+    out["ecbs_solved"] = "%d/%d" % (len(ok), len(insts))
+    out["ecbs_seconds"] = dt
+    out["ecbs_max_cost_over_lb"] = max(r["cost"] / r["lower_bound"] for r in ok) if ok else None
+    n_cpu = 6
+    t0 = time.perf_counter()
+    cres = [orc.ecbs(i.dimx, i.dimy, i.obstacles, i.starts, i.goals, 1.3, (cap_hl, 0, 30.0))
+            for i in insts[:n_cpu]]
+    dt = time.perf_counter() - t0
+    out["ecbs_cpu_instances_per_s_1core"] = sum(r["status"] == 0 for r in cres) / dt
+    out["ecbs_cpu_sample"] = "%d instances, oracle port" % n_cpu
+    out["ecbs_cost_gpu_vs_cpu"] = [[a["cost"], b["cost"]] for a, b in zip(res, cres)]
+    cap_hl = 500
+    t0 = time.perf_counter()
+    res = pkg.solver.solve_batch(pkg.solver.CBS, s8, max_hl=cap_hl, max_seconds=120)
+    dt = time.perf_counter() - t0
+    out["cbs_8x8_solved"] = "%d/%d" % (sum(r["status"] == 0 for r in res), len(s8))
+    out["cbs_8x8_seconds"] = dt
+    out["cbs_8x8_hl_expansions_per_s"] = sum(r["hl_expanded"] for r in res) / dt
+    out["cbs_8x8_ll_expansions_per_s"] = sum(r["ll_expanded"] for r in res) / dt
+    sub = s8[::20]
+    t0 = time.perf_counter()
+    cres = [orc.cbs(i.dimx, i.dimy, i.obstacles, i.starts, i.goals, (cap_hl, 0, 5.0)) for i in sub]
+    dt = time.perf_counter() - t0
+    out["cbs_8x8_cpu_hl_expansions_per_s_1core"] = sum(r["hl_expanded"] for r in cres) / dt
+    mism = [i.name for i, a, b in zip(sub, res[::20], cres)
+            if a["status"] == 0 and b["status"] == 0 and a["cost"] != b["cost"]]
+    out["cbs_8x8_cost_mismatches_vs_oracle"] = len(mism)
+    return out
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -259,7 +308,7 @@ def run_ours(args):
         traffic = tj["dram_bytes_per_goal"] * G
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                "kernel": "bfs_large_kernel<true>", "algorithmic_bytes_per_launch": alg_bytes,
+                "kernel": "bfs_tiles_kernel<true>", "algorithmic_bytes_per_launch": alg_bytes,
                 "kernel_ms": kern_ms}
 
     # ---- also: conflict sweep of C5 (N = 4096 agents on their goal fields) ----
@@ -297,6 +346,10 @@ def run_ours(args):
             "conflict_table_gbps": N * Tpad * 4 / (cms * 1e-3) / 1e9,
         })
         del table, length
+
+    # ---- also: the search metrics (m3): ECBS w=1.3 instances/s, CBS over 8x8 ---
+    if rank == 0 and not args.skip_search:
+        also.update(search_metrics(pkg))
 
     # ---- optional all-gather of the fields over NVLink (north_star) -----------
     if world > 1 and args.allgather:
@@ -383,6 +436,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--skip-conflicts", action="store_true")
+    ap.add_argument("--skip-search", action="store_true")
     ap.add_argument("--allgather", action="store_true", default=True)
     args = ap.parse_args()
     if args.impl == "reference":
