@@ -242,6 +242,8 @@ def run_ours(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if world > 1:
+        # keep stdout to the one JSON line (NCCL_DEBUG=VERSION prints a banner)
+        os.environ["NCCL_DEBUG"] = "WARN"
         torch.cuda.set_device(local)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     else:
@@ -252,7 +254,9 @@ def run_ours(args):
     inst = c5_instance(world)
     cells = DIM * DIM
     G = GOALS_PER_GPU
-    goals_xy = inst.goals[rank * G:(rank + 1) * G]
+    from libmultirobotplanning_b200.sharding import shard_range
+    g0, g1 = shard_range(world * G, rank, world)  # goals shard by rank, no collective
+    goals_xy = inst.goals[g0:g1]
     goal_cells = (goals_xy[:, 0] + DIM * goals_xy[:, 1]).astype(np.int32)
     mp = capi.Map(DIM, DIM, inst.obstacles)
     d_goals = torch.from_numpy(goal_cells).to(dev)
