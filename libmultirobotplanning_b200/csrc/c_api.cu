@@ -107,7 +107,7 @@ struct Scratch {
     cap = 0;
   }
 };
-static Scratch g_scratch[12];
+static Scratch g_scratch[16];
 
 template <class T>
 static int scratch(int slot, size_t count, T** out) {
@@ -619,8 +619,12 @@ static int conflictsHost(const int32_t* cell, const int32_t* len, int B, int N, 
   if (int rc = scratch(9, (size_t)4 * B, &d_res)) return rc;
   MRP_CUDA(cudaMemcpyAsync(d_cell, cell, nCell * 4, cudaMemcpyHostToDevice, c.stream));
   MRP_CUDA(cudaMemcpyAsync(d_len, len, (size_t)B * N * 4, cudaMemcpyHostToDevice, c.stream));
+  char* d_ws = nullptr;
+  const size_t wsBytes = B == 1 ? conflictsWorkspaceBytes(N, Tpad) : 0;
+  if (wsBytes)
+    if (int rc2 = scratch(12, wsBytes, &d_ws)) return rc2;
   int rc = (B == 1) ? launchConflicts(d_cell, d_len, N, Tpad, mode, wantFirst, wantCount,
-                                      d_res, c.stream)
+                                      d_res, d_ws, wsBytes, c.stream)
                     : launchConflictsBatch(d_cell, d_len, B, N, Tpad, mode, d_res, c.stream);
   if (rc) return rc;
   std::vector<unsigned long long> res((size_t)4 * B);
@@ -678,8 +682,14 @@ int mrp_conflicts_dev(const int32_t* d_cell, const int32_t* d_len, int N, int Tp
             "bad table shape N=%d Tpad=%d", N, Tpad);
   MRP_CHECK(want_first || want_count, MRP_ERR_INVALID, "nothing requested");
   if (int rc = ensureInit()) return rc;
+  // large N runs the hashed formulation; its transposed table lives in a
+  // grow-only scratch buffer of the context (allocated on first use)
+  char* d_ws = nullptr;
+  const size_t wsBytes = conflictsWorkspaceBytes(N, Tpad);
+  if (wsBytes)
+    if (int rc = scratch(12, wsBytes, &d_ws)) return rc;
   return launchConflicts(d_cell, d_len, N, Tpad, mode, want_first != 0, want_count != 0,
-                         d_result, static_cast<cudaStream_t>(stream));
+                         d_result, d_ws, wsBytes, static_cast<cudaStream_t>(stream));
 }
 
 int mrp_focal_counts(const int32_t* cell, const int32_t* len, int N, int Tpad, int self,

@@ -104,9 +104,11 @@ int launchBfsSmall(const uint32_t* d_rows, const int32_t* d_dims,
 size_t bfsLargeWorkspaceBytes(const mrp_map_s* map, int n_goals);
 int launchBfsLarge(const mrp_map_s* map, const int32_t* d_goal_cell,
                    int n_goals, int32_t* d_out, void* d_ws, cudaStream_t st);
+size_t conflictsWorkspaceBytes(int N, int Tpad);
 int launchConflicts(const int32_t* d_cell, const int32_t* d_len, int N,
                     int Tpad, int mode, bool wantFirst, bool wantCount,
-                    unsigned long long* d_result, cudaStream_t st);
+                    unsigned long long* d_result, void* d_ws, size_t wsBytes,
+                    cudaStream_t st);
 int launchConflictsBatch(const int32_t* d_cell, const int32_t* d_len, int B,
                          int N, int Tpad, int mode,
                          unsigned long long* d_result, cudaStream_t st);

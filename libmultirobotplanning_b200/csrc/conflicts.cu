@@ -17,6 +17,8 @@
 // The first conflict is the minimum of the packed key (t, type, i, j) — the
 // exact iteration order of the reference loops — reduced with a 64-bit
 // atomicMin; counts are reduced per CTA and added with one atomic.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace mrp {
@@ -24,6 +26,15 @@ namespace mrp {
 constexpr int kPB = 64;        // agents per block side
 constexpr int kTC = 64;        // timesteps per chunk
 constexpr int kStride = kTC + 3;  // 67: odd => conflict-light column reads
+
+__device__ __forceinline__ unsigned long long warpMin64Key(unsigned long long v) {
+#pragma unroll
+  for (int o = 16; o; o >>= 1) {
+    const unsigned long long t = __shfl_xor_sync(0xffffffffu, v, o);
+    v = t < v ? t : v;
+  }
+  return v;
+}
 
 // result layout per table (4 x u64): [0] min key, [1] count, [2] max len, [3] -
 __global__ void conflict_prep_kernel(const int32_t* __restrict__ len, int N,
@@ -168,6 +179,218 @@ conflict_pairs_kernel(const int32_t* __restrict__ cellAll,
   }
 }
 
+// ---------------------------------------------------------------------------
+// Large N: per-timestep hashing, O(N*T) instead of O(N^2*T).
+//
+// Same answers as the pair loops (example/cbs.cpp:343-383, ecbs.cpp:315-350):
+//   vertex conflicts at t  = sum over cells of C(k, 2), k agents on the cell;
+//   edge conflicts at t    = pairs {i, j} whose moves are reverse to each other
+//                            (two agents resting on one cell count, as in the
+//                            reference's test state1a==state2b && state1b==state2a);
+//   first conflict         = min packed key (t, type, i, j): per cell the two
+//                            smallest agent ids, per move the smallest reverse mover.
+// One CTA per timestep; the N positions of that timestep come from a
+// transposed, already clamped copy of the table (coalesced), and are inserted
+// into an open-addressing table in shared memory (64-bit keys, atomicCAS).
+// ---------------------------------------------------------------------------
+constexpr int kHashThreads = 512;
+constexpr int kHashMaxN = 4096;          // table of 2*N slots x 16 B <= 128 KB
+constexpr int kHashMinN = 257;
+constexpr int kHashPerThread = kHashMaxN / kHashThreads;
+
+__global__ void conflict_transpose_kernel(const int32_t* __restrict__ cell,
+                                          const int32_t* __restrict__ len, int N, int Tpad,
+                                          int mode,
+                                          const unsigned long long* __restrict__ result,
+                                          int32_t* __restrict__ posT) {
+  __shared__ int32_t tile[32][33];
+  const int maxLen = (int)result[2];
+  const int rows = maxLen - (mode == 0 ? 1 : 0) + 1;  // t = 0 .. max_t
+  const int t0 = blockIdx.y * 32, i0 = blockIdx.x * 32;
+  if (t0 >= rows) return;
+  {
+    const int i = i0 + threadIdx.y, t = t0 + threadIdx.x;
+    int v = -2 - i;  // agents without a path never match anything
+    if (i < N) {
+      const int L = len[i];
+      if (L > 0) v = cell[(size_t)i * Tpad + min(t, L - 1)];
+    }
+    tile[threadIdx.y][threadIdx.x] = v;
+  }
+  __syncthreads();
+  {
+    const int t = t0 + threadIdx.y, i = i0 + threadIdx.x;
+    if (t < rows && i < N) posT[(size_t)t * N + i] = tile[threadIdx.x][threadIdx.y];
+  }
+}
+
+__device__ __forceinline__ uint32_t hash64(unsigned long long k) {
+  k ^= k >> 33;
+  k *= 0xff51afd7ed558ccdull;
+  k ^= k >> 33;
+  k *= 0xc4ceb9fe1a85ec53ull;
+  k ^= k >> 33;
+  return (uint32_t)k;
+}
+
+template <bool kFirst, bool kCount>
+__global__ void __launch_bounds__(kHashThreads)
+conflict_hash_kernel(const int32_t* __restrict__ posT, int N, int mode, int H,
+                     unsigned long long* __restrict__ result) {
+  extern __shared__ unsigned long long hsm[];
+  unsigned long long* key = hsm;                                   // [H]
+  uint32_t* cnt = reinterpret_cast<uint32_t*>(hsm + H);            // [H]
+  uint32_t* minId = cnt + H;                                       // [H]
+  __shared__ unsigned long long sBest[kHashThreads / 32];
+  __shared__ unsigned long long sSum[kHashThreads / 32];
+  const int t = blockIdx.x;
+  const int maxLen = (int)result[2];
+  const int max_t = maxLen - (mode == 0 ? 1 : 0);
+  if (t >= max_t) return;
+  if (kFirst && !kCount) {
+    const unsigned long long b = *(volatile unsigned long long*)&result[0];
+    if (b != kNoConflict && (int)(b >> 41) < t) return;
+  }
+  const uint32_t mask = (uint32_t)H - 1u;
+  const int32_t* rowA = posT + (size_t)t * N;
+  const int32_t* rowB = rowA + N;
+  const int tid = threadIdx.x;
+  constexpr unsigned long long kEmpty = ~0ull;
+
+  int a[kHashPerThread], b[kHashPerThread], slot[kHashPerThread];
+#pragma unroll
+  for (int k = 0; k < kHashPerThread; ++k) {
+    const int i = tid + k * kHashThreads;
+    a[k] = i < N ? rowA[i] : 0;
+    b[k] = i < N ? rowB[i] : 0;
+  }
+  unsigned long long best = kNoConflict, sum = 0;
+  unsigned int published = 0;  // keeps the returning atomics alive
+
+  // ---------------- vertex conflicts ----------------
+  for (int s = tid; s < H; s += kHashThreads) {
+    key[s] = kEmpty;
+    cnt[s] = 0;
+    minId[s] = 0xffffffffu;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < kHashPerThread; ++k) {
+    const int i = tid + k * kHashThreads;
+    if (i >= N) continue;
+    const unsigned long long kk = (unsigned long long)(uint32_t)a[k];
+    uint32_t s = hash64(kk) & mask;
+    while (true) {
+      const unsigned long long prev = atomicCAS(&key[s], kEmpty, kk);
+      if (prev == kEmpty || prev == kk) break;
+      s = (s + 1) & mask;
+    }
+    published += atomicAdd(&cnt[s], 1u);
+    published += atomicMin(&minId[s], (uint32_t)i);
+    slot[k] = (int)s;
+  }
+  // returning atomics + fence: every update of the table has been performed
+  // before the barrier publishes it (a run with fire-and-forget reductions
+  // here was observed to lose updates under heavy probing)
+  __threadfence_block();
+  __syncthreads();
+  if (kCount)
+    for (int s = tid; s < H; s += kHashThreads) {
+      const unsigned long long c = cnt[s];
+      sum += c * (c - 1) / 2;
+    }
+  if (kFirst) {
+#pragma unroll
+    for (int k = 0; k < kHashPerThread; ++k) {
+      const int i = tid + k * kHashThreads;
+      if (i >= N) continue;
+      const uint32_t m = minId[slot[k]];
+      if (cnt[slot[k]] >= 2 && m != (uint32_t)i)
+        best = min(best, conflictKey(t, 0, (int)m, i));
+    }
+  }
+  __syncthreads();
+  // ---------------- edge (swap) conflicts ----------------
+  for (int s = tid; s < H; s += kHashThreads) {
+    key[s] = kEmpty;
+    cnt[s] = 0;
+    minId[s] = 0xffffffffu;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < kHashPerThread; ++k) {
+    const int i = tid + k * kHashThreads;
+    if (i >= N) continue;
+    const unsigned long long kk =
+        ((unsigned long long)(uint32_t)a[k] << 32) | (unsigned long long)(uint32_t)b[k];
+    uint32_t s = hash64(kk) & mask;
+    while (true) {
+      const unsigned long long prev = atomicCAS(&key[s], kEmpty, kk);
+      if (prev == kEmpty || prev == kk) break;
+      s = (s + 1) & mask;
+    }
+    published += atomicAdd(&cnt[s], 1u);
+    published += atomicMin(&minId[s], (uint32_t)i);
+  }
+  __threadfence_block();
+  __syncthreads();
+  unsigned long long partners = 0;
+#pragma unroll
+  for (int k = 0; k < kHashPerThread; ++k) {
+    const int i = tid + k * kHashThreads;
+    if (i >= N) continue;
+    const unsigned long long rk =
+        ((unsigned long long)(uint32_t)b[k] << 32) | (unsigned long long)(uint32_t)a[k];
+    uint32_t s = hash64(rk) & mask;
+    while (true) {
+      const unsigned long long cur = *(volatile unsigned long long*)&key[s];
+      if (cur == kEmpty) break;
+      if (cur == rk) {
+        const uint32_t r = cnt[s];
+        if (a[k] == b[k]) {
+          partners += r - 1;  // resting agents on this cell, minus the agent itself
+        } else {
+          partners += r;
+          if (kFirst) {
+            const int m = (int)minId[s];
+            best = min(best, conflictKey(t, 1, min(i, m), max(i, m)));
+          }
+        }
+        break;
+      }
+      s = (s + 1) & mask;
+    }
+  }
+  // every unordered pair was seen from both sides
+  // ---------------- reductions ----------------
+  if (kFirst) {
+    best = warpMin64Key(best);
+    if ((tid & 31) == 0) sBest[tid >> 5] = best;
+  }
+  if (kCount) {
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+      sum += __shfl_xor_sync(0xffffffffu, sum, o);
+      partners += __shfl_xor_sync(0xffffffffu, partners, o);
+    }
+    if ((tid & 31) == 0) sSum[tid >> 5] = sum * 2 + partners;  // 2 * (vertex + edge pairs)
+  }
+  __syncthreads();
+  if (published == 0xdeadbeefu) result[3] = 1;  // result[3] is scratch: keeps `published` live
+  if (tid == 0) {
+    if (kFirst) {
+      unsigned long long bb = kNoConflict;
+      for (int w = 0; w < kHashThreads / 32; ++w) bb = min(bb, sBest[w]);
+      if (bb != kNoConflict) atomicMin(&result[0], bb);
+    }
+    if (kCount) {
+      unsigned long long tot = 0;
+      for (int w = 0; w < kHashThreads / 32; ++w) tot += sSum[w];
+      if (tot) atomicAdd(&result[1], tot / 2);
+    }
+  }
+}
+
 // focal counts: one warp per candidate move, lanes stride over the agents
 __global__ void focal_counts_kernel(const int32_t* __restrict__ cell,
                                     const int32_t* __restrict__ len, int N,
@@ -223,11 +446,40 @@ static int launchPairs(const int32_t* d_cell, const int32_t* d_len, int B, int N
   return 0;
 }
 
+size_t conflictsWorkspaceBytes(int N, int Tpad) {
+  if (N < kHashMinN || N > kHashMaxN) return 0;
+  return (size_t)(Tpad + 1) * N * 4;
+}
+
 int launchConflicts(const int32_t* d_cell, const int32_t* d_len, int N, int Tpad,
                     int mode, bool wantFirst, bool wantCount,
-                    unsigned long long* d_result, cudaStream_t st) {
-  return launchPairs(d_cell, d_len, 1, N, Tpad, mode, wantFirst, wantCount,
-                     d_result, st);
+                    unsigned long long* d_result, void* d_ws, size_t wsBytes,
+                    cudaStream_t st) {
+  const size_t need = conflictsWorkspaceBytes(N, Tpad);
+  if (need == 0 || d_ws == nullptr || wsBytes < need || getenv("MRP_CONFLICTS_ALLPAIRS"))
+    return launchPairs(d_cell, d_len, 1, N, Tpad, mode, wantFirst, wantCount, d_result, st);
+  // hashed path: prep (max len) -> transpose + clamp -> one CTA per timestep
+  int32_t* posT = static_cast<int32_t*>(d_ws);
+  conflict_prep_kernel<<<1, 256, 0, st>>>(d_len, N, d_result);
+  dim3 tg((N + 31) / 32, (Tpad + 1 + 31) / 32);
+  conflict_transpose_kernel<<<tg, dim3(32, 32), 0, st>>>(d_cell, d_len, N, Tpad, mode,
+                                                           d_result, posT);
+  int H = 512;
+  while (H < 2 * N) H <<= 1;
+  const size_t smem = (size_t)H * 16;
+  auto run = [&](auto kern) {
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    kern<<<Tpad, kHashThreads, smem, st>>>(posT, N, mode, H, d_result);
+  };
+  if (wantFirst && wantCount)
+    run(conflict_hash_kernel<true, true>);
+  else if (wantFirst)
+    run(conflict_hash_kernel<true, false>);
+  else
+    run(conflict_hash_kernel<false, true>);
+  countLaunch(3);
+  MRP_CUDA(cudaGetLastError());
+  return 0;
 }
 
 int launchConflictsBatch(const int32_t* d_cell, const int32_t* d_len, int B,

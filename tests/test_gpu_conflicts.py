@@ -20,7 +20,8 @@ def _random_table(rng, N, T, n_cells, ragged=True):
 
 @pytest.mark.parametrize("N,T,cells", [(2, 2, 3), (3, 9, 4), (10, 45, 40), (65, 70, 300),
                                         (100, 130, 1024), (130, 33, 90), (200, 257, 1024),
-                                        (513, 64, 5000)])
+                                        (257, 40, 300), (513, 64, 5000), (700, 35, 400),
+                                        (1500, 20, 900)])
 @pytest.mark.parametrize("mode", [0, 1])
 def test_random_tables(capi, orc, N, T, cells, mode):
     rng = np.random.default_rng(N * 7919 + T * 31 + mode)
@@ -116,3 +117,46 @@ def test_large_table_properties(capi, orc):
     sub = np.r_[0:64, 100, 3000, 4000]
     assert capi.count_conflicts(cell[sub], ln[sub], 0) == orc.count_conflicts(cell[sub], ln[sub], 0)
     assert capi.first_conflict(cell[sub], ln[sub], 1024, 0) == orc.first_conflict(cell[sub], ln[sub], 1024, 0)
+
+
+def test_hashed_path_equals_all_pairs(capi, orc, monkeypatch):
+    """N in (256, 4096] runs the per-timestep hashing kernels; they must agree
+    with the all-pairs kernel (forced through MRP_CONFLICTS_ALLPAIRS) and, on a
+    size the oracle can do, with the oracle — including dense pile-ups, resting
+    agents and agents without a path."""
+    rng = np.random.default_rng(9)
+    for N, T, cells in ((300, 50, 200), (1024, 60, 3000), (4096, 40, 100000)):
+        cell, ln = _random_table(rng, N, T, cells)
+        ln[3] = 0
+        cell[10, :], ln[10] = cell[11, 0], T        # resting on agent 11's start
+        cell[11, :], ln[11] = cell[11, 0], T
+        cell[12, :], ln[12] = cell[11, 0], T
+        for mode in (0, 1):
+            f_h = capi.first_conflict(cell, ln, 32, mode)
+            c_h = capi.count_conflicts(cell, ln, mode)
+            monkeypatch.setenv("MRP_CONFLICTS_ALLPAIRS", "1")
+            f_p = capi.first_conflict(cell, ln, 32, mode)
+            c_p = capi.count_conflicts(cell, ln, mode)
+            monkeypatch.delenv("MRP_CONFLICTS_ALLPAIRS")
+            assert (f_h, c_h) == (f_p, c_p), (N, mode)
+            if N <= 1024:
+                assert f_h == orc.first_conflict(cell, ln, 32, mode)
+                assert c_h == orc.count_conflicts(cell, ln, mode)
+
+
+def test_hashed_path_stress_high_load(capi, orc):
+    """The hashed tables run at a load factor of ~0.5 when N approaches 4096;
+    an early version lost table updates there (fire-and-forget shared-memory
+    reductions racing the barrier).  Repeat on fresh random moves."""
+    rng = np.random.default_rng(77)
+    for trial in range(25):
+        N, cells = ((4000, 30000), (4096, 50000), (3900, 8000))[trial % 3]
+        a = rng.integers(0, cells, N).astype(np.int32)
+        b = np.clip(a + rng.integers(-1, 2, N), 0, cells - 1).astype(np.int32)
+        cell = np.stack([a, b], 1).astype(np.int32)
+        ln = np.full(N, 2, np.int32)
+        want_c = orc.count_conflicts(cell, ln, 0)
+        want_f = orc.first_conflict(cell, ln, 1000, 0)
+        for _ in range(3):
+            assert capi.count_conflicts(cell, ln, 0) == want_c
+        assert capi.first_conflict(cell, ln, 1000, 0) == want_f
