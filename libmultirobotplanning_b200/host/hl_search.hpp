@@ -82,6 +82,7 @@ enum class Algo { CBS = 0, ECBS = 1, CBSTA = 2 };
 // wall-clock split of a batch run, printed when MRP_HOST_PROFILE is set
 struct HostProfile {
   double gpuConflicts = 0, gpuLowLevel = 0, total = 0;
+  double pop = 0, build = 0, llPack = 0, llUnpack = 0, evalPack = 0, absorb = 0;
   long iterations = 0, nodes = 0, jobs = 0;
 };
 inline double nowSeconds() {
@@ -137,30 +138,38 @@ class BatchSolver {
       // one expansion per running instance
       std::vector<Pending> pending;
       bool anyRunning = false;
+      const double tPop = nowSeconds();
       const bool timeUp = m_opt.maxSeconds > 0 && elapsed() > m_opt.maxSeconds;
-      for (size_t k = 0; k < m_inst.size(); ++k) {
+      const double tNow = elapsed();
+      std::vector<std::unique_ptr<Node> > popped(m_inst.size());
+      for (long k = 0; k < (long)m_inst.size(); ++k) {
         Inst& I = m_inst[k];
         if (I.done) continue;
         if (I.open.empty()) {
-          finish(I, kNoSolution, nullptr, elapsed());
+          finish(I, kNoSolution, nullptr, tNow);
           continue;
         }
         if (timeUp || (m_opt.maxHlExpanded > 0 && I.res.hlExpanded >= m_opt.maxHlExpanded)) {
-          finish(I, kCapped, nullptr, elapsed());
+          finish(I, kCapped, nullptr, tNow);
           continue;
         }
         std::unique_ptr<Node> P = popBest(I);
         ++I.res.hlExpanded;  // onExpandHighLevelNode, cbs.hpp:121
         if (!P->found) {
-          finish(I, kSolved, P.get(), elapsed());
+          finish(I, kSolved, P.get(), tNow);
           continue;
         }
+        popped[k] = std::move(P);
+      }
+      for (size_t k = 0; k < m_inst.size(); ++k) {
+        if (!popped[k]) continue;
         anyRunning = true;
         Pending pd;
         pd.inst = (int)k;
-        pd.parent = std::move(P);
+        pd.parent = std::move(popped[k]);
         pending.push_back(std::move(pd));
       }
+      m_prof.pop += nowSeconds() - tPop;
       if (!anyRunning) break;
       expand(pending, fresh);
     }
@@ -169,10 +178,12 @@ class BatchSolver {
     if (getenv("MRP_HOST_PROFILE"))
       fprintf(stderr,
               "[mrp_host] %zu instances, %ld lock-step iterations, %ld nodes, %ld replans: "
-              "total %.3fs = conflicts(gpu call) %.3fs + replans(gpu call) %.3fs + host %.3fs\n",
+              "total %.3fs = conflicts(gpu call) %.3fs + replans(gpu call) %.3fs + host %.3fs "
+              "[pop %.2f build %.2f llPack %.2f llUnpack %.2f evalPack %.2f absorb %.2f]\n",
               m_inst.size(), m_prof.iterations, m_prof.nodes, m_prof.jobs, m_prof.total,
               m_prof.gpuConflicts, m_prof.gpuLowLevel,
-              m_prof.total - m_prof.gpuConflicts - m_prof.gpuLowLevel);
+              m_prof.total - m_prof.gpuConflicts - m_prof.gpuLowLevel, m_prof.pop, m_prof.build,
+              m_prof.llPack, m_prof.llUnpack, m_prof.evalPack, m_prof.absorb);
     return out;
   }
 
@@ -346,6 +357,7 @@ class BatchSolver {
                    std::vector<JobOut>& out) {
     out.assign(specs.size(), JobOut());
     if (specs.empty()) return;
+    const double tPack = nowSeconds();
     std::vector<mrp_job> jobs(specs.size());
     std::vector<int32_t> vc, ec;
     for (size_t k = 0; k < specs.size(); ++k) {
@@ -376,6 +388,7 @@ class BatchSolver {
     std::vector<mrp_path_info> info(specs.size());
     std::vector<int32_t> cells(specs.size() * (size_t)m_pathCap), gs(cells.size());
     const double tg = nowSeconds();
+    m_prof.llPack += tg - tPack;
     m_prof.jobs += (long)specs.size();
     gpuCheck(mrp_lowlevel_batch_fs(m_maps.data(), (int)m_maps.size(), m_fields, vc.data(),
                                    (int)vc.size() / 2, ec.data(), (int)ec.size() / 3,
@@ -383,7 +396,8 @@ class BatchSolver {
                                    tlen.empty() ? nullptr : tlen.data(), (int)tableNodes.size(), N,
                                    Tpad, jobs.data(), (int)jobs.size(), &prm, info.data(),
                                    cells.data(), gs.data()));
-    m_prof.gpuLowLevel += nowSeconds() - tg;
+    const double tUn = nowSeconds();
+    m_prof.gpuLowLevel += tUn - tg;
     for (size_t k = 0; k < specs.size(); ++k) {
       JobOut& o = out[k];
       o.status = info[k].status;
@@ -397,6 +411,7 @@ class BatchSolver {
         o.path.fmin = info[k].fmin;
       }
     }
+    m_prof.llUnpack += nowSeconds() - tUn;
   }
 
   void packTables(const std::vector<const Node*>& nodes, std::vector<int32_t>& tables,
@@ -410,7 +425,8 @@ class BatchSolver {
     }
     tables.assign(nodes.size() * (size_t)N * Tpad, 0);
     tlen.assign(nodes.size() * (size_t)N, 0);
-    for (size_t b = 0; b < nodes.size(); ++b)
+#pragma omp parallel for schedule(static)
+    for (long b = 0; b < (long)nodes.size(); ++b)
       for (size_t a = 0; a < nodes[b]->paths.size(); ++a) {
         if (!nodes[b]->paths[a]) continue;  // not planned yet (ECBS root construction)
         const auto& c = nodes[b]->paths[a]->cells;
@@ -422,10 +438,12 @@ class BatchSolver {
   // ---- conflicts of freshly created nodes ----------------------------------
   void evaluate(std::vector<Node*>& fresh) {
     if (fresh.empty()) return;
+    const double tEp = nowSeconds();
     std::vector<const Node*> nodes(fresh.begin(), fresh.end());
     std::vector<int32_t> tables, tlen;
     int N = 0, Tpad = 0;
     packTables(nodes, tables, tlen, N, Tpad);
+    m_prof.evalPack += nowSeconds() - tEp;
     const int B = (int)fresh.size();
     std::vector<int32_t> found(B), counts(B);
     std::vector<mrp_conflict> confl(B);
@@ -524,6 +542,7 @@ class BatchSolver {
       size_t firstJob, nJobs;
       bool failed = false;
     };
+    const double tBuild = nowSeconds();
     std::vector<ChildPlan> plans;
     std::vector<JobSpec> specs;
     std::vector<const Node*> tabs;
@@ -590,7 +609,9 @@ class BatchSolver {
       }
     }
     std::vector<JobOut> outs;
+    m_prof.build += nowSeconds() - tBuild;
     runLowLevel(specs, tabs, outs);
+    const double tAbs = nowSeconds();
     for (ChildPlan& cp : plans) {
       Inst& I = m_inst[pending[cp.pendingIdx].inst];
       if (I.done) continue;
@@ -614,6 +635,7 @@ class BatchSolver {
       n.id = I.nextId++;
       fresh.push_back(cp.node.release());
     }
+    m_prof.absorb += nowSeconds() - tAbs;
     // children of instances that were finished meanwhile must not leak
     for (auto it = fresh.begin(); it != fresh.end();) {
       if (m_inst[(*it)->inst].done) {
