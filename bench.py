@@ -213,6 +213,22 @@ def search_metrics(pkg):
     out["ecbs_cpu_instances_per_s_1core"] = sum(r["status"] == 0 for r in cres) / dt
     out["ecbs_cpu_sample"] = "%d instances, oracle port" % n_cpu
     out["ecbs_cost_gpu_vs_cpu"] = [[a["cost"], b["cost"]] for a, b in zip(res, cres)]
+    # smem-resident maps: all goals of all 1000 32x32 instances / 2000 8x8 instances
+    import torch
+    for tag, sset in (("32x32", s32), ("8x8", s8)):
+        pkg.capi.bfs_fields_batch(sset[:10])  # warm
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        fields = pkg.capi.bfs_fields_batch(sset)
+        dt = time.perf_counter() - t0
+        ncell = sum(f.size for f in fields)
+        out["bfs_%s_e2e_cells_per_s" % tag] = ncell / dt
+        out["bfs_%s_fields" % tag] = int(sum(len(f) for f in fields))
+    # the reference's own algorithm for this precompute: Floyd-Warshall over all
+    # cells (shortest_path_heuristic.hpp:47-53), oracle port, one 32x32 map
+    t0 = time.perf_counter()
+    orc.floyd_warshall(32, 32, s32[0].obstacles)
+    out["floyd_warshall_32x32_cpu_seconds_per_map"] = time.perf_counter() - t0
     cap_hl = 500
     t0 = time.perf_counter()
     res = pkg.solver.solve_batch(pkg.solver.CBS, s8, max_hl=cap_hl, max_seconds=120)
