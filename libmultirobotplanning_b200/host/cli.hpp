@@ -182,7 +182,8 @@ inline void writeOutput(std::ostream& out, const SolveResult& r, int dimx, bool 
 
 // shared main(): returns the process exit code
 inline int runCli(int argc, char** argv, Algo algo) {
-  const bool hasW = algo == Algo::ECBS, hasTA = algo == Algo::CBSTA;
+  const bool hasW = algo == Algo::ECBS || algo == Algo::ECBSTA;
+  const bool hasTA = algo == Algo::CBSTA || algo == Algo::ECBSTA;
   CliArgs args;
   std::string err;
   if (!parseArgs(argc, argv, hasW, hasTA, args, err)) {

@@ -77,7 +77,7 @@ struct SolveOptions {
   long maxTaskAssignments = 1000000000L;
 };
 
-enum class Algo { CBS = 0, ECBS = 1, CBSTA = 2 };
+enum class Algo { CBS = 0, ECBS = 1, CBSTA = 2, ECBSTA = 3 };
 
 // wall-clock split of a batch run, printed when MRP_HOST_PROFILE is set
 struct HostProfile {
@@ -135,6 +135,7 @@ class BatchSolver {
       evaluate(fresh);
       for (Node* n : fresh) m_inst[n->inst].open.insert(n);
       fresh.clear();
+      if (m_algo == Algo::ECBSTA) spawnMinRoots();
       // one expansion per running instance
       std::vector<Pending> pending;
       bool anyRunning = false;
@@ -209,6 +210,9 @@ class BatchSolver {
     int found = 0;
     mrp_conflict conflict;
   };
+  bool isTA() const { return m_algo == Algo::CBSTA || m_algo == Algo::ECBSTA; }
+  bool isFocal() const { return m_algo == Algo::ECBS || m_algo == Algo::ECBSTA; }
+
   struct OpenOrder {  // lowest cost (cbs.hpp:187-191), then lowest id
     bool operator()(const Node* a, const Node* b) const {
       return std::make_pair(a->cost, a->id) < std::make_pair(b->cost, b->id);
@@ -223,6 +227,7 @@ class BatchSolver {
     int fieldBase = 0;                 // first field of this instance in the set
     std::map<int, int> fieldOfGoal;    // goal cell -> field index (cbs_ta)
     std::unique_ptr<NextBestAssignment<int, int> > assignment;
+    long nextRootNodeCost = 0;  // ecbs_ta (STYLE_MINROOT, ecbs_ta.hpp:142,345)
     SolveResult res;
   };
   struct Pending {
@@ -251,7 +256,7 @@ class BatchSolver {
       I.mapIdx = (int)m_maps.size();
       m_maps.push_back(m);
       I.fieldBase = (int)goalCell.size();
-      if (m_algo == Algo::CBSTA) {
+      if (isTA()) {
         for (const auto& pg : in.potentialGoals)
           for (int g : pg)
             if (!I.fieldOfGoal.count(g)) {
@@ -270,7 +275,7 @@ class BatchSolver {
     // (Environment ctor, example/cbs_ta.cpp:254-281,570-578)
     gpuCheck(mrp_fieldset_create(m_maps.data(), (int)m_maps.size(), goalMap.data(),
                                  goalCell.data(), (int)goalCell.size(), &m_fields));
-    if (m_algo == Algo::CBSTA) {
+    if (isTA()) {
       for (Inst& I : m_inst) {
         const MapfInstance& in = *I.in;
         const int nf = (int)I.fieldOfGoal.size();
@@ -302,7 +307,7 @@ class BatchSolver {
 
   int fieldFor(const Inst& I, int agent, int goalCell) const {
     if (goalCell < 0) return -1;
-    if (m_algo == Algo::CBSTA) return I.fieldOfGoal.at(goalCell);
+    if (isTA()) return I.fieldOfGoal.at(goalCell);
     return I.fieldBase + agent;
   }
 
@@ -324,7 +329,22 @@ class BatchSolver {
 
   std::unique_ptr<Node> popBest(Inst& I) {
     auto best = I.open.begin();
-    if (m_algo == Algo::ECBS) {
+    if (m_algo == Algo::ECBSTA) {
+      // FOCAL rebuilt every iteration: cost <= nextRootNodeCost, best by
+      // (focalHeuristic, cost) — ecbs_ta.hpp:160-181,420-428; ties by id
+      bool have = false;
+      for (auto it = I.open.begin(); it != I.open.end(); ++it) {
+        const Node& n = **it;
+        if (!((float)n.cost <= (float)I.nextRootNodeCost)) break;  // ordered by cost
+        if (!have || std::make_tuple(n.focal, n.cost, n.id) <
+                         std::make_tuple((*best)->focal, (*best)->cost, (*best)->id)) {
+          best = it;
+          have = true;
+        }
+      }
+      // `have` is false only if the bound fell below the cheapest node; the
+      // reference would pop an empty FOCAL there — take the cheapest node
+    } else if (m_algo == Algo::ECBS) {
       long minLB = (*best)->LB;
       for (const Node* n : I.open) minLB = std::min(minLB, n->LB);
       const float bound = (float)minLB * m_opt.w;  // fp32 like ecbs.hpp:181
@@ -381,8 +401,8 @@ class BatchSolver {
     int N = 0, Tpad = 0;
     if (!tableNodes.empty()) packTables(tableNodes, tables, tlen, N, Tpad);
     mrp_lowlevel_params prm;
-    prm.variant = m_algo == Algo::CBSTA ? 1 : 0;
-    prm.w = m_algo == Algo::ECBS ? m_opt.w : 0.0f;
+    prm.variant = isTA() ? 1 : 0;
+    prm.w = isFocal() ? m_opt.w : 0.0f;
     prm.max_expanded = m_opt.maxLlExpanded;
     prm.path_cap = m_pathCap;
     std::vector<mrp_path_info> info(specs.size());
@@ -449,11 +469,19 @@ class BatchSolver {
     std::vector<mrp_conflict> confl(B);
     // getFirstConflict bound: size-1 for cbs/ecbs (cbs.cpp:338-341), size for
     // cbs_ta (cbs_ta.cpp:372-375); focalHeuristic counts with the same table
-    const int mode = m_algo == Algo::CBSTA ? 1 : 0;
+    const int mode = isTA() ? 1 : 0;
     const double tg = nowSeconds();
     m_prof.nodes += B;
     gpuCheck(mrp_conflicts_batch(tables.data(), tlen.data(), B, N, Tpad, m_dimx, mode,
                                  found.data(), confl.data(), counts.data()));
+    if (m_algo == Algo::ECBSTA) {
+      // ecbs_ta mixes the bounds: getFirstConflict uses max(size)
+      // (ecbs_ta.cpp:445), focalHeuristic max(size-1) (ecbs_ta.cpp:353)
+      std::vector<int32_t> found0(B);
+      std::vector<mrp_conflict> confl0(B);
+      gpuCheck(mrp_conflicts_batch(tables.data(), tlen.data(), B, N, Tpad, m_dimx, 0,
+                                   found0.data(), confl0.data(), counts.data()));
+    }
     m_prof.gpuConflicts += nowSeconds() - tg;
     for (int b = 0; b < B; ++b) {
       fresh[b]->found = found[b];
@@ -478,30 +506,17 @@ class BatchSolver {
           finish(I, kNoSolution, nullptr, 0);
           continue;
         }
+      } else if (m_algo == Algo::ECBSTA) {
+        nextTasks(I, n->task);  // ecbs_ta.hpp:104 plans even without an assignment
       } else {
         n->task.assign(I.in->goals.begin(), I.in->goals.end());
       }
       roots[k] = std::move(n);
     }
-    if (m_algo == Algo::ECBS) {
-      // agents one after the other, each seeing the already planned ones
-      // through the focal heuristics (ecbs.hpp:118-136)
-      size_t maxN = 0;
-      for (const Inst& I : m_inst) maxN = std::max(maxN, I.in->numAgents());
-      for (size_t a = 0; a < maxN; ++a) {
-        std::vector<JobSpec> specs;
-        std::vector<const Node*> tabs;
-        for (size_t k = 0; k < m_inst.size(); ++k) {
-          if (!roots[k] || a >= m_inst[k].in->numAgents()) continue;
-          const int goal = roots[k]->task[a];
-          specs.push_back({(int)k, (int)a, goal, fieldFor(m_inst[k], (int)a, goal),
-                           roots[k]->cons[a].get(), (int)tabs.size(), (int)a});
-          tabs.push_back(roots[k].get());
-        }
-        std::vector<JobOut> outs;
-        runLowLevel(specs, tabs, outs);
-        for (size_t j = 0; j < specs.size(); ++j) absorbRoot(roots, specs[j], outs[j]);
-      }
+    if (isFocal()) {
+      planSequential(roots, true);
+      for (size_t k = 0; k < m_inst.size(); ++k)
+        if (roots[k]) m_inst[k].nextRootNodeCost = (long)((float)roots[k]->LB * m_opt.w);
     } else {
       std::vector<JobSpec> specs;
       for (size_t k = 0; k < m_inst.size(); ++k) {
@@ -514,16 +529,43 @@ class BatchSolver {
       }
       std::vector<JobOut> outs;
       runLowLevel(specs, std::vector<const Node*>(), outs);
-      for (size_t j = 0; j < specs.size(); ++j) absorbRoot(roots, specs[j], outs[j]);
+      for (size_t j = 0; j < specs.size(); ++j) absorbRoot(roots, specs[j], outs[j], true);
     }
     for (size_t k = 0; k < m_inst.size(); ++k)
       if (roots[k]) fresh.push_back(roots[k].release());
   }
 
-  void absorbRoot(std::vector<std::unique_ptr<Node> >& roots, const JobSpec& s, JobOut& o) {
+  // Plans the agents of whole (root) nodes one after the other, each seeing the
+  // already planned ones through the focal heuristics (ecbs.hpp:118-136,
+  // ecbs_ta.hpp:107-126,318-330); nodes[k] belongs to instance k (may be null).
+  // initial == true: a failing search ends the instance (first root);
+  // otherwise the node is just dropped (later roots of ecbs_ta).
+  void planSequential(std::vector<std::unique_ptr<Node> >& nodes, bool initial) {
+    size_t maxN = 0;
+    for (size_t k = 0; k < nodes.size(); ++k)
+      if (nodes[k]) maxN = std::max(maxN, m_inst[k].in->numAgents());
+    for (size_t a = 0; a < maxN; ++a) {
+      std::vector<JobSpec> specs;
+      std::vector<const Node*> tabs;
+      for (size_t k = 0; k < nodes.size(); ++k) {
+        if (!nodes[k] || a >= m_inst[k].in->numAgents()) continue;
+        const int goal = nodes[k]->task[a];
+        specs.push_back({(int)k, (int)a, goal, fieldFor(m_inst[k], (int)a, goal),
+                         nodes[k]->cons[a].get(), (int)tabs.size(), (int)a});
+        tabs.push_back(nodes[k].get());
+      }
+      std::vector<JobOut> outs;
+      runLowLevel(specs, tabs, outs);
+      for (size_t j = 0; j < specs.size(); ++j) absorbRoot(nodes, specs[j], outs[j], initial);
+    }
+  }
+
+  void absorbRoot(std::vector<std::unique_ptr<Node> >& roots, const JobSpec& s, JobOut& o,
+                  bool initial) {
     if (!roots[s.inst]) return;
     if (o.status != 0) {  // cbs.hpp:96-100: a failing root search ends the search
-      finish(m_inst[s.inst], o.status == 2 ? kCapped : kNoSolution, nullptr, 0);
+      if (initial || o.status == 2)
+        finish(m_inst[s.inst], o.status == 2 ? kCapped : kNoSolution, nullptr, 0);
       roots[s.inst].reset();
       return;
     }
@@ -531,6 +573,45 @@ class BatchSolver {
     n.cost += o.path.cost;
     n.LB += o.path.fmin;
     n.paths[s.agent] = std::make_shared<const AgentPath>(std::move(o.path));
+  }
+
+  // ecbs_ta, STYLE_MINROOT (ecbs_ta.hpp:299-348): once the cheapest open node
+  // exceeds nextRootNodeCost the next-best assignment becomes a new root, then
+  // the bound is reset from the cheapest node's LB.
+  void spawnMinRoots() {
+    std::vector<std::unique_ptr<Node> > roots(m_inst.size());
+    std::vector<char> triggered(m_inst.size(), 0);
+    bool any = false;
+    for (size_t k = 0; k < m_inst.size(); ++k) {
+      Inst& I = m_inst[k];
+      if (I.done || I.open.empty()) continue;
+      if (!((*I.open.begin())->cost > I.nextRootNodeCost)) continue;
+      triggered[k] = 1;
+      std::unique_ptr<Node> r(new Node());
+      if (!nextTasks(I, r->task)) continue;
+      r->inst = (int)k;
+      r->paths.resize(I.in->numAgents());
+      r->cons.assign(I.in->numAgents(), m_noCons);
+      r->isRoot = true;
+      roots[k] = std::move(r);
+      any = true;
+    }
+    if (any) {
+      planSequential(roots, false);
+      std::vector<Node*> fresh;
+      for (size_t k = 0; k < m_inst.size(); ++k)
+        if (roots[k] && !m_inst[k].done) {
+          roots[k]->id = m_inst[k].nextId++;
+          fresh.push_back(roots[k].release());
+        }
+      evaluate(fresh);
+      for (Node* n : fresh) m_inst[n->inst].open.insert(n);
+    }
+    for (size_t k = 0; k < m_inst.size(); ++k) {
+      Inst& I = m_inst[k];
+      if (triggered[k] && !I.done && !I.open.empty())
+        I.nextRootNodeCost = (long)((float)(*I.open.begin())->LB * m_opt.w);
+    }
   }
 
   // ---- one expansion step for every pending parent -----------------------------
@@ -550,7 +631,7 @@ class BatchSolver {
       Inst& I = m_inst[pending[pi].inst];
       const Node& P = *pending[pi].parent;
       int tableIdx = -1;
-      if (m_algo == Algo::ECBS) {
+      if (isFocal()) {
         tableIdx = (int)tabs.size();
         tabs.push_back(&P);
       }

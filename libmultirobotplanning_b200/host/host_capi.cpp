@@ -18,7 +18,7 @@ extern "C" {
 
 const char* mrph_last_error(void) { return g_err.c_str(); }
 
-// algo: 0 cbs, 1 ecbs, 2 cbs_ta.  Instances are CSR-flattened:
+// algo: 0 cbs, 1 ecbs, 2 cbs_ta, 3 ecbs_ta.  Instances are CSR-flattened:
 // dims[n][2]; obst_off[n+1] into obst_xy[][2]; agent_off[n+1] into
 // start_cell[] / goal_cell[]; cbs_ta: pg_off[total_agents+1] into pg_cell[].
 // Outputs per instance; paths: path_off[total_agents+1] into path_cell/path_g.
@@ -39,7 +39,7 @@ int mrph_solve_batch(int algo, int n_inst, const int32_t* dims, const int32_t* o
       in.obstXY.assign(obst_xy + 2 * obst_off[k], obst_xy + 2 * obst_off[k + 1]);
       for (int a = agent_off[k]; a < agent_off[k + 1]; ++a) {
         in.starts.push_back(start_cell[a]);
-        if (algo == 2)
+        if (algo == 2 || algo == 3)
           in.potentialGoals.emplace_back(pg_cell + pg_off[a], pg_cell + pg_off[a + 1]);
         else
           in.goals.push_back(goal_cell[a]);

@@ -12,7 +12,7 @@ from . import _capi
 _PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_PKG, "libmrp_host.so")
 BIN_DIR = os.path.join(os.path.dirname(_PKG), "bin")
-CBS, ECBS, CBS_TA = 0, 1, 2
+CBS, ECBS, CBS_TA, ECBS_TA = 0, 1, 2, 3
 SOLVED, NO_SOLUTION, CAPPED = 0, 1, 2
 
 _lib = None
@@ -56,7 +56,7 @@ def solve_batch(algo, instances, w=1.0, max_hl=0, max_ll=8000, max_seconds=0.0,
     starts = _i32(np.concatenate([i.cell(np.asarray(i.starts)) for i in instances]) if n else [])
     goals = pg_off = pg_cell = None
     total = int(aoff[-1])
-    if algo == CBS_TA:
+    if algo in (CBS_TA, ECBS_TA):
         pg_off = np.zeros(total + 1, np.int32)
         cells = []
         a = 0

@@ -1187,6 +1187,147 @@ static int cbsTaSearch(const Grid& grid, const std::vector<int>& starts,
   return fail(ORC_NO_SOLUTION);
 }
 
+
+// ---------------------------------------------------------------------------
+// ECBS-TA — ecbs_ta.hpp:94-352 with REBUILT_FOCAL_LIST and STYLE_MINROOT (both
+// defined on, ecbs_ta.hpp:8,11) and the Environment of example/ecbs_ta.cpp
+// (cbs_ta moves + the ecbs focal heuristics; getFirstConflict with the
+// cbs_ta bound, focalHeuristic with the cbs bound — ecbs_ta.cpp:353,445).
+// ---------------------------------------------------------------------------
+static int ecbsTaSearch(const Grid& grid, const std::vector<int>& starts,
+                        const std::vector<std::vector<int>>& potentialGoals, float w,
+                        int64_t maxTaskAssignments, Caps caps, std::vector<Plan>& solution,
+                        orc_result* res) {
+  const size_t N = starts.size();
+  const int V = grid.cells();
+  std::vector<int32_t> apsp((size_t)V * V);
+  floydWarshall(grid, apsp.data());
+  NextBestAssignment nba;
+  for (size_t i = 0; i < N; ++i)
+    for (int goal : potentialGoals[i])
+      nba.setCost((int)i, goal, apsp[(size_t)starts[i] * V + goal]);
+  nba.solve();
+  int64_t numTA = 0;
+  auto nextTaskAssignment = [&](std::map<int, int>& tasks) {
+    if ((uint64_t)numTA > (uint64_t)maxTaskAssignments) return;
+    nba.nextSolution(tasks);
+    if (!tasks.empty()) ++numTA;
+  };
+  caps.start();
+  LowLevelEnv env;
+  env.grid = &grid;
+  env.variant = 1;
+  int64_t hl = 0;
+  auto fail = [&](int status) {
+    res->hl_expanded = hl;
+    res->ll_expanded = env.expanded;
+    res->n_task_assignments = numTA;
+    res->runtime_s = caps.elapsed();
+    return status;
+  };
+  auto planAll = [&](HLNode& n) -> int {  // agents one after the other (ecbs_ta.hpp:107-126)
+    for (size_t i = 0; i < N; ++i) {
+      auto it = n.tasks.find((int)i);
+      const int goal = it == n.tasks.end() ? -1 : it->second;
+      env.setContext((int)i, &n.constraints[i], goal);
+      env.field = goal >= 0 ? apsp.data() + (size_t)goal * V : nullptr;
+      env.solution = &n.solution;
+      int st = aStarEpsilon(env, w, starts[i], n.solution[i], caps.maxLL);
+      if (st != ORC_SOLVED) return st;
+      n.cost += n.solution[i].cost;
+      n.LB += n.solution[i].fmin;
+    }
+    n.focal = countConflicts(n.solution);
+    return ORC_SOLVED;
+  };
+  HLNode start;
+  start.solution.resize(N);
+  start.constraints.resize(N);
+  start.isRoot = true;
+  nextTaskAssignment(start.tasks);
+  {
+    int st = planAll(start);
+    if (st != ORC_SOLVED) return fail(st);
+  }
+  int nextRootNodeCost = (int)(start.LB * w);  // Cost = float product, ecbs_ta.hpp:142
+  std::vector<HLNode> open;  // small: linear scans stand in for the two heaps
+  open.push_back(start);
+  int id = 1;
+  auto topOf = [&]() {
+    size_t b = 0;
+    for (size_t k = 1; k < open.size(); ++k)
+      if (open[k].cost < open[b].cost) b = k;
+    return b;
+  };
+  while (!open.empty()) {
+    if ((caps.maxHL > 0 && hl >= caps.maxHL) || caps.timeUp()) return fail(ORC_CAPPED);
+    // FOCAL rebuilt every iteration: nodes with cost <= nextRootNodeCost,
+    // best by (focalHeuristic, cost) — ecbs_ta.hpp:160-181,420-428
+    int best = -1;
+    for (size_t k = 0; k < open.size(); ++k) {
+      if (!((float)open[k].cost <= (float)nextRootNodeCost)) continue;
+      if (best < 0 || std::make_pair(open[k].focal, open[k].cost) <
+                          std::make_pair(open[best].focal, open[best].cost))
+        best = (int)k;
+    }
+    if (best < 0) return fail(ORC_NO_SOLUTION);  // the reference would dereference an empty heap
+    HLNode P = open[best];
+    open.erase(open.begin() + best);
+    ++hl;
+    orc_conflict conflict;
+    if (!firstConflict(grid, P.solution, 1, &conflict)) {
+      solution = P.solution;
+      return fail(ORC_SOLVED);
+    }
+    NewConstraint nc[2];
+    int n = constraintsFromConflict(grid, conflict, nc);
+    for (int k = 0; k < n; ++k) {
+      int i = nc[k].agent;
+      HLNode child = P;
+      child.id = id;
+      if (nc[k].edge)
+        addEdgeConstraint(grid, child.constraints[i], nc[k].t, nc[k].a, nc[k].b);
+      else
+        addVertexConstraint(grid, child.constraints[i], nc[k].t, nc[k].a);
+      child.cost -= child.solution[i].cost;
+      child.LB -= child.solution[i].fmin;
+      auto it = child.tasks.find(i);
+      const int goal = it == child.tasks.end() ? -1 : it->second;
+      env.setContext(i, &child.constraints[i], goal);
+      env.field = goal >= 0 ? apsp.data() + (size_t)goal * V : nullptr;
+      env.solution = &child.solution;
+      int st = aStarEpsilon(env, w, starts[i], child.solution[i], caps.maxLL);
+      if (st == ORC_CAPPED) return fail(ORC_CAPPED);
+      child.cost += child.solution[i].cost;
+      child.LB += child.solution[i].fmin;
+      child.focal = countConflicts(child.solution);
+      if (st == ORC_SOLVED) open.push_back(child);
+      ++id;
+    }
+    // STYLE_MINROOT: a new root once the cheapest open node exceeds the bound
+    // (ecbs_ta.hpp:299-348)
+    if (open.empty()) return fail(ORC_NO_SOLUTION);
+    if (open[topOf()].cost > nextRootNodeCost) {
+      HLNode r;
+      nextTaskAssignment(r.tasks);
+      if (!r.tasks.empty()) {
+        r.solution.resize(N);
+        r.constraints.resize(N);
+        r.id = id;
+        r.isRoot = true;
+        int st = planAll(r);
+        if (st == ORC_CAPPED) return fail(ORC_CAPPED);
+        if (st == ORC_SOLVED) {
+          open.push_back(r);
+          ++id;
+        }
+      }
+      nextRootNodeCost = (int)(open[topOf()].LB * w);
+    }
+  }
+  return fail(ORC_NO_SOLUTION);
+}
+
 }  // namespace orc
 
 // ===========================================================================
@@ -1373,6 +1514,32 @@ int orc_cbs_ta(const orc_instance* inst, int64_t max_task_assignments,
   Caps k = toCaps(caps);
   std::vector<Plan> sol;
   int st = cbsTaSearch(g, starts, pg, max_task_assignments, k, sol, res);
+  res->status = st;
+  if (st == ORC_SOLVED) {
+    finishResult(sol, res);
+    exportPaths(g, sol, path_off, path_xyg, path_cap);
+  }
+  return st;
+}
+
+int orc_ecbs_ta(const orc_instance* inst, float w, int64_t max_task_assignments,
+                const orc_caps* caps, orc_result* res, int32_t* path_off, int32_t* path_xyg,
+                int path_cap) {
+  Grid g;
+  std::vector<int> starts, goals;
+  unpackInstance(inst, g, starts, goals);
+  std::vector<std::vector<int>> pg(inst->n_agents);
+  for (int i = 0; i < inst->n_agents; ++i) {
+    std::set<int> seen;
+    for (int k = inst->pg_off[i]; k < inst->pg_off[i + 1]; ++k) {
+      int cell = inst->pg_xy[2 * k] + g.dimx * inst->pg_xy[2 * k + 1];
+      if (seen.insert(cell).second) pg[i].push_back(cell);
+    }
+  }
+  std::memset(res, 0, sizeof *res);
+  Caps k = toCaps(caps);
+  std::vector<Plan> sol;
+  int st = ecbsTaSearch(g, starts, pg, w, max_task_assignments, k, sol, res);
   res->status = st;
   if (st == ORC_SOLVED) {
     finishResult(sol, res);

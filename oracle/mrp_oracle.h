@@ -123,6 +123,11 @@ int orc_cbs_ta(const orc_instance* inst, int64_t max_task_assignments,
                const orc_caps* caps, orc_result* res, int32_t* path_off,
                int32_t* path_xyg, int path_cap);
 
+/* ecbs_ta.hpp:94-352 (REBUILT_FOCAL_LIST + STYLE_MINROOT), example/ecbs_ta.cpp */
+int orc_ecbs_ta(const orc_instance* inst, float w, int64_t max_task_assignments,
+                const orc_caps* caps, orc_result* res, int32_t* path_off,
+                int32_t* path_xyg, int path_cap);
+
 /* ---- assignment (assignment.hpp:34-118, next_best_assignment.hpp:37-201) ---- */
 /* edges: [n_edges][3] = (agent, task, cost).  sol_task[a] = task or -1.
  * returns total cost. n_agents_out agents are those that appear in edges. */

@@ -210,6 +210,13 @@ def cbs_ta(dimx, dimy, obst_xy, start_xy, potential_goals,
                 path_cap)
 
 
+def ecbs_ta(dimx, dimy, obst_xy, start_xy, potential_goals, w, max_task_assignments=10**9,
+            caps=None, path_cap=1 << 16):
+    inst, keep = _instance(dimx, dimy, obst_xy, start_xy, potential_goals=potential_goals)
+    return _run("orc_ecbs_ta", inst, (C.c_float(w), C.c_int64(max_task_assignments)), caps,
+                path_cap)
+
+
 def assignment(edges, n_agents, n_tasks):
     e = np.ascontiguousarray(edges, dtype=np.int64).reshape(-1, 3)
     sol = np.full(max(n_agents, 1), -1, np.int32)

@@ -149,6 +149,37 @@ def test_cbs_ta_c4_like(capi, orc, set32):
     check_solution(inst, r["paths"], 1)
 
 
+def test_ecbs_ta(capi, orc, ref_fixtures, set32):
+    """ecbs_ta: the reference pins the cbs_ta answers at
+    w = 1.0 (test/test_ecbs_ta.py:25-39); beyond that the w bound must hold."""
+    from libmultirobotplanning_b200 import solver
+    for name, d in ref_fixtures.items():
+        exp = d["expected"]
+        if "cbs_ta_cost" not in exp:
+            continue
+        inst = Inst(d)
+        r = solver.solve_batch(solver.ECBS_TA, [inst], w=1.0, max_hl=5000)[0]
+        assert r["status"] == 0 and r["cost"] == exp["cbs_ta_cost"], name
+        if "agent0_last" in exp:
+            x, y, g = r["paths"][0][-1]
+            assert {"x": x, "y": y, "t": g} == exp["agent0_last"]
+        if "agent1_last_xy" in exp:
+            assert list(r["paths"][1][-1][:2]) == exp["agent1_last_xy"]
+    base = next(i for i in set32 if i.name == "map_32by32_obst204_agents10_ex3")
+    inst = base.with_all_goals_potential()
+    opt = solver.solve_batch(solver.CBS_TA, [inst], max_hl=3000)[0]
+    r1 = solver.solve_batch(solver.ECBS_TA, [inst], w=1.0, max_hl=3000)[0]
+    o1 = orc.ecbs_ta(inst.dimx, inst.dimy, inst.obstacles, inst.starts,
+                     [g.tolist() for g in inst.potential_goals], 1.0, caps=(3000, 0, 60.0))
+    assert r1["status"] == 0 and o1["status"] == 0 and opt["status"] == 0
+    assert r1["cost"] == o1["cost"] == opt["cost"]
+    r = solver.solve_batch(solver.ECBS_TA, [inst], w=1.3, max_hl=3000)[0]
+    assert r["status"] == 0
+    assert np.float32(r["cost"]) <= np.float32(r["lower_bound"]) * np.float32(1.3)
+    assert opt["cost"] <= r["cost"] <= 1.3 * opt["cost"]
+    check_solution(inst, r["paths"], 1)
+
+
 def test_cli_binaries(capi, ref_fixtures, tmp_path):
     from libmultirobotplanning_b200 import instances as I
     for name, tool, extra, key in (("mapf_simple1", "cbs", [], "cbs_cost"),
@@ -157,7 +188,9 @@ def test_cli_binaries(capi, ref_fixtures, tmp_path):
                                    ("mapf_simple1", "ecbs", ["--suboptimality=1.0"], "ecbs_w1_cost"),
                                    ("mapfta_simple1_a2", "cbs_ta", [], "cbs_ta_cost"),
                                    ("mapfta_simple1_a3", "cbs_ta", ["--maxTaskAssignments", "5"],
-                                    "cbs_ta_cost")):
+                                    "cbs_ta_cost"),
+                                   ("mapfta_simple1_a2", "ecbs_ta", ["-w", "1.0"], "cbs_ta_cost"),
+                                   ("mapfta_simple1_a1", "ecbs_ta", [], "cbs_ta_cost")):
         d = ref_fixtures[name]
         x = Inst(d)
         inst = I.Instance(name, x.dimx, x.dimy, x.obstacles, x.starts,
@@ -175,7 +208,7 @@ def test_cli_binaries(capi, ref_fixtures, tmp_path):
         assert y["statistics"]["cost"] == d["expected"][key]
         assert list(y["statistics"].keys())[:5] == ["cost", "makespan", "runtime",
                                                     "highLevelExpanded", "lowLevelExpanded"]
-        assert ("numTaskAssignments" in y["statistics"]) == (tool == "cbs_ta")
+        assert ("numTaskAssignments" in y["statistics"]) == (tool in ("cbs_ta", "ecbs_ta"))
         assert re.search(r"^schedule:\n  agent0:\n    - x: \d+\n      y: \d+\n      t: 0\n", text, re.M)
         assert sorted(y["schedule"]) == ["agent%d" % a for a in range(len(x.starts))]
         if "agent0_last" in d["expected"]:

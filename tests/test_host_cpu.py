@@ -39,13 +39,13 @@ def test_yaml_reader_both_styles(tmp_path, set8, set32):
     assert [g.tolist() for g in d["potential_goals"]] == [[1, 2], []]
 
 
-@pytest.mark.parametrize("tool", ["cbs", "ecbs", "cbs_ta"])
+@pytest.mark.parametrize("tool", ["cbs", "ecbs", "cbs_ta", "ecbs_ta"])
 def test_cli_flags(tool):
     exe = os.path.join(BIN, tool)
     r = subprocess.run([exe, "--help"], capture_output=True, text=True)
     assert r.returncode == 0 and "--input" in r.stdout and "--output" in r.stdout
-    assert ("--suboptimality" in r.stdout) == (tool == "ecbs")
-    assert ("--maxTaskAssignments" in r.stdout) == (tool == "cbs_ta")
+    assert ("--suboptimality" in r.stdout) == (tool in ("ecbs", "ecbs_ta"))
+    assert ("--maxTaskAssignments" in r.stdout) == (tool in ("cbs_ta", "ecbs_ta"))
     r = subprocess.run([exe, "-i", "x.yaml"], capture_output=True, text=True)
     assert r.returncode == 1 and "required but missing" in r.stderr
     r = subprocess.run([exe, "--bogus"], capture_output=True, text=True)

@@ -38,6 +38,22 @@ def test_cbs_ta_fixtures(orc, ref_fixtures):
             assert list(r["paths"][1][-1][:2]) == exp["agent1_last_xy"], name
 
 
+def test_ecbs_ta_fixtures(orc, ref_fixtures):
+    # test/test_ecbs_ta.py:25-39 asserts the cbs_ta values at w = 1.0
+    for name, d in ref_fixtures.items():
+        exp = d["expected"]
+        if "cbs_ta_cost" not in exp:
+            continue
+        r = orc.ecbs_ta(d["dimx"], d["dimy"], d["obstacles"], d["starts"],
+                        d["potentialGoals"], 1.0, caps=CAPS)
+        assert r["status"] == orc.SOLVED and r["cost"] == exp["cbs_ta_cost"], name
+        if "agent0_last" in exp:
+            x, y, t = r["paths"][0][-1]
+            assert {"x": x, "y": y, "t": t} == exp["agent0_last"], name
+        if "agent1_last_xy" in exp:
+            assert list(r["paths"][1][-1][:2]) == exp["agent1_last_xy"], name
+
+
 def test_extra_cbs_anchors(orc, ref_fixtures):
     # swap2 12/6, swap4 28/8 (edge conflicts)
     for name, cost, makespan in (("mapf_swap2", 12, 6), ("mapf_swap4", 28, 8)):
