@@ -212,6 +212,11 @@ def search_metrics(pkg):
     dt = time.perf_counter() - t0
     out["ecbs_cpu_instances_per_s_1core"] = sum(r["status"] == 0 for r in cres) / dt
     out["ecbs_cpu_sample"] = "%d instances, oracle port" % n_cpu
+    ref = reference_binary_rate("ecbs", insts[:n_cpu], ("-w", "1.3"))
+    if ref:
+        out["ecbs_reference_binary_instances_per_s_1core"] = ref
+        out["ecbs_reference_binary"] = ("unmodified example/ecbs.cpp + stand-in Boost/yaml-cpp "
+                                        "headers (oracle/_ref), statistics.runtime convention")
     out["ecbs_cost_gpu_vs_cpu"] = [[a["cost"], b["cost"]] for a, b in zip(res, cres)]
     # smem-resident maps: all goals of all 1000 32x32 instances / 2000 8x8 instances
     import torch
@@ -246,6 +251,36 @@ def search_metrics(pkg):
             if a["status"] == 0 and b["status"] == 0 and a["cost"] != b["cost"]]
     out["cbs_8x8_cost_mismatches_vs_oracle"] = len(mism)
     return out
+
+
+def reference_binary_rate(tool, insts, extra, timeout=60.0):
+    """instances per second of the reference's own binary (oracle/_ref, built
+    from the unmodified sources against stand-in third-party headers), by the
+    reference's timing convention: statistics.runtime = search() only."""
+    import tempfile
+    import yaml
+    from libmultirobotplanning_b200 import instances as I
+    exe = os.path.join(ROOT, "oracle", "_ref", tool)
+    if not os.path.exists(exe):
+        return None
+    total, solved = 0.0, 0
+    with tempfile.TemporaryDirectory() as d:
+        for inst in insts:
+            inp, outp = os.path.join(d, "i.yaml"), os.path.join(d, "o.yaml")
+            I.save_yaml(inst, inp)
+            if os.path.exists(outp):
+                os.remove(outp)
+            try:
+                subprocess.run([exe, "-i", inp, "-o", outp, *extra], stdout=subprocess.DEVNULL,
+                               stderr=subprocess.DEVNULL, timeout=timeout, check=True)
+            except Exception:
+                total += timeout
+                continue
+            if os.path.exists(outp):
+                with open(outp) as f:
+                    total += float(yaml.safe_load(f)["statistics"]["runtime"])
+                solved += 1
+    return solved / total if total > 0 else None
 
 
 def run_ours(args):

@@ -213,9 +213,14 @@ class BatchSolver {
   bool isTA() const { return m_algo == Algo::CBSTA || m_algo == Algo::ECBSTA; }
   bool isFocal() const { return m_algo == Algo::ECBS || m_algo == Algo::ECBSTA; }
 
-  struct OpenOrder {  // lowest cost (cbs.hpp:187-191), then lowest id
+  // lowest cost first (cbs.hpp:187-191).  Among equal costs the reference's
+  // order is whatever Boost's heap does; here: fewer conflicts first (the count
+  // is computed anyway), then lowest id.  Any order among equal costs keeps
+  // CBS optimal; this one reaches a conflict-free node sooner.
+  struct OpenOrder {
     bool operator()(const Node* a, const Node* b) const {
-      return std::make_pair(a->cost, a->id) < std::make_pair(b->cost, b->id);
+      return std::make_tuple(a->cost, a->focal, a->id) <
+             std::make_tuple(b->cost, b->focal, b->id);
     }
   };
   struct Inst {

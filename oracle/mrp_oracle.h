@@ -6,9 +6,14 @@
  * be checked against them.  Only tests/, __graft_entry__.smoke() and the
  * cpu_baseline / --impl reference legs of bench.py may load it.
  *
- * Parity status: the reference cannot be compiled in this image (Boost and
- * yaml-cpp are absent), so the oracle is pinned against the known answers held
- * by the reference's own tests (test/test_cbs.py:24-34, test/test_ecbs.py:25-35,
+ * Parity status: the reference cannot be compiled as shipped in this image
+ * (Boost and yaml-cpp are absent).  The oracle is pinned twice:
+ *  (1) against the UNMODIFIED reference cbs / ecbs sources compiled with
+ *      stand-in third-party headers (oracle/ref_build -> oracle/_ref/): 582 CBS
+ *      instances with identical cost, makespan and expansion counts, 36 ECBS
+ *      w=1.3 instances (tests/golden/ref_binary_golden.json,
+ *      tests/test_oracle_pinned.py::test_oracle_equals_reference_binaries);
+ *  (2) against the known answers held by the reference's own tests (test/test_cbs.py:24-34, test/test_ecbs.py:25-35,
  * test/test_cbs_ta.py:24-38, test/test_assignment.py:19-63,
  * test/test_next_best_assignment.py:19-110) — see tests/test_oracle_pinned.py.
  * Function-level outputs (distance fields, conflict tuples, focal counts) are

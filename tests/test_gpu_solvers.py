@@ -100,6 +100,30 @@ def test_cbs_8x8_set_matches_oracle_golden(capi, set8, oracle_golden):
             check_solution(i, r["paths"], 0)
 
 
+def test_cbs_matches_reference_binaries(capi, set8, set32):
+    """582 optimal sums-of-costs produced by the UNMODIFIED reference cbs binary
+    (tests/golden/ref_binary_golden.json, see make_ref_golden.py)."""
+    import json
+    from libmultirobotplanning_b200 import solver
+    g = json.load(open(os.path.join(ROOT, "tests", "golden", "ref_binary_golden.json")))
+    by = {i.name: i for i in set8 + set32}
+    for dims in ((8, 8), (32, 32)):
+        names = [n for n in sorted(g["cbs"]) if (by[n].dimx, by[n].dimy) == dims]
+        res = solver.solve_batch(solver.CBS, [by[n] for n in names], max_hl=300000,
+                                 max_seconds=400)
+        for n, r in zip(names, res):
+            assert r["status"] == 0, n
+            assert r["cost"] == g["cbs"][n]["cost"], n
+    # ECBS w = 1.3: within the bound, and in the neighbourhood of the reference's cost
+    names = sorted(g["ecbs_w1.3"])
+    res = solver.solve_batch(solver.ECBS, [by[n] for n in names], w=1.3, max_hl=20000,
+                             max_seconds=300)
+    for n, r in zip(names, res):
+        assert r["status"] == 0, n
+        assert np.float32(r["cost"]) <= np.float32(r["lower_bound"]) * np.float32(1.3)
+        assert r["cost"] <= 1.05 * g["ecbs_w1.3"][n]["cost"], n
+
+
 def test_cbs_32x32_and_ecbs_bound(capi, set32, oracle_golden):
     from libmultirobotplanning_b200 import solver
     names = [n for n in oracle_golden["cbs"] if n.startswith("map_32by32")]

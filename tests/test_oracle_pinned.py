@@ -232,3 +232,53 @@ def test_lowlevel_oracle_constraints(orc):
     r = orc.lowlevel(5, 1, [], 1, 0, 4, vc=[[9, 4]])
     # reach the goal (4), rest for free until t=8, step off at t=9 and back
     assert r["cost"] == 6
+
+
+def test_oracle_equals_reference_binaries(orc, set8, set32):
+    """tests/golden/ref_binary_golden.json holds the answers of the UNMODIFIED
+    reference cbs / ecbs (example/cbs.cpp, ecbs.cpp + the library headers,
+    compiled against stand-in Boost / yaml-cpp headers: oracle/ref_build).  The
+    oracle must reproduce every optimal sum-of-costs; it even reproduces the
+    expansion counts because both sides then break ties the same way."""
+    import json
+    import os
+    g = json.load(open(os.path.join(os.path.dirname(__file__), "golden",
+                                    "ref_binary_golden.json")))
+    by = {i.name: i for i in set8 + set32}
+    names = sorted(g["cbs"])[::3]
+    for name in names:
+        r, i = g["cbs"][name], by[name]
+        o = orc.cbs(i.dimx, i.dimy, i.obstacles, i.starts, i.goals, (400000, 0, 30.0))
+        assert o["status"] == orc.SOLVED and o["cost"] == r["cost"], name
+        assert (o["hl_expanded"], o["ll_expanded"]) == (r["highLevelExpanded"],
+                                                        r["lowLevelExpanded"]), name
+    for name, r in g["ecbs_w1.3"].items():
+        i = by[name]
+        o = orc.ecbs(i.dimx, i.dimy, i.obstacles, i.starts, i.goals, 1.3, (400000, 0, 30.0))
+        assert o["status"] == orc.SOLVED
+        # ties inside FOCAL may resolve differently: same bound, nearly equal cost
+        assert abs(o["cost"] - r["cost"]) <= 0.02 * r["cost"], name
+        assert o["cost"] <= 1.3 * o["lower_bound"]
+
+
+def test_reference_binaries_live(ref_fixtures, tmp_path):
+    """Only where oracle/_ref/ was built (the build container): the reference's
+    own binaries against its own pinned answers."""
+    import os
+    import subprocess
+    import yaml
+    from libmultirobotplanning_b200 import instances as I
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "oracle", "_ref", "cbs")
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref not built")
+    for name in ("mapf_simple1", "mapf_circle", "mapf_atGoal"):
+        d = ref_fixtures[name]
+        inst = I.Instance(name, d["dimx"], d["dimy"], np.array(d["obstacles"]).reshape(-1, 2),
+                          np.array(d["starts"]), np.array(d["goals"]))
+        inp, out = str(tmp_path / "i.yaml"), str(tmp_path / "o.yaml")
+        I.save_yaml(inst, inp)
+        for tool, extra in (("cbs", []), ("ecbs", ["-w", "1.0"])):
+            subprocess.run([os.path.join(root, "oracle", "_ref", tool), "-i", inp, "-o", out]
+                           + extra, check=True, stdout=subprocess.DEVNULL)
+            assert yaml.safe_load(open(out))["statistics"]["cost"] == d["expected"]["cbs_cost"]
