@@ -6,6 +6,11 @@
 // example/cbs_ta.cpp:252-514, so the reference's unmodified templates can be
 // instantiated with these classes:
 //
+// (the plan / neighbour containers are template parameters of the methods, so
+// both libMultiRobotPlanning::PlanResult / Neighbor and the look-alikes of
+// mapf_types.hpp work; oracle/ref_build/templates_gpuenv.cpp does exactly this
+// with the reference's headers):
+//
 //   mrp_host::Environment mapf(dimx, dimy, obstacles, goals);
 //   libMultiRobotPlanning::CBS<State, Action, int, Conflict, Constraints,
 //                              mrp_host::Environment> cbs(mapf);
@@ -108,7 +113,8 @@ class Environment {
     return m_heuristic[m_agentIdx * (size_t)m_dimx * m_dimy + s.x + m_dimx * s.y];
   }
 
-  int focalStateHeuristic(const State& s, int /*gScore*/, const std::vector<Plan>& solution) {
+  template <class PlanT>
+  int focalStateHeuristic(const State& s, int /*gScore*/, const std::vector<PlanT>& solution) {
     int n = 0;
     for (size_t i = 0; i < solution.size(); ++i)
       if (i != m_agentIdx && !solution[i].states.empty() &&
@@ -117,8 +123,9 @@ class Environment {
     return n;
   }
 
+  template <class PlanT>
   int focalTransitionHeuristic(const State& s1a, const State& s1b, int /*g1a*/, int /*g1b*/,
-                               const std::vector<Plan>& solution) {
+                               const std::vector<PlanT>& solution) {
     int n = 0;
     for (size_t i = 0; i < solution.size(); ++i)
       if (i != m_agentIdx && !solution[i].states.empty()) {
@@ -129,7 +136,8 @@ class Environment {
   }
 
   // number of vertex + edge conflicts of a joint plan — on the GPU
-  int focalHeuristic(const std::vector<Plan>& solution) {
+  template <class PlanT>
+  int focalHeuristic(const std::vector<PlanT>& solution) {
     std::vector<int32_t> cell, len;
     int Tpad;
     detail::packSolution(solution, m_dimx, cell, len, Tpad);
@@ -144,7 +152,8 @@ class Environment {
            s.time > m_lastGoalConstraint;
   }
 
-  void getNeighbors(const State& s, std::vector<Neighbor<State, Action, int> >& neighbors) {
+  template <class NeighborT>
+  void getNeighbors(const State& s, std::vector<NeighborT>& neighbors) {
     neighbors.clear();
     static const int dx[5] = {0, -1, 1, 0, 0}, dy[5] = {0, 0, 0, 1, -1};
     static const Action act[5] = {Action::Wait, Action::Left, Action::Right, Action::Up,
@@ -152,12 +161,13 @@ class Environment {
     for (int k = 0; k < 5; ++k) {
       State n(s.time + 1, s.x + dx[k], s.y + dy[k]);
       if (stateValid(n) && transitionValid(s, n))
-        neighbors.emplace_back(Neighbor<State, Action, int>(n, act[k], 1));
+        neighbors.emplace_back(NeighborT(n, act[k], 1));
     }
   }
 
   // first conflict in the order (time, Vertex < Edge, agent1, agent2) — on the GPU
-  bool getFirstConflict(const std::vector<Plan>& solution, Conflict& result) {
+  template <class PlanT>
+  bool getFirstConflict(const std::vector<PlanT>& solution, Conflict& result) {
     std::vector<int32_t> cell, len;
     int Tpad;
     detail::packSolution(solution, m_dimx, cell, len, Tpad);
@@ -205,7 +215,8 @@ class Environment {
   int lowLevelExpanded() const { return m_lowLevelExpanded; }
 
  private:
-  State getState(size_t agentIdx, const std::vector<Plan>& solution, size_t t) {
+  template <class PlanT>
+  State getState(size_t agentIdx, const std::vector<PlanT>& solution, size_t t) {
     if (t < solution[agentIdx].states.size()) return solution[agentIdx].states[t].first;
     return solution[agentIdx].states.back().first;
   }
@@ -293,7 +304,8 @@ class EnvironmentTA {
     return atGoal && s.time > m_lastGoalConstraint;
   }
 
-  void getNeighbors(const State& s, std::vector<Neighbor<State, Action, int> >& neighbors) {
+  template <class NeighborT>
+  void getNeighbors(const State& s, std::vector<NeighborT>& neighbors) {
     neighbors.clear();
     static const int dx[5] = {0, -1, 1, 0, 0}, dy[5] = {0, 0, 0, 1, -1};
     static const Action act[5] = {Action::Wait, Action::Left, Action::Right, Action::Up,
@@ -306,11 +318,12 @@ class EnvironmentTA {
         const bool atGoal = m_goal == nullptr || (s.x == m_goal->x && s.y == m_goal->y);
         cost = atGoal ? 0 : 1;
       }
-      neighbors.emplace_back(Neighbor<State, Action, int>(n, act[k], cost));
+      neighbors.emplace_back(NeighborT(n, act[k], cost));
     }
   }
 
-  bool getFirstConflict(const std::vector<Plan>& solution, Conflict& result) {
+  template <class PlanT>
+  bool getFirstConflict(const std::vector<PlanT>& solution, Conflict& result) {
     std::vector<int32_t> cell, len;
     int Tpad;
     detail::packSolution(solution, m_dimx, cell, len, Tpad);
@@ -372,7 +385,8 @@ class EnvironmentTA {
   }
 
  private:
-  State getState(size_t agentIdx, const std::vector<Plan>& solution, size_t t) {
+  template <class PlanT>
+  State getState(size_t agentIdx, const std::vector<PlanT>& solution, size_t t) {
     if (t < solution[agentIdx].states.size()) return solution[agentIdx].states[t].first;
     return solution[agentIdx].states.back().first;
   }

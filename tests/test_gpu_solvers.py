@@ -243,3 +243,31 @@ def test_environment_adapter(capi):
     from libmultirobotplanning_b200 import solver
     # two agents walking into each other on a 3x1 corridor: vertex conflict at t=1
     assert solver.lib().mrph_environment_selftest() == 10
+
+
+def test_reference_templates_drive_gpu_environment(capi, ref_fixtures, tmp_path):
+    """oracle/_ref/templates_gpuenv = the reference's UNMODIFIED CBS / ECBS /
+    CBSTA templates instantiated with this repository's GPU-backed Environment
+    (built by oracle/ref_build where /root/reference exists; the binary travels
+    to the GPU box).  The reference's own loops must reach its pinned answers
+    through our callbacks."""
+    from libmultirobotplanning_b200 import instances as I
+    exe = os.path.join(ROOT, "oracle", "_ref", "templates_gpuenv")
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/templates_gpuenv not built (needs /root/reference)")
+    for name, d in ref_fixtures.items():
+        exp = d["expected"]
+        x = Inst(d)
+        inst = I.Instance(name, x.dimx, x.dimy, x.obstacles, x.starts,
+                          getattr(x, "goals", None), getattr(x, "potential_goals", None))
+        inp = str(tmp_path / (name + ".yaml"))
+        I.save_yaml(inst, inp)
+        runs = []
+        if "cbs_cost" in exp:
+            runs = [("cbs", [], exp["cbs_cost"]), ("ecbs", ["1.0"], exp["ecbs_w1_cost"])]
+        if "cbs_ta_cost" in exp:
+            runs = [("cbs_ta", [], exp["cbs_ta_cost"])]
+        for algo, extra, want in runs:
+            r = subprocess.run([exe, algo, inp] + extra, capture_output=True, text=True)
+            assert r.returncode == 0, (name, algo, r.stderr[-300:])
+            assert ("cost %d" % want) in r.stdout, (name, algo, r.stdout[-200:])
