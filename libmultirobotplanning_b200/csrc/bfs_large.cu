@@ -49,6 +49,10 @@ struct BfsTileParams {
   int spillCap;  // capacity of the global fallback lists (same multiple)
   int nCompute;  // threads that run the level logic; the rest only store
   int dbg;  // debug: bit0 = skip level stores, bit1 = skip obstacle stores
+  // optional indirection (goals the queue kernel handed over, bfs_queue.cu):
+  // goalList[0..*goalListCount) are indices into goals / out
+  const uint32_t* goalList;
+  const uint32_t* goalListCount;
 };
 
 constexpr int kWsHeaderWords = 64;  // [0] goal counter, [1] overflow flag
@@ -108,8 +112,9 @@ bfs_tiles_kernel(BfsTileParams p) {
       if (tid == 0) sGoal = (int)atomicAdd(p.ws, 1u);
       __syncthreads();
     }
-    const int gidx = sGoal;
-    if (gidx >= p.n_goals) break;
+    int gidx = sGoal;
+    if (gidx >= (p.goalList ? (int)*p.goalListCount : p.n_goals)) break;
+    if (p.goalList) gidx = (int)p.goalList[gidx];
     const int cap = spilled ? spillCap : p.cap;
     // two lists of `cap` (tile, free word) entries, then cand[cap], pm[cap]
     uint2* list0 = reinterpret_cast<uint2*>(spilled ? g : smem);
@@ -398,16 +403,39 @@ extern "C" int mrp_debug_bfs_timing(unsigned long long* out) {
 }
 #endif
 
-size_t bfsLargeWorkspaceBytes(const mrp_map_s* map, int n_goals) {
-  (void)n_goals;
+static size_t tilesWorkspaceBytes(const mrp_map_s* map) {
   const TileGeom t = tileGeometry(map);
   const int blocks = tileBlocks(t, t.smemState);
   return ((size_t)kWsHeaderWords + t.wsWordsPerCta * (size_t)blocks) * 4;
 }
 
+size_t bfsLargeWorkspaceBytes(const mrp_map_s* map, int n_goals) {
+  size_t bytes = tilesWorkspaceBytes(map);
+  if (bfsQueueFits(map)) bytes += bfsQueueWorkspaceWords(n_goals) * 4;
+  return bytes;
+}
+
+static int launchBfsTiles(const mrp_map_s* map, const int32_t* d_goal_cell, int n_goals,
+                          int32_t* d_out, void* d_ws, const uint32_t* d_goalList,
+                          const uint32_t* d_goalListCount, cudaStream_t st);
+
+// Maps whose bitmap fits shared memory run the queue kernel; the goals it
+// hands over (a level larger than its queues) and all larger maps run the
+// tiled kernel.
 int launchBfsLarge(const mrp_map_s* map, const int32_t* d_goal_cell, int n_goals,
                    int32_t* d_out, void* d_ws, cudaStream_t st) {
   if (n_goals <= 0) return 0;
+  if (!bfsQueueFits(map))
+    return launchBfsTiles(map, d_goal_cell, n_goals, d_out, d_ws, nullptr, nullptr, st);
+  if (int rc = launchBfsQueue(map, d_goal_cell, n_goals, d_out, d_ws, st)) return rc;
+  uint32_t* qws = static_cast<uint32_t*>(d_ws);
+  return launchBfsTiles(map, d_goal_cell, n_goals, d_out, qws + bfsQueueWorkspaceWords(n_goals),
+                        qws + 64, qws + 2, st);
+}
+
+static int launchBfsTiles(const mrp_map_s* map, const int32_t* d_goal_cell, int n_goals,
+                          int32_t* d_out, void* d_ws, const uint32_t* d_goalList,
+                          const uint32_t* d_goalListCount, cudaStream_t st) {
   const TileGeom t = tileGeometry(map);
   MRP_CHECK(t.TW < 65536 && t.TH < 65536, MRP_ERR_UNSUPPORTED,
             "map %dx%d exceeds the packed tile coordinates", map->dimx, map->dimy);
@@ -429,6 +457,8 @@ int launchBfsLarge(const mrp_map_s* map, const int32_t* d_goal_cell, int n_goals
   p.nCompute = t.threads >= 256 ? t.threads / 2 : t.threads;
   if (const char* e = getenv("MRP_BFS_COMPUTE")) p.nCompute = atoi(e);
   p.dbg = getenv("MRP_BFS_DBG") ? atoi(getenv("MRP_BFS_DBG")) : 0;
+  p.goalList = d_goalList;
+  p.goalListCount = d_goalListCount;
   MRP_CUDA(cudaMemsetAsync(d_ws, 0, kWsHeaderWords * 4, st));
   int blocks = tileBlocks(t, t.smemState);
   if (blocks > n_goals) blocks = n_goals;

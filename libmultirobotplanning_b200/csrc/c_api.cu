@@ -215,17 +215,29 @@ int mrp_map_create(int dimx, int dimy, const int32_t* obst_xy, int n_obst,
     for (int x = 0; x < dimx; ++x)
       if ((bits[((size_t)(y >> 5) * W + (x >> 5)) * 32 + (y & 31)] >> (x & 31)) & 1u)
         bits84[(size_t)(y >> 2) * TW8 + (x >> 3)] |= 1u << (((y & 3) << 3) | (x & 7));
+  // third layout: row-major with a zero border for the queue BFS kernel
+  const int WPR = ((dimx + 2 + 31) / 32) | 1;
+  std::vector<uint32_t> rowbits((size_t)(dimy + 4) * WPR, 0u);
+  for (int y = 0; y < dimy; ++y)
+    for (int x = 0; x < dimx; ++x)
+      if ((bits[((size_t)(y >> 5) * W + (x >> 5)) * 32 + (y & 31)] >> (x & 31)) & 1u)
+        rowbits[(size_t)(y + 1) * WPR + ((x + 1) >> 5)] |= 1u << ((x + 1) & 31);
   m->d_bits = nullptr;
   m->d_bits84 = nullptr;
+  m->d_rowbits = nullptr;
   cudaError_t e = cudaMalloc(&m->d_bits, bits.size() * 4);
   if (e == cudaSuccess)
     e = cudaMemcpy(m->d_bits, bits.data(), bits.size() * 4, cudaMemcpyHostToDevice);
   if (e == cudaSuccess) e = cudaMalloc(&m->d_bits84, bits84.size() * 4);
   if (e == cudaSuccess)
     e = cudaMemcpy(m->d_bits84, bits84.data(), bits84.size() * 4, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMalloc(&m->d_rowbits, rowbits.size() * 4);
+  if (e == cudaSuccess)
+    e = cudaMemcpy(m->d_rowbits, rowbits.data(), rowbits.size() * 4, cudaMemcpyHostToDevice);
   if (e != cudaSuccess) {
     cudaFree(m->d_bits);
     cudaFree(m->d_bits84);
+    cudaFree(m->d_rowbits);
     delete[] m->h_bits;
     delete m;
     return fail(MRP_ERR_CUDA, "map upload failed: %s", cudaGetErrorString(e));
@@ -240,6 +252,7 @@ int mrp_map_destroy(mrp_map map) {
   if (ctx().ready) cudaSetDevice(ctx().device);
   cudaFree(map->d_bits);
   cudaFree(map->d_bits84);
+  cudaFree(map->d_rowbits);
   delete[] map->h_bits;
   delete map;
   return 0;

@@ -62,6 +62,10 @@ struct mrp_map_s {
   // free mask in 8x4-cell tiles (bfs_large.cu): bits84[ty*TW8 + tx], bit
   // 8*(y&3) + (x&7), TW8 = ceil(dimx/8), TH4 = ceil(dimy/4)
   uint32_t* d_bits84;
+  // free mask, row-major with a one-cell border of zeros and two more zero
+  // rows at the bottom, dimy+4 rows in all (bfs_queue.cu):
+  // rowbits[(y+1)*WPR + ((x+1)>>5)] bit (x+1)&31, WPR = ceil((dimx+2)/32) | 1
+  uint32_t* d_rowbits;
 };
 
 struct mrp_fieldset_s {
@@ -103,6 +107,10 @@ int launchBfsSmall(const uint32_t* d_rows, const int32_t* d_dims,
                    cudaStream_t st);
 size_t bfsLargeWorkspaceBytes(const mrp_map_s* map, int n_goals);
 int launchBfsLarge(const mrp_map_s* map, const int32_t* d_goal_cell,
+                   int n_goals, int32_t* d_out, void* d_ws, cudaStream_t st);
+bool bfsQueueFits(const mrp_map_s* map);
+size_t bfsQueueWorkspaceWords(int n_goals);
+int launchBfsQueue(const mrp_map_s* map, const int32_t* d_goal_cell,
                    int n_goals, int32_t* d_out, void* d_ws, cudaStream_t st);
 size_t conflictsWorkspaceBytes(int N, int Tpad);
 int launchConflicts(const int32_t* d_cell, const int32_t* d_len, int N,

@@ -1,3 +1,4 @@
+import os
 """GPU parity: distance fields through the C ABI vs the CPU oracle (bit-exact)."""
 import zlib
 
@@ -49,6 +50,26 @@ def test_random_maps(capi, orc, dimx, dimy, density):
     got = capi.bfs_fields(dimx, dimy, obst, goals)
     want = orc.bfs_fields(dimx, dimy, obst, goals)
     assert np.array_equal(got, want)
+
+
+@pytest.mark.parametrize("env", [{"MRP_BFS_QCAP": "32"}, {"MRP_BFS_TILES": "1"},
+                                 {"MRP_BFS_QCAP": "64", "MRP_BFS_THREADS": "64"}])
+def test_queue_overflow_and_tiled_fallback(capi, orc, env):
+    """The queue kernel hands goals whose wavefront outgrows its shared-memory
+    queues to the tiled kernel; MRP_BFS_TILES forces the tiled kernel."""
+    rng = np.random.default_rng(77)
+    try:
+        os.environ.update(env)
+        for dimx, dimy, density in [(257, 300, 0.25), (100, 37, 0.1), (40, 50, 0.3)]:
+            obst = _rand_map(rng, dimx, dimy, density)
+            cells = rng.choice(dimx * dimy, 9, replace=False)
+            goals = np.stack([cells % dimx, cells // dimx], 1)
+            got = capi.bfs_fields(dimx, dimy, obst, goals)
+            want = orc.bfs_fields(dimx, dimy, obst, goals)
+            assert np.array_equal(got, want)
+    finally:
+        for k in env:
+            os.environ.pop(k, None)
 
 
 def test_empty_and_errors(capi):
