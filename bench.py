@@ -363,7 +363,7 @@ def run_ours(args):
         traffic = tj["dram_bytes_per_goal"] * G
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                "kernel": "bfs_tiles_kernel<true>", "algorithmic_bytes_per_launch": alg_bytes,
+                "kernel": "bfs_queue_kernel", "algorithmic_bytes_per_launch": alg_bytes,
                 "kernel_ms": kern_ms}
 
     # ---- also: conflict sweep of C5 (N = 4096 agents on their goal fields) ----

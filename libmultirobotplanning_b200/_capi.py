@@ -10,7 +10,8 @@ import os
 import numpy as np
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG, "libmrp_b200.so")
+# MRP_B200_LIB: A/B timing of two builds of the same library (tools/), never a fallback
+LIB_PATH = os.environ.get("MRP_B200_LIB") or os.path.join(_PKG, "libmrp_b200.so")
 INF = 2147483647
 
 

@@ -47,7 +47,7 @@ bl = bl[:G].astype(np.int64)
 init = (bl[:, 2] - bl[:, 0]) / 1e3
 loop = (bl[:, 3] - bl[:, 2]) / 1e3
 sweep = (bl[:, 1] - bl[:, 3]) / 1e3
-for name, v in (("init", init), ("level loop", loop), ("sweep+exit", sweep), ("total", init + loop + sweep)):
+for name, v in (("init", init), ("level loop", loop), ("tail rings+exit", sweep), ("total", init + loop + sweep)):
     print("%-10s min %.1f  p25 %.1f  median %.1f  p75 %.1f  max %.1f us" % (name, v.min(), np.percentile(v, 25), np.median(v), np.percentile(v, 75), v.max()))
 order = np.argsort(loop)
 print("fastest loop blocks", order[:8], "slowest", order[-8:])
