@@ -119,6 +119,86 @@ def load_set(path) -> List[Instance]:
 
 
 # ---------------------------------------------------------------------------
+# movingai.com MAPF benchmarks (.map / .scen) — SURVEY.md §8(f4).
+# Same slicing and file naming as the reference's
+# example/standard_benchmark_converter.py:30-89 (agents sorted by bucket, the
+# first 10, 20, ... agents of a scenario per instance).  One deliberate
+# difference: that script compares each map character with the whole SET of
+# occupied characters (line 45), which is never true, so the YAML files it
+# writes have no obstacles at all; here '@', 'T' and 'O' are obstacles, as the
+# script's own `occupied_char` default intends.
+# ---------------------------------------------------------------------------
+MOVINGAI_OCCUPIED = frozenset("@TO")
+MOVINGAI_VALID = frozenset("@.TGOSW")
+
+
+def load_movingai_map(path):
+    """-> (width, height, obstacles[n, 2] int32 as (x, y))."""
+    with open(path) as f:
+        lines = f.read().splitlines()
+    hdr = {}
+    k = 0
+    while k < len(lines) and lines[k].strip() != "map":
+        parts = lines[k].split()
+        if len(parts) == 2:
+            hdr[parts[0]] = parts[1]
+        k += 1
+    if "height" not in hdr or "width" not in hdr or k == len(lines):
+        raise ValueError("%s: not a movingai .map file" % path)
+    height, width = int(hdr["height"]), int(hdr["width"])
+    rows = lines[k + 1:k + 1 + height]
+    if len(rows) != height:
+        raise ValueError("%s: %d map rows, header says %d" % (path, len(rows), height))
+    obst = []
+    for y, row in enumerate(rows):
+        if len(row) != width:
+            raise ValueError("%s: row %d has %d cells, header says %d" % (path, y, len(row), width))
+        for x, c in enumerate(row):
+            if c not in MOVINGAI_VALID:
+                raise ValueError("%s: unknown map character %r at (%d, %d)" % (path, c, x, y))
+            if c in MOVINGAI_OCCUPIED:
+                obst.append((x, y))
+    return width, height, np.array(obst, np.int32).reshape(-1, 2)
+
+
+def load_movingai_scen(path, width, height, obstacles=None):
+    """-> list of ((sx, sy), (gx, gy)), sorted by bucket like the reference's converter."""
+    with open(path) as f:
+        lines = [l for l in f.read().splitlines() if l.strip()]
+    if not lines or "version 1" not in lines[0]:
+        raise ValueError("%s: .scen version type does not match" % path)
+    rows = []
+    for l in lines[1:]:
+        c = l.split("\t") if "\t" in l else l.split()
+        if len(c) < 9:
+            raise ValueError("%s: malformed scenario line %r" % (path, l))
+        bucket, w, h = int(c[0]), int(c[2]), int(c[3])
+        if (w, h) != (width, height):
+            raise ValueError("%s: scenario is for a %dx%d map, not %dx%d" % (path, w, h, width, height))
+        rows.append((bucket, (int(c[4]), int(c[5])), (int(c[6]), int(c[7]))))
+    rows.sort(key=lambda r: r[0])  # stable: the order inside a bucket is kept
+    blocked = set(map(tuple, np.asarray(obstacles).tolist())) if obstacles is not None else set()
+    for _, s, g in rows:
+        if s in blocked or g in blocked:
+            raise ValueError("%s: start %s / goal %s lies on an obstacle" % (path, s, g))
+    return [(s, g) for _, s, g in rows]
+
+
+def movingai_instances(scen_path, map_path, min_agents=10, agent_step=10, max_agents=None):
+    """One Instance per agent count min_agents, min_agents + agent_step, ... (the
+    first k agents of the scenario), named like the converter's output files."""
+    width, height, obst = load_movingai_map(map_path)
+    pairs = load_movingai_scen(scen_path, width, height, obst)
+    hi = len(pairs) if max_agents is None else min(len(pairs), max_agents)
+    out = []
+    for k in range(min_agents, hi + 1, agent_step):
+        starts = np.array([p[0] for p in pairs[:k]], np.int32).reshape(-1, 2)
+        goals = np.array([p[1] for p in pairs[:k]], np.int32).reshape(-1, 2)
+        out.append(Instance("%s_%d_agents" % (scen_path, k), width, height, obst, starts, goals))
+    return out
+
+
+# ---------------------------------------------------------------------------
 # Synthetic generators (SURVEY.md §8(d), configs C3 and C5) — stateless RNG so
 # CPU and GPU sides can regenerate identical inputs.
 # ---------------------------------------------------------------------------

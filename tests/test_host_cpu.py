@@ -64,3 +64,51 @@ def test_cli_fails_loudly_without_gpu(tmp_path):
                        text=True)
     assert r.returncode != 0 and "no CPU fallback" in r.stderr
     assert not os.path.exists(out)
+
+
+def _write_movingai(tmp_path):
+    rows = ["....@...", ".T......", "........", "..O....G", "S......W", "........"]
+    (tmp_path / "t.map").write_text("type octile\nheight 6\nwidth 8\nmap\n" + "\n".join(rows) + "\n")
+    scen = ["version 1"]
+    pairs = [(1, (0, 0), (7, 5)), (0, (7, 0), (0, 5)), (0, (3, 2), (5, 2)), (2, (0, 2), (7, 2))]
+    for b, s, g in pairs:
+        scen.append("\t".join(map(str, [b, "t.map", 8, 6, s[0], s[1], g[0], g[1], 7.0])))
+    (tmp_path / "t.scen").write_text("\n".join(scen) + "\n")
+    return str(tmp_path / "t.scen"), str(tmp_path / "t.map")
+
+
+def test_movingai_ingestion(tmp_path):
+    """movingai .map/.scen reader: slicing and naming of the reference's
+    standard_benchmark_converter.py, obstacles '@', 'T', 'O' kept."""
+    from libmultirobotplanning_b200 import instances as I
+    scen, mp = _write_movingai(tmp_path)
+    w, h, obst = I.load_movingai_map(mp)
+    assert (w, h) == (8, 6)
+    assert sorted(map(tuple, obst.tolist())) == [(1, 1), (2, 3), (4, 0)]
+    pairs = I.load_movingai_scen(scen, w, h, obst)
+    # sorted by bucket, stable inside a bucket
+    assert pairs == [((7, 0), (0, 5)), ((3, 2), (5, 2)), ((0, 0), (7, 5)), ((0, 2), (7, 2))]
+    insts = I.movingai_instances(scen, mp, min_agents=2, agent_step=1)
+    assert [i.n_agents for i in insts] == [2, 3, 4]
+    assert insts[0].name.endswith("_2_agents")
+    # round trip through the YAML the CLIs read
+    out = str(tmp_path / "x.yaml")
+    I.save_yaml(insts[2], out)
+    back = I.load_yaml(out)
+    assert np.array_equal(back.starts, insts[2].starts) and np.array_equal(back.goals, insts[2].goals)
+    assert np.array_equal(back.obstacles, insts[2].obstacles) and (back.dimx, back.dimy) == (8, 6)
+    # malformed inputs
+    (tmp_path / "bad.map").write_text("type octile\nheight 1\nwidth 2\nmap\n.x\n")
+    with pytest.raises(ValueError):
+        I.load_movingai_map(str(tmp_path / "bad.map"))
+    (tmp_path / "bad.scen").write_text("version 1\n0\tt.map\t8\t6\t4\t0\t1\t1\t1.0\n")
+    with pytest.raises(ValueError):
+        I.load_movingai_scen(str(tmp_path / "bad.scen"), 8, 6, obst)  # start on '@'
+
+
+def test_movingai_oracle_solves(tmp_path, orc):
+    from libmultirobotplanning_b200 import instances as I
+    scen, mp = _write_movingai(tmp_path)
+    inst = I.movingai_instances(scen, mp, min_agents=4, agent_step=1)[0]
+    r = orc.cbs(inst.dimx, inst.dimy, inst.obstacles, inst.starts, inst.goals)
+    assert r["status"] == 0 and r["cost"] >= 12 + 12 + 2 + 7
