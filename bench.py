@@ -183,16 +183,25 @@ def descend_paths(torch, fields, inst, starts_cell, n_agents, max_t):
     return table.contiguous(), length.contiguous()
 
 
+ECBS_BATCH = 1000  # replans of a lock-step iteration share one launch: throughput grows with the batch
+
+
 def search_metrics(pkg):
     """Instance throughput of the batched searches next to the oracle on one
-    host core (same caps).  ECBS: the 100-agent 32x32 files (config C3's base
-    case), w = 1.3.  CBS: the full 8x8 set (config C2) under an expansion cap."""
+    host core (same caps).  ECBS (config C3): all 1000 32x32_obst204 files
+    scaled to 100 agents (the 100-agent files as they are, the others with
+    instances.synthetic_c3), w = 1.3, one lock-step batch.  CBS: the full 8x8
+    set (config C2) under an expansion cap."""
     from oracle import orc
     out = {}
     g = os.path.join(ROOT, "tests", "golden")
     s32 = pkg.instances.load_set(os.path.join(g, "bench_32x32.npz"))
     s8 = pkg.instances.load_set(os.path.join(g, "bench_8x8.npz"))
     insts = [i for i in s32 if i.n_agents == 100]
+    n_files = len(insts)
+    # config C3: every other file of the set scaled to 100 agents (stateless RNG)
+    insts += [pkg.instances.synthetic_c3(b, k, 100)
+              for k, b in enumerate(i for i in s32 if i.n_agents != 100)][:ECBS_BATCH - n_files]
     cap_hl = 2000
     pkg.solver.solve_batch(pkg.solver.ECBS, insts[:2], w=1.3, max_hl=50)  # warm
     t0 = time.perf_counter()
@@ -200,8 +209,9 @@ def search_metrics(pkg):
     dt = time.perf_counter() - t0
     ok = [r for r in res if r["status"] == 0]
     out["ecbs_w1.3_instances_per_s"] = len(ok) / dt
-    out["ecbs_config"] = "32x32_obst204, 100 agents, %d instances in one lock-step batch, " \
-                         "cap %d high-level expansions" % (len(insts), cap_hl)
+    out["ecbs_config"] = "32x32_obst204, 100 agents, %d instances (%d benchmark files + %d scaled by " \
+                         "synthetic_c3) in one lock-step batch, cap %d high-level expansions" % (
+                             len(insts), n_files, len(insts) - n_files, cap_hl)
     out["ecbs_solved"] = "%d/%d" % (len(ok), len(insts))
     out["ecbs_seconds"] = dt
     out["ecbs_max_cost_over_lb"] = max(r["cost"] / r["lower_bound"] for r in ok) if ok else None

@@ -402,23 +402,31 @@ class BatchSolver {
       j.self = s.self;
     }
     // path tables of the other agents (ECBS focal heuristics)
-    std::vector<int32_t> tables, tlen;
+    std::vector<int32_t>& tables = m_llTables;
+    std::vector<int32_t>& tlen = m_llTlen;
+    const bool haveTables = !tableNodes.empty();
     int N = 0, Tpad = 0;
-    if (!tableNodes.empty()) packTables(tableNodes, tables, tlen, N, Tpad);
+    if (haveTables) packTables(tableNodes, tables, tlen, N, Tpad);
     mrp_lowlevel_params prm;
     prm.variant = isTA() ? 1 : 0;
     prm.w = isFocal() ? m_opt.w : 0.0f;
     prm.max_expanded = m_opt.maxLlExpanded;
     prm.path_cap = m_pathCap;
     std::vector<mrp_path_info> info(specs.size());
-    std::vector<int32_t> cells(specs.size() * (size_t)m_pathCap), gs(cells.size());
+    // output staging is kept across calls (no zero fill of tens of MB per launch)
+    if (m_llCells.size() < specs.size() * (size_t)m_pathCap) {
+      m_llCells.resize(specs.size() * (size_t)m_pathCap);
+      m_llGs.resize(m_llCells.size());
+    }
+    std::vector<int32_t>& cells = m_llCells;
+    std::vector<int32_t>& gs = m_llGs;
     const double tg = nowSeconds();
     m_prof.llPack += tg - tPack;
     m_prof.jobs += (long)specs.size();
     gpuCheck(mrp_lowlevel_batch_fs(m_maps.data(), (int)m_maps.size(), m_fields, vc.data(),
                                    (int)vc.size() / 2, ec.data(), (int)ec.size() / 3,
-                                   tables.empty() ? nullptr : tables.data(),
-                                   tlen.empty() ? nullptr : tlen.data(), (int)tableNodes.size(), N,
+                                   haveTables ? tables.data() : nullptr,
+                                   haveTables ? tlen.data() : nullptr, (int)tableNodes.size(), N,
                                    Tpad, jobs.data(), (int)jobs.size(), &prm, info.data(),
                                    cells.data(), gs.data()));
     const double tUn = nowSeconds();
@@ -448,7 +456,9 @@ class BatchSolver {
       for (const auto& p : n->paths)
         if (p) Tpad = std::max(Tpad, (int)p->cells.size());
     }
-    tables.assign(nodes.size() * (size_t)N * Tpad, 0);
+    // cells past a path's length are never read (the kernels clamp to len-1),
+    // so the tables are not cleared: only the lengths are
+    if (tables.size() < nodes.size() * (size_t)N * Tpad) tables.resize(nodes.size() * (size_t)N * Tpad);
     tlen.assign(nodes.size() * (size_t)N, 0);
 #pragma omp parallel for schedule(static)
     for (long b = 0; b < (long)nodes.size(); ++b)
@@ -465,7 +475,8 @@ class BatchSolver {
     if (fresh.empty()) return;
     const double tEp = nowSeconds();
     std::vector<const Node*> nodes(fresh.begin(), fresh.end());
-    std::vector<int32_t> tables, tlen;
+    std::vector<int32_t>& tables = m_evTables;
+    std::vector<int32_t>& tlen = m_evTlen;
     int N = 0, Tpad = 0;
     packTables(nodes, tables, tlen, N, Tpad);
     m_prof.evalPack += nowSeconds() - tEp;
@@ -741,6 +752,8 @@ class BatchSolver {
   mrp_fieldset m_fields = nullptr;
   const ConsPtr m_noCons = std::make_shared<const ConsList>();
   HostProfile m_prof;
+  // staging buffers reused across lock-step iterations
+  mutable std::vector<int32_t> m_llTables, m_llTlen, m_evTables, m_evTlen, m_llCells, m_llGs;
 };
 
 }  // namespace mrp_host

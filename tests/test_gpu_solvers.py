@@ -271,3 +271,36 @@ def test_reference_templates_drive_gpu_environment(capi, ref_fixtures, tmp_path)
             r = subprocess.run([exe, algo, inp] + extra, capture_output=True, text=True)
             assert r.returncode == 0, (name, algo, r.stderr[-300:])
             assert ("cost %d" % want) in r.stdout, (name, algo, r.stdout[-200:])
+
+
+def test_movingai_instance_cbs_and_ecbs(capi, orc, tmp_path):
+    """A movingai-format map (non-square, larger than one 32x32 tile, so the distance fields
+    come from the queue BFS kernel) through the ingestion path: CBS cost equals the oracle's,
+    ECBS stays within w."""
+    from libmultirobotplanning_b200 import instances as I
+    from libmultirobotplanning_b200 import solver
+    rng = np.random.default_rng(5)
+    W, H = 48, 40
+    grid = np.where(rng.random((H, W)) < 0.15, "@", ".")
+    grid[rng.random((H, W)) < 0.03] = "T"
+    free = [(x, y) for y in range(H) for x in range(W) if grid[y, x] == "."]
+    (tmp_path / "m.map").write_text("type octile\nheight %d\nwidth %d\nmap\n" % (H, W) +
+                                    "\n".join("".join(r) for r in grid) + "\n")
+    # starts / goals inside the largest component so that every agent has a path
+    _, _, obst = I.load_movingai_map(str(tmp_path / "m.map"))
+    f = orc.bfs_fields(W, H, obst, [free[0]])[0].reshape(H, W)
+    comp = [c for c in free if f[c[1], c[0]] != capi.INF]
+    pick = rng.choice(len(comp), 12, replace=False)
+    lines = ["version 1"]
+    for k in range(6):
+        s, g = comp[pick[2 * k]], comp[pick[2 * k + 1]]
+        lines.append("\t".join(map(str, [k // 2, "m.map", W, H, s[0], s[1], g[0], g[1], 1.0])))
+    (tmp_path / "m.scen").write_text("\n".join(lines) + "\n")
+    inst = I.movingai_instances(str(tmp_path / "m.scen"), str(tmp_path / "m.map"), 6, 1)[0]
+    want = orc.cbs(W, H, inst.obstacles, inst.starts, inst.goals)
+    assert want["status"] == 0
+    r = solver.solve_batch(solver.CBS, [inst], max_hl=20000)[0]
+    assert r["status"] == 0 and r["cost"] == want["cost"]
+    check_solution(inst, r["paths"], 0)
+    e = solver.solve_batch(solver.ECBS, [inst], w=1.2, max_hl=20000)[0]
+    assert e["status"] == 0 and want["cost"] <= e["cost"] <= np.float32(1.2) * np.float32(want["cost"])
