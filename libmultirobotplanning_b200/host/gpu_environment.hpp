@@ -8,8 +8,8 @@
 //
 // (the plan / neighbour containers are template parameters of the methods, so
 // both libMultiRobotPlanning::PlanResult / Neighbor and the look-alikes of
-// mapf_types.hpp work; oracle/ref_build/templates_gpuenv.cpp does exactly this
-// with the reference's headers):
+// mapf_types.hpp work; the parity tests instantiate the reference's own
+// cbs.hpp / ecbs.hpp / cbs_ta.hpp with these classes):
 //
 //   mrp_host::Environment mapf(dimx, dimy, obstacles, goals);
 //   libMultiRobotPlanning::CBS<State, Action, int, Conflict, Constraints,
