@@ -208,32 +208,33 @@ int mrp_map_create(int dimx, int dimy, const int32_t* obst_xy, int n_obst,
   m->S = S;
   m->h_bits = new uint32_t[bits.size()];
   std::memcpy(m->h_bits, bits.data(), bits.size() * 4);
-  // second layout: 8x4-cell tiles for the tiled BFS kernel
-  const int TW8 = (dimx + 7) / 8, TH4 = (dimy + 3) / 4;
-  std::vector<uint32_t> bits84((size_t)TW8 * TH4, 0u);
-  for (int y = 0; y < dimy; ++y)
-    for (int x = 0; x < dimx; ++x)
-      if ((bits[((size_t)(y >> 5) * W + (x >> 5)) * 32 + (y & 31)] >> (x & 31)) & 1u)
-        bits84[(size_t)(y >> 2) * TW8 + (x >> 3)] |= 1u << (((y & 3) << 3) | (x & 7));
-  // third layout: row-major with a zero border for the queue BFS kernel
-  const int WPR = ((dimx + 2 + 31) / 32) | 1;
-  std::vector<uint32_t> rowbits((size_t)(dimy + 4) * WPR, 0u);
-  for (int y = 0; y < dimy; ++y)
-    for (int x = 0; x < dimx; ++x)
-      if ((bits[((size_t)(y >> 5) * W + (x >> 5)) * 32 + (y & 31)] >> (x & 31)) & 1u)
-        rowbits[(size_t)(y + 1) * WPR + ((x + 1) >> 5)] |= 1u << ((x + 1) & 31);
   m->d_bits = nullptr;
   m->d_bits84 = nullptr;
   m->d_rowbits = nullptr;
   cudaError_t e = cudaMalloc(&m->d_bits, bits.size() * 4);
   if (e == cudaSuccess)
     e = cudaMemcpy(m->d_bits, bits.data(), bits.size() * 4, cudaMemcpyHostToDevice);
-  if (e == cudaSuccess) e = cudaMalloc(&m->d_bits84, bits84.size() * 4);
-  if (e == cudaSuccess)
-    e = cudaMemcpy(m->d_bits84, bits84.data(), bits84.size() * 4, cudaMemcpyHostToDevice);
-  if (e == cudaSuccess) e = cudaMalloc(&m->d_rowbits, rowbits.size() * 4);
-  if (e == cudaSuccess)
-    e = cudaMemcpy(m->d_rowbits, rowbits.data(), rowbits.size() * 4, cudaMemcpyHostToDevice);
+  if (W > 1 || S > 1) {
+    // maps larger than one 32x32 tile: the layouts of the large-map BFS kernels.
+    // second layout: 8x4-cell tiles for the tiled BFS kernel
+    const int TW8 = (dimx + 7) / 8, TH4 = (dimy + 3) / 4;
+    std::vector<uint32_t> bits84((size_t)TW8 * TH4, 0u);
+    // third layout: row-major with a zero border for the queue BFS kernel
+    const int WPR = ((dimx + 2 + 31) / 32) | 1;
+    std::vector<uint32_t> rowbits((size_t)(dimy + 4) * WPR, 0u);
+    for (int y = 0; y < dimy; ++y)
+      for (int x = 0; x < dimx; ++x)
+        if ((bits[((size_t)(y >> 5) * W + (x >> 5)) * 32 + (y & 31)] >> (x & 31)) & 1u) {
+          bits84[(size_t)(y >> 2) * TW8 + (x >> 3)] |= 1u << (((y & 3) << 3) | (x & 7));
+          rowbits[(size_t)(y + 1) * WPR + ((x + 1) >> 5)] |= 1u << ((x + 1) & 31);
+        }
+    if (e == cudaSuccess) e = cudaMalloc(&m->d_bits84, bits84.size() * 4);
+    if (e == cudaSuccess)
+      e = cudaMemcpy(m->d_bits84, bits84.data(), bits84.size() * 4, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMalloc(&m->d_rowbits, rowbits.size() * 4);
+    if (e == cudaSuccess)
+      e = cudaMemcpy(m->d_rowbits, rowbits.data(), rowbits.size() * 4, cudaMemcpyHostToDevice);
+  }
   if (e != cudaSuccess) {
     cudaFree(m->d_bits);
     cudaFree(m->d_bits84);

@@ -81,7 +81,7 @@ enum class Algo { CBS = 0, ECBS = 1, CBSTA = 2, ECBSTA = 3 };
 
 // wall-clock split of a batch run, printed when MRP_HOST_PROFILE is set
 struct HostProfile {
-  double gpuConflicts = 0, gpuLowLevel = 0, total = 0;
+  double gpuConflicts = 0, gpuLowLevel = 0, total = 0, setup = 0;
   double pop = 0, build = 0, llPack = 0, llUnpack = 0, evalPack = 0, absorb = 0;
   long iterations = 0, nodes = 0, jobs = 0;
 };
@@ -122,7 +122,9 @@ class BatchSolver {
   std::vector<SolveResult> run() {
     std::vector<SolveResult> out(m_inst.size());
     if (m_inst.empty()) return out;
+    const double tSetup = nowSeconds();
     setup();
+    m_prof.setup = nowSeconds() - tSetup;
     const auto t0 = std::chrono::steady_clock::now();
     auto elapsed = [&t0]() {
       return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
@@ -133,7 +135,7 @@ class BatchSolver {
     while (true) {
       ++m_prof.iterations;
       evaluate(fresh);
-      for (Node* n : fresh) m_inst[n->inst].open.insert(n);
+      insertFresh(fresh);
       fresh.clear();
       if (m_algo == Algo::ECBSTA) spawnMinRoots();
       // one expansion per running instance
@@ -143,6 +145,9 @@ class BatchSolver {
       const bool timeUp = m_opt.maxSeconds > 0 && elapsed() > m_opt.maxSeconds;
       const double tNow = elapsed();
       std::vector<std::unique_ptr<Node> > popped(m_inst.size());
+      // instances are independent: the per-instance bookkeeping of a lock-step
+      // iteration runs on all host cores
+#pragma omp parallel for schedule(dynamic, 16) if (m_inst.size() >= kParallelMin)
       for (long k = 0; k < (long)m_inst.size(); ++k) {
         Inst& I = m_inst[k];
         if (I.done) continue;
@@ -173,6 +178,9 @@ class BatchSolver {
       m_prof.pop += nowSeconds() - tPop;
       if (!anyRunning) break;
       expand(pending, fresh);
+      // the expanded parents are released on all cores as well
+#pragma omp parallel for schedule(dynamic, 16) if (pending.size() >= kParallelMin)
+      for (long pi = 0; pi < (long)pending.size(); ++pi) pending[pi].parent.reset();
     }
     for (size_t k = 0; k < m_inst.size(); ++k) out[k] = std::move(m_inst[k].res);
     m_prof.total = nowSeconds() - tRun;
@@ -180,11 +188,12 @@ class BatchSolver {
       fprintf(stderr,
               "[mrp_host] %zu instances, %ld lock-step iterations, %ld nodes, %ld replans: "
               "total %.3fs = conflicts(gpu call) %.3fs + replans(gpu call) %.3fs + host %.3fs "
-              "[pop %.2f build %.2f llPack %.2f llUnpack %.2f evalPack %.2f absorb %.2f]\n",
+              "[pop %.2f build %.2f llPack %.2f llUnpack %.2f evalPack %.2f absorb %.2f]; "
+              "setup (maps + distance fields, outside the reference's timer too) %.3fs\n",
               m_inst.size(), m_prof.iterations, m_prof.nodes, m_prof.jobs, m_prof.total,
               m_prof.gpuConflicts, m_prof.gpuLowLevel,
               m_prof.total - m_prof.gpuConflicts - m_prof.gpuLowLevel, m_prof.pop, m_prof.build,
-              m_prof.llPack, m_prof.llUnpack, m_prof.evalPack, m_prof.absorb);
+              m_prof.llPack, m_prof.llUnpack, m_prof.evalPack, m_prof.absorb, m_prof.setup);
     return out;
   }
 
@@ -210,6 +219,9 @@ class BatchSolver {
     int found = 0;
     mrp_conflict conflict;
   };
+  // batches smaller than this stay on the calling thread (a single instance from
+  // the command-line binaries must not wake a thread team per iteration)
+  static constexpr size_t kParallelMin = 64;
   bool isTA() const { return m_algo == Algo::CBSTA || m_algo == Algo::ECBSTA; }
   bool isFocal() const { return m_algo == Algo::ECBS || m_algo == Algo::ECBSTA; }
 
@@ -330,6 +342,21 @@ class BatchSolver {
     }
     for (Node* o : I.open) delete o;
     I.open.clear();
+  }
+
+  // pushes the evaluated nodes into the OPEN lists of their instances; `fresh`
+  // holds the nodes of one instance in consecutive positions
+  void insertFresh(const std::vector<Node*>& fresh) {
+    std::vector<std::pair<size_t, size_t> > runs;
+    for (size_t i = 0; i < fresh.size();) {
+      size_t j = i + 1;
+      while (j < fresh.size() && fresh[j]->inst == fresh[i]->inst) ++j;
+      runs.push_back(std::make_pair(i, j));
+      i = j;
+    }
+#pragma omp parallel for schedule(dynamic, 16) if (runs.size() >= kParallelMin)
+    for (long r = 0; r < (long)runs.size(); ++r)
+      for (size_t i = runs[r].first; i < runs[r].second; ++i) m_inst[fresh[i]->inst].open.insert(fresh[i]);
   }
 
   std::unique_ptr<Node> popBest(Inst& I) {
@@ -460,7 +487,7 @@ class BatchSolver {
     // so the tables are not cleared: only the lengths are
     if (tables.size() < nodes.size() * (size_t)N * Tpad) tables.resize(nodes.size() * (size_t)N * Tpad);
     tlen.assign(nodes.size() * (size_t)N, 0);
-#pragma omp parallel for schedule(static)
+#pragma omp parallel for schedule(static) if (nodes.size() >= kParallelMin)
     for (long b = 0; b < (long)nodes.size(); ++b)
       for (size_t a = 0; a < nodes[b]->paths.size(); ++a) {
         if (!nodes[b]->paths[a]) continue;  // not planned yet (ECBS root construction)
@@ -640,17 +667,17 @@ class BatchSolver {
       bool failed = false;
     };
     const double tBuild = nowSeconds();
-    std::vector<ChildPlan> plans;
-    std::vector<JobSpec> specs;
-    std::vector<const Node*> tabs;
-    for (size_t pi = 0; pi < pending.size(); ++pi) {
+    // every pending parent builds its children on its own (all host cores),
+    // then the plans / job specs are concatenated in pending order
+    std::vector<std::vector<ChildPlan> > localPlans(pending.size());
+    std::vector<std::vector<JobSpec> > localSpecs(pending.size());
+#pragma omp parallel for schedule(dynamic, 16) if (pending.size() >= kParallelMin)
+    for (long pi = 0; pi < (long)pending.size(); ++pi) {
+      std::vector<ChildPlan>& plans = localPlans[pi];
+      std::vector<JobSpec>& specs = localSpecs[pi];
       Inst& I = m_inst[pending[pi].inst];
       const Node& P = *pending[pi].parent;
-      int tableIdx = -1;
-      if (isFocal()) {
-        tableIdx = (int)tabs.size();
-        tabs.push_back(&P);
-      }
+      const int tableIdx = isFocal() ? (int)pi : -1;  // tabs[pi] = the parent of pending[pi]
       if (m_algo == Algo::CBSTA && P.isRoot) {
         // an expanded root with a conflict spawns the next-best assignment as
         // a new root (cbs_ta.hpp:142-172).  The reference copies isRoot into
@@ -705,43 +732,64 @@ class BatchSolver {
         plans.push_back(std::move(cp));
       }
     }
+    std::vector<ChildPlan> plans;
+    std::vector<JobSpec> specs;
+    std::vector<const Node*> tabs;
+    std::vector<size_t> firstPlan(pending.size() + 1, 0);
+    for (size_t pi = 0; pi < pending.size(); ++pi) {
+      if (isFocal()) tabs.push_back(pending[pi].parent.get());
+      const size_t base = specs.size();
+      for (ChildPlan& cp : localPlans[pi]) {
+        cp.firstJob += base;
+        plans.push_back(std::move(cp));
+      }
+      specs.insert(specs.end(), localSpecs[pi].begin(), localSpecs[pi].end());
+      firstPlan[pi + 1] = plans.size();
+    }
     std::vector<JobOut> outs;
     m_prof.build += nowSeconds() - tBuild;
     runLowLevel(specs, tabs, outs);
     const double tAbs = nowSeconds();
-    for (ChildPlan& cp : plans) {
-      Inst& I = m_inst[pending[cp.pendingIdx].inst];
-      if (I.done) continue;
-      Node& n = *cp.node;
-      bool ok = true, capped = false;
-      for (size_t j = cp.firstJob; j < cp.firstJob + cp.nJobs; ++j) {
-        if (outs[j].status == 2) capped = true;
-        if (outs[j].status != 0) ok = false;
+    std::vector<Node*> made(plans.size(), nullptr);
+#pragma omp parallel for schedule(dynamic, 16) if (pending.size() >= kParallelMin)
+    for (long pi = 0; pi < (long)pending.size(); ++pi) {
+      Inst& I = m_inst[pending[pi].inst];
+      for (size_t q = firstPlan[pi]; q < firstPlan[pi + 1]; ++q) {
+        ChildPlan& cp = plans[q];
+        if (I.done) continue;
+        Node& n = *cp.node;
+        bool ok = true, capped = false;
+        for (size_t j = cp.firstJob; j < cp.firstJob + cp.nJobs; ++j) {
+          if (outs[j].status == 2) capped = true;
+          if (outs[j].status != 0) ok = false;
+        }
+        if (capped) {  // a capped replan could hide the optimum: give up honestly
+          finish(I, kCapped, nullptr, 0);
+          continue;
+        }
+        if (!ok) continue;  // no path under these constraints: the child is dropped
+        for (size_t j = cp.firstJob; j < cp.firstJob + cp.nJobs; ++j) {
+          const int a = specs[j].agent;
+          n.cost += outs[j].path.cost;
+          n.LB += outs[j].path.fmin;
+          n.paths[a] = std::make_shared<const AgentPath>(std::move(outs[j].path));
+        }
+        n.id = I.nextId++;
+        made[q] = cp.node.release();
       }
-      if (capped) {  // a capped replan could hide the optimum: give up honestly
-        finish(I, kCapped, nullptr, 0);
-        continue;
-      }
-      if (!ok) continue;  // no path under these constraints: the child is dropped
-      for (size_t j = cp.firstJob; j < cp.firstJob + cp.nJobs; ++j) {
-        const int a = specs[j].agent;
-        n.cost += outs[j].path.cost;
-        n.LB += outs[j].path.fmin;
-        n.paths[a] = std::make_shared<const AgentPath>(std::move(outs[j].path));
-      }
-      n.id = I.nextId++;
-      fresh.push_back(cp.node.release());
     }
+    for (Node* n : made)
+      if (n) fresh.push_back(n);
     m_prof.absorb += nowSeconds() - tAbs;
     // children of instances that were finished meanwhile must not leak
-    for (auto it = fresh.begin(); it != fresh.end();) {
-      if (m_inst[(*it)->inst].done) {
-        delete *it;
-        it = fresh.erase(it);
-      } else {
-        ++it;
-      }
+    size_t keep = 0;
+    for (size_t i = 0; i < fresh.size(); ++i) {
+      if (m_inst[fresh[i]->inst].done)
+        delete fresh[i];
+      else
+        fresh[keep++] = fresh[i];
     }
+    fresh.resize(keep);
   }
 
   Algo m_algo;

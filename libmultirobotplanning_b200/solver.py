@@ -24,6 +24,9 @@ def lib():
         if not os.path.exists(LIB_PATH):
             raise _capi.MrpError(-1, "%s not found: run __graft_entry__.build()" % LIB_PATH)
         _capi.lib()  # libmrp_b200.so first (dependency)
+        # the OpenMP team of the host driver sleeps between parallel regions:
+        # spinning workers would fight the CUDA driver threads for the cores
+        os.environ.setdefault("OMP_WAIT_POLICY", "PASSIVE")
         _lib = C.CDLL(LIB_PATH)
         _lib.mrph_last_error.restype = C.c_char_p
     return _lib
