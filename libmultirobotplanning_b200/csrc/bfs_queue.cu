@@ -17,7 +17,11 @@
 //     A thread tests its 4 neighbours in `open`, claims the open ones with a
 //     shared-memory atomicAnd (exactly one winner per cell), stores the level
 //     into the int32 field and appends the cell to the next queue; queue
-//     slots are handed out with one atomic per warp (ballot ranking).
+//     slots are handed out with one atomic per warp (one ballot per direction
+//     ranks the winners).  A level costs about as many cycles as the
+//     instructions on a warp's path through it (a dependent instruction
+//     issues every ~4 cycles), so the body is kept short: bit-position
+//     entries, row offsets as immediates, no bounds check on the slot.
 //   * One barrier per level: queues are double-buffered and the three level
 //     counters rotate, so nothing has to be reset between two barriers.
 //   * MRP_INF (obstacles, other components) is written AHEAD of the wavefront
@@ -47,8 +51,9 @@ struct BfsQueueParams {
   int dimx, dimy;
   int WPR;       // words per bitmap row (odd)
   int nOpenWords;
-  int cap;       // queue capacity (entries)
-  int dbg;       // debug: bit0 = skip the field stores of the level loop
+  int cap;       // queue capacity (entries, a power of two)
+  uint32_t wprMagic;  // row of bitmap word w = umulhi(w, wprMagic) >> wprShift  (= w / WPR)
+  int wprShift;
 };
 
 #ifdef MRP_BFS_TIMING
@@ -135,6 +140,76 @@ __device__ __forceinline__ void templateRing(int32_t* __restrict__ out, int R, i
   }
 }
 
+// Claims with the row offset as an immediate when the row stride is a
+// compile-time constant.
+template <int kOff>
+__device__ __forceinline__ uint32_t atomAndOff(uint32_t addr, uint32_t mask) {
+  uint32_t old;
+  asm volatile("atom.shared.and.b32 %0, [%1+%3], %2;" : "=r"(old) : "r"(addr), "r"(mask), "n"(kOff) : "memory");
+  return old;
+}
+template <int kOff>
+__device__ __forceinline__ void stGlobalOffIf(void* ptr, int32_t v, bool pred) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\t@p st.global.u32 [%0+%3], %1;\n\t}" ::"l"(ptr),
+               "r"(v), "r"((uint32_t)pred), "n"(kOff)
+               : "memory");
+}
+
+// Tail of a cell expansion: win tests, ranking, slot allocation, queue
+// appends and level stores (see the call site).  pcU/pcD + kOffU/kOffD are the
+// field addresses of the upper and lower neighbour, pc -+ 4 the left and right.
+template <int kOffU, int kOffD>
+__device__ __forceinline__ void appendAndStore(uint32_t oU, uint32_t oD, uint32_t oL, uint32_t oR, uint32_t bit,
+                                               uint32_t bitL, uint32_t bitR, uint32_t ltMask, uint32_t slotA,
+                                               uint32_t lane0Mask, uint32_t qnS, uint32_t capMask, uint32_t eU,
+                                               uint32_t eD, uint32_t e, char* pcU, char* pcD, int level) {
+  char* const pc = kOffU != 0 ? pcU : pcU + (pcD - pcU) / 2;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred pu, pd, pl, pr;\n\t"
+      ".reg .b32 x, bu, bd, bl, br, nu, nd, nl, nr, nud, nudl, tot, slot, ru, rd, rl, rr, qb, a, v;\n\t"
+      "and.b32 x, %0, %4;\n\tsetp.ne.u32 pu, x, 0;\n\t"
+      "and.b32 x, %1, %4;\n\tsetp.ne.u32 pd, x, 0;\n\t"
+      "and.b32 x, %2, %5;\n\tsetp.ne.u32 pl, x, 0;\n\t"
+      "and.b32 x, %3, %6;\n\tsetp.ne.u32 pr, x, 0;\n\t"
+      "vote.sync.ballot.b32 bu, pu, 0xffffffff;\n\t"
+      "vote.sync.ballot.b32 bd, pd, 0xffffffff;\n\t"
+      "vote.sync.ballot.b32 bl, pl, 0xffffffff;\n\t"
+      "vote.sync.ballot.b32 br, pr, 0xffffffff;\n\t"
+      "popc.b32 nu, bu;\n\tpopc.b32 nd, bd;\n\tpopc.b32 nl, bl;\n\tpopc.b32 nr, br;\n\t"
+      "add.u32 nud, nu, nd;\n\tadd.u32 nudl, nud, nl;\n\tadd.u32 tot, nudl, nr;\n\t"
+      "and.b32 x, tot, %9;\n\t"
+      "atom.shared.add.u32 slot, [%8], x;\n\t"
+      "and.b32 x, bu, %7;\n\tpopc.b32 ru, x;\n\t"
+      "and.b32 x, bd, %7;\n\tpopc.b32 rd, x;\n\tadd.u32 rd, rd, nu;\n\t"
+      "and.b32 x, bl, %7;\n\tpopc.b32 rl, x;\n\tadd.u32 rl, rl, nud;\n\t"
+      "and.b32 x, br, %7;\n\tpopc.b32 rr, x;\n\tadd.u32 rr, rr, nudl;\n\t"
+      "shfl.sync.idx.b32 slot, slot, 0, 0x1f, 0xffffffff;\n\t"
+      "and.b32 slot, slot, %11;\n\t"
+      "mad.lo.u32 qb, slot, 4, %10;\n\t"
+      "mad.lo.u32 a, ru, 4, qb;\n\t@pu st.shared.u32 [a], %12;\n\t"
+      "mad.lo.u32 a, rd, 4, qb;\n\t@pd st.shared.u32 [a], %13;\n\t"
+      "mad.lo.u32 a, rl, 4, qb;\n\tadd.u32 v, %14, -1;\n\t@pl st.shared.u32 [a], v;\n\t"
+      "mad.lo.u32 a, rr, 4, qb;\n\tadd.u32 v, %14, 1;\n\t@pr st.shared.u32 [a], v;\n\t"
+      "@pu st.global.u32 [%15+%19], %18;\n\t"
+      "@pd st.global.u32 [%16+%20], %18;\n\t"
+      "@pl st.global.u32 [%17+-4], %18;\n\t"
+      "@pr st.global.u32 [%17+4], %18;\n\t"
+      "}" ::"r"(oU),
+      "r"(oD), "r"(oL), "r"(oR), "r"(bit), "r"(bitL), "r"(bitR), "r"(ltMask), "r"(slotA), "r"(lane0Mask), "r"(qnS),
+      "r"(capMask), "r"(eU), "r"(eD), "r"(e), "l"(pcU), "l"(pcD), "l"(pc), "r"(level), "n"(kOffU), "n"(kOffD)
+      : "memory");
+}
+
+// kWPR / kDimX: words per bitmap row and cells per map row as compile-time
+// constants (0 = read them from the parameters).  The 1024-column map of the
+// headline configuration gets its own instance: row offsets become immediates.
+//
+// A queue entry is the BIT POSITION of the cell in the bordered bitmap,
+// e = (y + 1) * 32 * WPR + (x + 1): word = e >> 5, bit = e & 31, the four
+// neighbours are e -+ 32*WPR and e -+ 1, and the field index follows from
+// e - (e / (32*WPR)) * (32*WPR - dimx).
+template <int kWPR, int kDimX>
 __global__ void __launch_bounds__(1024, 1) bfs_queue_kernel(BfsQueueParams p) {
   extern __shared__ uint32_t smem[];
   __shared__ int sCount[3];
@@ -143,12 +218,17 @@ __global__ void __launch_bounds__(1024, 1) bfs_queue_kernel(BfsQueueParams p) {
   const int tid = threadIdx.x, lane = tid & 31;
   const int nThreads = blockDim.x;
   const uint32_t ltMask = (1u << lane) - 1u;
-  const int WPR = p.WPR, dimx = p.dimx, cap = p.cap;
-  const int cells = p.dimx * p.dimy;
+  const int WPR = kWPR ? kWPR : p.WPR, dimx = kDimX ? kDimX : p.dimx, cap = p.cap;
+  const uint32_t S = 32u * (uint32_t)WPR;          // bitmap bits per row
+  const uint32_t padBits = S - (uint32_t)dimx;     // e - Y * padBits - (dimx + 1) = field index
+  const int cells = dimx * p.dimy;
   uint32_t* open = smem;
   uint32_t* q0 = smem + ((p.nOpenWords + 3) & ~3);
   const uint32_t openS = pin((uint32_t)__cvta_generic_to_shared(open));
-  const uint32_t q0S = pin((uint32_t)__cvta_generic_to_shared(q0)), q1S = q0S + 4u * (uint32_t)cap;
+  // each queue is followed by 128 words of slack: a warp appends at most 96
+  // entries, and the slot index is wrapped instead of bounds-checked
+  const uint32_t q0S = pin((uint32_t)__cvta_generic_to_shared(q0)), q1S = q0S + 4u * (uint32_t)(cap + 128);
+  const uint32_t capMask = (uint32_t)cap - 1u;     // cap is a power of two
   const uint32_t cntS = pin((uint32_t)__cvta_generic_to_shared(sCount));
   // slot allocation: lane 0 adds to the level counter, the other lanes add 0
   // to private scratch words (one ATOMS for the warp, and no uniform address
@@ -156,10 +236,9 @@ __global__ void __launch_bounds__(1024, 1) bfs_queue_kernel(BfsQueueParams p) {
   const uint32_t scrS = pin((uint32_t)__cvta_generic_to_shared(sScratch) + 4u * (uint32_t)lane);
   // cells of the zero rows below the map: all four neighbours are closed (one
   // word per lane, so the idle lanes of a warp do not collide)
-  const uint32_t dummy = ((uint32_t)(p.dimy + 2) << 16) | (32u * (uint32_t)(lane % WPR) + 1u);
+  const uint32_t dummy = (uint32_t)(p.dimy + 2) * S + 32u * (uint32_t)(lane % WPR) + 1u;
   const uint32_t rowB = 4u * (uint32_t)WPR;
   const size_t outRowB = 4 * (size_t)dimx;
-  const uint32_t nodbg = (p.dbg & 1) ? 0u : 1u;
   // 16-byte stores for the template when rows and the buffer allow it
   const bool vec = (dimx & 3) == 0 && (reinterpret_cast<uintptr_t>(p.out) & 15) == 0;
   const int ringFirst = nThreads >= 256 ? nThreads - 128 : nThreads - 32;
@@ -201,14 +280,13 @@ __global__ void __launch_bounds__(1024, 1) bfs_queue_kernel(BfsQueueParams p) {
     if (goalFree) {
       if (tid == 0) {
         // levels 0 and 1 by one thread: the goal and its (up to 4) open
-        // neighbours.  From level 2 on every frontier cell has a visited
-        // neighbour, so a cell appends at most 3 cells (2 ballots rank them).
+        // neighbours
         open[gw] &= ~gbit;
         out[goal] = 0;
-        const uint32_t ge = ((uint32_t)(gy + 1) << 16) | (uint32_t)(gx + 1);
+        const uint32_t ge = (uint32_t)(gy + 1) * S + (uint32_t)(gx + 1);
         const int dwi[4] = {-WPR, WPR, ((gx + 1) & 31) == 0 ? -1 : 0, ((gx + 1) & 31) == 31 ? 1 : 0};
         const int dbit[4] = {0, 0, -1, 1};
-        const uint32_t de[4] = {0xffff0000u, 0x10000u, 0xffffffffu, 1u};
+        const uint32_t de[4] = {0u - S, S, 0xffffffffu, 1u};
         const int dout[4] = {-dimx, dimx, -1, 1};
         int n = 0;
         for (int k = 0; k < 4; ++k) {
@@ -227,7 +305,8 @@ __global__ void __launch_bounds__(1024, 1) bfs_queue_kernel(BfsQueueParams p) {
 #endif
       // counters of the current level, the next level, and the one to reset
       uint32_t aCi = cntS + 8u, aNi = cntS, aRi = cntS + 4u;
-      // field address of bitmap cell (X, Y) = outb + 4 * (Y * dimx + X)
+      // field address of the cell at bit position e in row Y:
+      //   outb + 4 * (e - Y * padBits)
       char* const outb = reinterpret_cast<char*>(out) - 4 * (size_t)(dimx + 1);
       int count, level;
       for (level = 2;; ++level) {
@@ -239,7 +318,7 @@ __global__ void __launch_bounds__(1024, 1) bfs_queue_kernel(BfsQueueParams p) {
                      : "r"(aCi), "r"(qcS + firstOff)
                      : "memory");
         // a level that outgrew the queue ends the attempt (the counter keeps
-        // counting past the capacity, the entries are dropped)
+        // counting past the capacity, the entries wrap around)
         if (count == 0 || count > cap) break;
         if (tid == 0) stShared(aRi, 0u);
         // template ring of this level, by the last warps of the CTA (the
@@ -251,44 +330,44 @@ __global__ void __launch_bounds__(1024, 1) bfs_queue_kernel(BfsQueueParams p) {
           g_bfsqLevels[level][1] = (unsigned)clock64();
         }
 #endif
+        // slot counter of this level for lane 0, a private word for the others
+        const uint32_t slotA = lane == 0 ? aNi : scrS;
+        const uint32_t lane0Mask = lane == 0 ? 0xffffffffu : 0u;
         for (int i = tid; i - lane < count;) {
           // lanes past the end expand a dummy cell whose neighbourhood is closed
           if (i >= count) e = dummy;
-          const uint32_t X = e & 0xffffu, Y = e >> 16;
-          const uint32_t b = X & 31u;
-          const uint32_t aC = openS + 4u * (Y * (uint32_t)WPR + (X >> 5));
+          const uint32_t b = e & 31u, w = e >> 5;
+          const uint32_t aC = openS + 4u * w;
           const uint32_t aL = b == 0u ? aC - 4u : aC, aR = b == 31u ? aC + 4u : aC;
           const uint32_t bit = 1u << b;
           const uint32_t bitL = __funnelshift_r(bit, bit, 1), bitR = __funnelshift_l(bit, bit, 1);
           // claims: four independent atomics in flight, no pre-check (an ATOMS
           // costs the same LSU time whatever the number of active lanes, and a
           // bit only ever goes 1 -> 0)
-          const uint32_t oU = atomAnd(aC - rowB, ~bit), oD = atomAnd(aC + rowB, ~bit);
+          uint32_t oU, oD;
+          if constexpr (kWPR != 0) {
+            oU = atomAndOff<-4 * kWPR>(aC, ~bit);
+            oD = atomAndOff<4 * kWPR>(aC, ~bit);
+          } else {
+            oU = atomAnd(aC - rowB, ~bit);
+            oD = atomAnd(aC + rowB, ~bit);
+          }
           const uint32_t oL = atomAnd(aL, ~bitL), oR = atomAnd(aR, ~bitR);
-          char* const pc = outb + 4 * (size_t)(Y * (uint32_t)dimx + X);  // this cell in the field
-          const uint32_t tU = (oU >> b) & 1u, tD = (oD >> b) & 1u;
-          const uint32_t tL = (oL & bitL) != 0u, tR = (oR & bitR) != 0u;
-          // queue slots: a cell appends c <= 3 cells; two ballots (the bits of
-          // c) rank them, one atomic per warp
-          const uint32_t c = tU + tD + tL + tR;
-          const uint32_t B0 = __ballot_sync(0xffffffffu, c & 1u);
-          const uint32_t B1 = __ballot_sync(0xffffffffu, c & 2u);
-          const uint32_t total = __popc(B0) + 2 * __popc(B1);
-          if (total != 0) {
-            uint32_t slot = atomAddShared(lane == 0 ? aNi : scrS, lane == 0 ? total : 0u);
-            slot = __shfl_sync(0xffffffffu, slot, 0);
-            if (slot + total <= (uint32_t)cap) {
-              const uint32_t qU = qnS + 4u * (slot + __popc(B0 & ltMask) + 2 * __popc(B1 & ltMask));
-              const uint32_t qD = qU + 4u * tU, qL = qD + 4u * tD, qR = qL + 4u * tL;
-              stSharedIf(qU, e - 0x10000u, tU);
-              stSharedIf(qD, e + 0x10000u, tD);
-              stSharedIf(qL, e - 1u, tL);
-              stSharedIf(qR, e + 1u, tR);
-              stGlobalIf(pc - outRowB, level, tU & nodbg);
-              stGlobalIf(pc + outRowB, level, tD & nodbg);
-              stGlobalIf(pc - 4, level, tL & nodbg);
-              stGlobalIf(pc + 4, level, tR & nodbg);
-            }
+          // this cell in the field (row Y of the bitmap = word / WPR)
+          const uint32_t Y = kWPR ? w / (uint32_t)(kWPR ? kWPR : 1) : __umulhi(w, p.wprMagic) >> p.wprShift;
+          char* const pc = outb + 4 * (size_t)(e - Y * padBits);
+          // winners, queue slots and stores in one PTX block (the four win
+          // predicates stay in predicate registers from the test to the
+          // stores).  Slots are direction-major inside the warp's block: one
+          // ballot per direction ranks the winners, one atomic per warp (lane 0
+          // adds the total, the other lanes add 0 to private words) allocates,
+          // and the slot index wraps at the capacity instead of being checked.
+          if constexpr (kDimX != 0) {
+            appendAndStore<-4 * kDimX, 4 * kDimX>(oU, oD, oL, oR, bit, bitL, bitR, ltMask, slotA, lane0Mask, qnS,
+                                                  capMask, e - S, e + S, e, pc, pc, level);
+          } else {
+            appendAndStore<0, 0>(oU, oD, oL, oR, bit, bitL, bitR, ltMask, slotA, lane0Mask, qnS, capMask, e - S,
+                                 e + S, e, pc - outRowB, pc + outRowB, level);
           }
           i += nThreads;
           if (i - lane >= count) break;
@@ -335,6 +414,8 @@ struct QueueGeom {
   bool fits;
 };
 
+constexpr int kQueueSlack = 128;  // words behind each queue (see the kernel)
+
 static QueueGeom queueGeometry(const mrp_map_s* map) {
   QueueGeom q;
   q.WPR = ((map->dimx + 2 + 31) / 32) | 1;
@@ -345,13 +426,18 @@ static QueueGeom queueGeometry(const mrp_map_s* map) {
   if (const char* e = getenv("MRP_BFS_THREADS")) th = atoi(e);
   q.threads = th;
   // a wavefront on an open grid holds < 2*(dimx+dimy) cells; leave 4x room
-  size_t cap = std::min<size_t>(8192, std::max<size_t>(256, 4 * (size_t)span));
+  // (rounded up to a power of two: the slot index is wrapped, not checked)
+  size_t cap = 256;
+  while (cap < 8192 && cap < 4 * (size_t)span) cap *= 2;
   const size_t openBytes = (size_t)((q.nOpenWords + 3) & ~3) * 4;
   const size_t limit = ctx().smemOptin - 1024;
-  while (cap > 256 && openBytes + 2 * cap * 4 > limit) cap /= 2;
-  if (const char* e = getenv("MRP_BFS_QCAP")) cap = std::max(32, atoi(e));
+  while (cap > 256 && openBytes + 2 * (cap + kQueueSlack) * 4 > limit) cap /= 2;
+  if (const char* e = getenv("MRP_BFS_QCAP")) {
+    cap = 32;
+    while ((int)cap < atoi(e)) cap *= 2;
+  }
   q.cap = (int)cap;
-  q.smemBytes = openBytes + 2 * cap * 4;
+  q.smemBytes = openBytes + 2 * (cap + kQueueSlack) * 4;
   q.fits = q.smemBytes <= limit && map->dimx < 65534 && map->dimy < 65534;
   return q;
 }
@@ -361,12 +447,19 @@ bool bfsQueueFits(const mrp_map_s* map) {
   return queueGeometry(map).fits;
 }
 
-static int queueBlocks(const QueueGeom& q) {
-  cudaFuncSetAttribute(bfs_queue_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                       (int)q.smemBytes);
+typedef void (*QueueKernel)(BfsQueueParams);
+
+// the instance for this map: row strides as immediates for 1024-column maps
+static QueueKernel queueKernelFor(const mrp_map_s* map, const QueueGeom& q) {
+  if (map->dimx == 1024 && q.WPR == 33 && !getenv("MRP_BFS_GENERIC")) return bfs_queue_kernel<33, 1024>;
+  return bfs_queue_kernel<0, 0>;
+}
+
+static int queueBlocks(QueueKernel fn, const QueueGeom& q) {
+  cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)q.smemBytes);
   int perSm = 1;
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, bfs_queue_kernel, q.threads,
-                                                    q.smemBytes) != cudaSuccess ||
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, fn, q.threads, q.smemBytes) !=
+          cudaSuccess ||
       perSm < 1)
     perSm = 1;
   if (perSm > 8) perSm = 8;
@@ -393,11 +486,16 @@ int launchBfsQueue(const mrp_map_s* map, const int32_t* d_goal_cell, int n_goals
   p.WPR = q.WPR;
   p.nOpenWords = q.nOpenWords;
   p.cap = q.cap;
-  p.dbg = getenv("MRP_BFS_DBG") ? atoi(getenv("MRP_BFS_DBG")) : 0;
+  // w / WPR for w < 2^27 (exact): magic = ceil(2^(32+s) / WPR), s = floor(log2 WPR)
+  int sh = 0;
+  while ((2 << sh) <= q.WPR) ++sh;
+  p.wprShift = sh;
+  p.wprMagic = (uint32_t)((((unsigned long long)1 << (32 + sh)) + (unsigned)q.WPR - 1) / (unsigned)q.WPR);
   MRP_CUDA(cudaMemsetAsync(d_ws, 0, 64 * 4, st));
-  int blocks = queueBlocks(q);
+  const QueueKernel fn = queueKernelFor(map, q);
+  int blocks = queueBlocks(fn, q);
   if (blocks > n_goals) blocks = n_goals;
-  bfs_queue_kernel<<<blocks, q.threads, q.smemBytes, st>>>(p);
+  fn<<<blocks, q.threads, q.smemBytes, st>>>(p);
   countLaunch();
   MRP_CUDA(cudaGetLastError());
   return 0;
