@@ -15,8 +15,8 @@
 //     the cells of a diagonal wavefront fall into distinct banks.
 //   * A level is a compacted queue of frontier cells, one thread per cell.
 //     A thread tests its 4 neighbours in `open`, claims the open ones with a
-//     shared-memory atomicAnd (exactly one winner per cell), stores the level
-//     into the int32 field and appends the cell to the next queue; queue
+//     shared-memory atomicAnd (exactly one winner per cell), stores its own
+//     level into the int32 field and appends the winners to the next queue; queue
 //     slots are handed out with one atomic per warp (one ballot per direction
 //     ranks the winners).  A level costs about as many cycles as the
 //     instructions on a warp's path through it (a dependent instruction
@@ -89,11 +89,6 @@ __device__ __forceinline__ void stSharedIf(uint32_t addr, uint32_t v, uint32_t p
                "r"(v), "r"(pred)
                : "memory");
 }
-__device__ __forceinline__ void stGlobalIf(void* ptr, int32_t v, uint32_t pred) {
-  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\t@p st.global.u32 [%0], %1;\n\t}" ::"l"(ptr),
-               "r"(v), "r"(pred)
-               : "memory");
-}
 __device__ __forceinline__ uint32_t atomAddShared(uint32_t addr, uint32_t v) {
   uint32_t old;
   asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(old) : "r"(addr), "r"(v) : "memory");
@@ -148,22 +143,12 @@ __device__ __forceinline__ uint32_t atomAndOff(uint32_t addr, uint32_t mask) {
   asm volatile("atom.shared.and.b32 %0, [%1+%3], %2;" : "=r"(old) : "r"(addr), "r"(mask), "n"(kOff) : "memory");
   return old;
 }
-template <int kOff>
-__device__ __forceinline__ void stGlobalOffIf(void* ptr, int32_t v, bool pred) {
-  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\t@p st.global.u32 [%0+%3], %1;\n\t}" ::"l"(ptr),
-               "r"(v), "r"((uint32_t)pred), "n"(kOff)
-               : "memory");
-}
-
-// Tail of a cell expansion: win tests, ranking, slot allocation, queue
-// appends and level stores (see the call site).  pcU/pcD + kOffU/kOffD are the
-// field addresses of the upper and lower neighbour, pc -+ 4 the left and right.
-template <int kOffU, int kOffD>
-__device__ __forceinline__ void appendAndStore(uint32_t oU, uint32_t oD, uint32_t oL, uint32_t oR, uint32_t bit,
-                                               uint32_t bitL, uint32_t bitR, uint32_t ltMask, uint32_t slotA,
-                                               uint32_t lane0Mask, uint32_t qnS, uint32_t capMask, uint32_t eU,
-                                               uint32_t eD, uint32_t e, char* pcU, char* pcD, int level) {
-  char* const pc = kOffU != 0 ? pcU : pcU + (pcD - pcU) / 2;
+// Tail of a cell expansion: win tests, ranking, slot allocation and queue
+// appends (see the call site).
+__device__ __forceinline__ void appendWinners(uint32_t oU, uint32_t oD, uint32_t oL, uint32_t oR, uint32_t bit,
+                                              uint32_t bitL, uint32_t bitR, uint32_t ltMask, uint32_t slotA,
+                                              uint32_t lane0Mask, uint32_t qnS, uint32_t capMask, uint32_t eU,
+                                              uint32_t eD, uint32_t e) {
   asm volatile(
       "{\n\t"
       ".reg .pred pu, pd, pl, pr;\n\t"
@@ -191,13 +176,9 @@ __device__ __forceinline__ void appendAndStore(uint32_t oU, uint32_t oD, uint32_
       "mad.lo.u32 a, rd, 4, qb;\n\t@pd st.shared.u32 [a], %13;\n\t"
       "mad.lo.u32 a, rl, 4, qb;\n\tadd.u32 v, %14, -1;\n\t@pl st.shared.u32 [a], v;\n\t"
       "mad.lo.u32 a, rr, 4, qb;\n\tadd.u32 v, %14, 1;\n\t@pr st.shared.u32 [a], v;\n\t"
-      "@pu st.global.u32 [%15+%19], %18;\n\t"
-      "@pd st.global.u32 [%16+%20], %18;\n\t"
-      "@pl st.global.u32 [%17+-4], %18;\n\t"
-      "@pr st.global.u32 [%17+4], %18;\n\t"
       "}" ::"r"(oU),
       "r"(oD), "r"(oL), "r"(oR), "r"(bit), "r"(bitL), "r"(bitR), "r"(ltMask), "r"(slotA), "r"(lane0Mask), "r"(qnS),
-      "r"(capMask), "r"(eU), "r"(eD), "r"(e), "l"(pcU), "l"(pcD), "l"(pc), "r"(level), "n"(kOffU), "n"(kOffD)
+      "r"(capMask), "r"(eU), "r"(eD), "r"(e)
       : "memory");
 }
 
@@ -238,7 +219,6 @@ __global__ void __launch_bounds__(1024, 1) bfs_queue_kernel(BfsQueueParams p) {
   // word per lane, so the idle lanes of a warp do not collide)
   const uint32_t dummy = (uint32_t)(p.dimy + 2) * S + 32u * (uint32_t)(lane % WPR) + 1u;
   const uint32_t rowB = 4u * (uint32_t)WPR;
-  const size_t outRowB = 4 * (size_t)dimx;
   // 16-byte stores for the template when rows and the buffer allow it
   const bool vec = (dimx & 3) == 0 && (reinterpret_cast<uintptr_t>(p.out) & 15) == 0;
   const int ringFirst = nThreads >= 256 ? nThreads - 128 : nThreads - 32;
@@ -353,22 +333,18 @@ __global__ void __launch_bounds__(1024, 1) bfs_queue_kernel(BfsQueueParams p) {
             oD = atomAnd(aC + rowB, ~bit);
           }
           const uint32_t oL = atomAnd(aL, ~bitL), oR = atomAnd(aR, ~bitR);
-          // this cell in the field (row Y of the bitmap = word / WPR)
+          // The distance of a cell is stored when the cell is expanded (one full
+          // store per warp pass instead of four sparse ones for the cells it
+          // discovers); row Y of the bitmap = word / WPR.
           const uint32_t Y = kWPR ? w / (uint32_t)(kWPR ? kWPR : 1) : __umulhi(w, p.wprMagic) >> p.wprShift;
-          char* const pc = outb + 4 * (size_t)(e - Y * padBits);
-          // winners, queue slots and stores in one PTX block (the four win
-          // predicates stay in predicate registers from the test to the
-          // stores).  Slots are direction-major inside the warp's block: one
-          // ballot per direction ranks the winners, one atomic per warp (lane 0
-          // adds the total, the other lanes add 0 to private words) allocates,
-          // and the slot index wraps at the capacity instead of being checked.
-          if constexpr (kDimX != 0) {
-            appendAndStore<-4 * kDimX, 4 * kDimX>(oU, oD, oL, oR, bit, bitL, bitR, ltMask, slotA, lane0Mask, qnS,
-                                                  capMask, e - S, e + S, e, pc, pc, level);
-          } else {
-            appendAndStore<0, 0>(oU, oD, oL, oR, bit, bitL, bitR, ltMask, slotA, lane0Mask, qnS, capMask, e - S,
-                                 e + S, e, pc - outRowB, pc + outRowB, level);
-          }
+          if (i < count) *reinterpret_cast<int32_t*>(outb + 4 * (size_t)(e - Y * padBits)) = level - 1;
+          // winners and queue slots in one PTX block (the four win predicates
+          // stay in predicate registers from the test to the stores).  Slots are
+          // direction-major inside the warp's block: one ballot per direction
+          // ranks the winners, one atomic per warp (lane 0 adds the total, the
+          // other lanes add 0 to private words) allocates, and the slot index
+          // wraps at the capacity instead of being checked.
+          appendWinners(oU, oD, oL, oR, bit, bitL, bitR, ltMask, slotA, lane0Mask, qnS, capMask, e - S, e + S, e);
           i += nThreads;
           if (i - lane >= count) break;
           e = ldShared(qcS + 4u * (uint32_t)min(i, count - 1));
@@ -421,8 +397,10 @@ static QueueGeom queueGeometry(const mrp_map_s* map) {
   q.WPR = ((map->dimx + 2 + 31) / 32) | 1;
   q.nOpenWords = (map->dimy + 4) * q.WPR;  // border rows + two zero rows (dummy cell)
   const int span = map->dimx + map->dimy;
-  int th = 64;
-  while (th < 1024 && th < span / 2) th <<= 1;
+  // 12 warps serve a 1024x1024 map as fast as 32 (the level loop is bound by
+  // the shared-memory atomics and the scattered stores, not by warp count;
+  // measured 1014 us per goal at 384 threads, 1037 at 512, 1066 at 768)
+  int th = std::min(384, std::max(64, (span / 4 + 31) & ~31));
   if (const char* e = getenv("MRP_BFS_THREADS")) th = atoi(e);
   q.threads = th;
   // a wavefront on an open grid holds < 2*(dimx+dimy) cells; leave 4x room
