@@ -186,35 +186,67 @@ def descend_paths(torch, fields, inst, starts_cell, n_agents, max_t):
 ECBS_BATCH = 1000  # replans of a lock-step iteration share one launch: throughput grows with the batch
 
 
-def search_metrics(pkg):
+def c3_shard(pkg, s32, rank):
+    """The ECBS batch of one rank (config C3, instances sharded across GPUs,
+    ECBS_BATCH per GPU).  Rank 0: the 100-agent benchmark files as they are and
+    the other files scaled to 100 agents by instances.synthetic_c3.  Rank r > 0:
+    the same maps with other agents: every file cut to at most 90 of its agents
+    and refilled to 100 with the stateless RNG offset by the rank."""
+    I = pkg.instances
+    if rank == 0:
+        insts = [i for i in s32 if i.n_agents == 100]
+        n_files = len(insts)
+        insts += [I.synthetic_c3(b, k, 100)
+                  for k, b in enumerate(i for i in s32 if i.n_agents != 100)][:ECBS_BATCH - n_files]
+        return insts, n_files
+    insts = []
+    for k, b in enumerate(s32[:ECBS_BATCH]):
+        m = min(b.n_agents, 90)
+        cut = I.Instance(b.name, b.dimx, b.dimy, b.obstacles, b.starts[:m], b.goals[:m])
+        insts.append(I.synthetic_c3(cut, k + 1000 * rank, 100))
+    return insts, 0
+
+
+def search_metrics(pkg, rank=0, world=1, dist=None, dev=None):
     """Instance throughput of the batched searches next to the oracle on one
-    host core (same caps).  ECBS (config C3): all 1000 32x32_obst204 files
-    scaled to 100 agents (the 100-agent files as they are, the others with
-    instances.synthetic_c3), w = 1.3, one lock-step batch.  CBS: the full 8x8
-    set (config C2) under an expansion cap."""
-    from oracle import orc
+    host core (same caps).  ECBS (config C3): 1000 instances per GPU on the
+    32x32_obst204 maps at 100 agents, w = 1.3, one lock-step batch per rank,
+    no collective on the data path (the ranks only add up their counts); the
+    host driver of a rank gets cores / world threads.  CBS: the full 8x8 set
+    (config C2) under an expansion cap, rank 0."""
+    import torch
     out = {}
     g = os.path.join(ROOT, "tests", "golden")
     s32 = pkg.instances.load_set(os.path.join(g, "bench_32x32.npz"))
-    s8 = pkg.instances.load_set(os.path.join(g, "bench_8x8.npz"))
-    insts = [i for i in s32 if i.n_agents == 100]
-    n_files = len(insts)
-    # config C3: every other file of the set scaled to 100 agents (stateless RNG)
-    insts += [pkg.instances.synthetic_c3(b, k, 100)
-              for k, b in enumerate(i for i in s32 if i.n_agents != 100)][:ECBS_BATCH - n_files]
+    insts, n_files = c3_shard(pkg, s32, rank)
     cap_hl = 2000
     pkg.solver.solve_batch(pkg.solver.ECBS, insts[:2], w=1.3, max_hl=50)  # warm
+    if world > 1:
+        dist.barrier()
     t0 = time.perf_counter()
     res = pkg.solver.solve_batch(pkg.solver.ECBS, insts, w=1.3, max_hl=cap_hl, max_seconds=120)
     dt = time.perf_counter() - t0
     ok = [r for r in res if r["status"] == 0]
-    out["ecbs_w1.3_instances_per_s"] = len(ok) / dt
-    out["ecbs_config"] = "32x32_obst204, 100 agents, %d instances (%d benchmark files + %d scaled by " \
-                         "synthetic_c3) in one lock-step batch, cap %d high-level expansions" % (
-                             len(insts), n_files, len(insts) - n_files, cap_hl)
-    out["ecbs_solved"] = "%d/%d" % (len(ok), len(insts))
-    out["ecbs_seconds"] = dt
-    out["ecbs_max_cost_over_lb"] = max(r["cost"] / r["lower_bound"] for r in ok) if ok else None
+    n_ok, n_all, dt_max = len(ok), len(insts), dt
+    ratio = max(r["cost"] / r["lower_bound"] for r in ok) if ok else 0.0
+    if world > 1:
+        t = torch.tensor([n_ok, n_all], device=dev, dtype=torch.float64)
+        dist.all_reduce(t)
+        m = torch.tensor([dt, ratio], device=dev, dtype=torch.float64)
+        dist.all_reduce(m, op=dist.ReduceOp.MAX)
+        n_ok, n_all, dt_max, ratio = int(t[0].item()), int(t[1].item()), float(m[0].item()), float(m[1].item())
+    if rank != 0:
+        return out
+    from oracle import orc
+    s8 = pkg.instances.load_set(os.path.join(g, "bench_8x8.npz"))
+    out["ecbs_w1.3_instances_per_s"] = n_ok / dt_max
+    out["ecbs_config"] = "32x32_obst204, 100 agents, %d instances per GPU in one lock-step batch per rank " \
+                         "(rank 0: %d benchmark files + %d scaled by synthetic_c3; other ranks: the same maps, " \
+                         "agents redrawn), cap %d high-level expansions, %d rank(s)" % (
+                             len(insts), n_files, len(insts) - n_files, cap_hl, world)
+    out["ecbs_solved"] = "%d/%d" % (n_ok, n_all)
+    out["ecbs_seconds"] = dt_max
+    out["ecbs_max_cost_over_lb"] = ratio if n_ok else None
     n_cpu = 6
     t0 = time.perf_counter()
     cres = [orc.ecbs(i.dimx, i.dimy, i.obstacles, i.starts, i.goals, 1.3, (cap_hl, 0, 30.0))
@@ -413,8 +445,8 @@ def run_ours(args):
         del table, length
 
     # ---- also: the search metrics (m3): ECBS w=1.3 instances/s, CBS over 8x8 ---
-    if rank == 0 and not args.skip_search:
-        also.update(search_metrics(pkg))
+    if not args.skip_search:
+        also.update(search_metrics(pkg, rank, world, dist, dev))
 
     # ---- optional all-gather of the fields over NVLink (north_star) -----------
     if world > 1 and args.allgather:
@@ -504,6 +536,12 @@ def main():
     ap.add_argument("--skip-search", action="store_true")
     ap.add_argument("--allgather", action="store_true", default=True)
     args = ap.parse_args()
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world > 1:
+        # the host drivers of the ranks share the box's cores (read by libgomp when it
+        # loads; torchrun presets 1 thread per worker, which would serialise them)
+        os.environ["OMP_NUM_THREADS"] = os.environ.get(
+            "MRP_BENCH_OMP", str(max(1, (os.cpu_count() or 1) // world)))
     if args.impl == "reference":
         run_reference(args)
     else:
