@@ -335,8 +335,6 @@ def run_ours(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if world > 1:
-        # keep stdout to the one JSON line (NCCL_DEBUG=VERSION prints a banner)
-        os.environ["NCCL_DEBUG"] = "WARN"
         torch.cuda.set_device(local)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     else:
@@ -542,6 +540,11 @@ def main():
         # loads; torchrun presets 1 thread per worker, which would serialise them)
         os.environ["OMP_NUM_THREADS"] = os.environ.get(
             "MRP_BENCH_OMP", str(max(1, (os.cpu_count() or 1) // world)))
+        os.environ.setdefault("OMP_WAIT_POLICY", "passive")  # idle workers must not spin on shared cores
+        # stdout carries exactly one JSON line: NCCL prints its version banner at every
+        # debug level from VERSION up (WARN included), and to stdout unless redirected
+        os.environ["NCCL_DEBUG"] = "NONE"
+        os.environ["NCCL_DEBUG_FILE"] = "/dev/stderr"
     if args.impl == "reference":
         run_reference(args)
     else:
