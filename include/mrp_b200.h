@@ -47,6 +47,17 @@ typedef enum {
  * one) and creates the library's streams.  Idempotent. */
 int mrp_init(int device);
 int mrp_shutdown(void);
+/* Lanes.  The reference is single-threaded and its Environment is not
+ * re-entrant (setLowLevelContext, example/cbs.cpp:266-276); this library is
+ * thread-compatible per LANE: a lane owns its streams, staging buffers and
+ * replan workspace, calls made in one lane are serialised, calls made in
+ * different lanes overlap on the device (the batched drivers run sub-batches
+ * of instances in separate lanes so that one long replan does not hold up the
+ * others).  mrp_set_lane binds the calling host thread to lane 0 <= k <
+ * mrp_max_lanes(); threads start in lane 0.  Maps and field sets may be
+ * shared between lanes (they are read-only on the device). */
+int mrp_set_lane(int lane);
+int mrp_max_lanes(void);
 int mrp_device_count(void);
 const char* mrp_last_error(void);
 /* "major.minor name smcount" of the bound device, for logs */

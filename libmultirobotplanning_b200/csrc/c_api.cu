@@ -28,59 +28,6 @@ int fail(int code, const char* fmt, ...) {
   return code;
 }
 
-Context& ctx() {
-  static Context c;
-  return c;
-}
-
-std::mutex& apiMutex() {
-  static std::mutex m;
-  return m;
-}
-
-static int initLocked(int device) {
-  Context& c = ctx();
-  if (c.ready && (device < 0 || device == c.device)) return 0;
-  int n = 0;
-  cudaError_t e = cudaGetDeviceCount(&n);
-  if (e != cudaSuccess || n == 0)
-    return fail(MRP_ERR_NO_DEVICE,
-                "no CUDA device available (%s); this library has no CPU fallback",
-                e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
-  if (device < 0) {
-    if (cudaGetDevice(&device) != cudaSuccess) device = 0;
-  }
-  MRP_CHECK(device < n, MRP_ERR_INVALID, "device %d out of range (%d devices)",
-            device, n);
-  MRP_CUDA(cudaSetDevice(device));
-  cudaDeviceProp prop;
-  MRP_CUDA(cudaGetDeviceProperties(&prop, device));
-  if (c.ready) {
-    cudaStreamDestroy(c.stream);
-    cudaStreamDestroy(c.copyStream);
-  }
-  c.device = device;
-  c.smCount = prop.multiProcessorCount;
-  c.smemOptin = prop.sharedMemPerBlockOptin;
-  MRP_CUDA(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
-  MRP_CUDA(cudaStreamCreateWithFlags(&c.copyStream, cudaStreamNonBlocking));
-  char buf[256];
-  snprintf(buf, sizeof buf, "%d.%d %s sm=%d smem_optin=%zu", prop.major, prop.minor,
-           prop.name, prop.multiProcessorCount, (size_t)prop.sharedMemPerBlockOptin);
-  c.info = buf;
-  c.ready = true;
-  return 0;
-}
-
-int ensureInit() {
-  if (ctx().ready) {
-    // other libraries (torch) may have changed the current device
-    cudaSetDevice(ctx().device);
-    return 0;
-  }
-  return initLocked(-1);
-}
-
 // grow-only device scratch slots for the host-pointer entry points
 struct Scratch {
   void* p = nullptr;
@@ -107,7 +54,96 @@ struct Scratch {
     cap = 0;
   }
 };
-static Scratch g_scratch[16];
+
+struct PinnedScratch {
+  void* p = nullptr;
+  size_t cap = 0;
+  int get(size_t bytes, void** out) {
+    if (bytes > cap) {
+      if (p) cudaFreeHost(p);
+      p = nullptr;
+      cap = 0;
+      size_t want = std::max(bytes, (size_t)1 << 16);
+      want += want / 4;
+      cudaError_t e = cudaHostAlloc(&p, want, cudaHostAllocDefault);
+      if (e != cudaSuccess)
+        return fail(MRP_ERR_NOMEM, "cudaHostAlloc(%zu) failed: %s", want, cudaGetErrorString(e));
+      cap = want;
+    }
+    *out = p;
+    return 0;
+  }
+  void release() {
+    if (p) cudaFreeHost(p);
+    p = nullptr;
+    cap = 0;
+  }
+};
+
+struct Lane {
+  Context c;
+  std::mutex m;
+  Scratch scratch[16];
+  PinnedScratch pinned[4];
+  LaneLL ll;
+};
+static Lane g_lanes[kMaxLanes];
+static thread_local int t_lane = 0;
+static std::atomic<int> g_device{-1};  // the device of the first initialised lane
+
+static Lane& lane() { return g_lanes[t_lane]; }
+Context& ctx() { return lane().c; }
+std::mutex& apiMutex() { return lane().m; }
+LaneLL& laneLL() { return lane().ll; }
+int pinnedScratch(int slot, size_t bytes, void** out) { return lane().pinned[slot].get(bytes, out); }
+#define g_scratch (lane().scratch)
+
+static int initLocked(int device) {
+  Context& c = ctx();
+  if (c.ready && (device < 0 || device == c.device)) return 0;
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0)
+    return fail(MRP_ERR_NO_DEVICE,
+                "no CUDA device available (%s); this library has no CPU fallback",
+                e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+  if (device < 0) device = g_device.load();  // lanes follow the first one
+  if (device < 0) {
+    if (cudaGetDevice(&device) != cudaSuccess) device = 0;
+  }
+  MRP_CHECK(device < n, MRP_ERR_INVALID, "device %d out of range (%d devices)",
+            device, n);
+  MRP_CUDA(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  MRP_CUDA(cudaGetDeviceProperties(&prop, device));
+  if (c.ready) {
+    cudaStreamDestroy(c.stream);
+    cudaStreamDestroy(c.copyStream);
+  }
+  c.device = device;
+  c.smCount = prop.multiProcessorCount;
+  c.smemOptin = prop.sharedMemPerBlockOptin;
+  MRP_CUDA(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
+  MRP_CUDA(cudaStreamCreateWithFlags(&c.copyStream, cudaStreamNonBlocking));
+  char buf[256];
+  snprintf(buf, sizeof buf, "%d.%d %s sm=%d smem_optin=%zu", prop.major, prop.minor,
+           prop.name, prop.multiProcessorCount, (size_t)prop.sharedMemPerBlockOptin);
+  c.info = buf;
+  c.ready = true;
+  g_device.store(device);
+  return 0;
+}
+
+int ensureInit() {
+  if (ctx().ready) {
+    // other libraries (torch) may have changed the current device
+    cudaSetDevice(ctx().device);
+    return 0;
+  }
+  return initLocked(-1);
+}
+
+
 
 template <class T>
 static int scratch(int slot, size_t count, T** out) {
@@ -159,17 +195,33 @@ int mrp_init(int device) {
 }
 
 int mrp_shutdown(void) {
-  std::lock_guard<std::mutex> lk(apiMutex());
-  Context& c = ctx();
-  if (!c.ready) return 0;
-  cudaSetDevice(c.device);
-  cudaDeviceSynchronize();
-  for (auto& s : g_scratch) s.release();
-  cudaStreamDestroy(c.stream);
-  cudaStreamDestroy(c.copyStream);
-  c.ready = false;
+  for (Lane& L : g_lanes) {
+    std::lock_guard<std::mutex> lk(L.m);
+    Context& c = L.c;
+    if (!c.ready) continue;
+    cudaSetDevice(c.device);
+    cudaDeviceSynchronize();
+    for (auto& s : L.scratch) s.release();
+    for (auto& s : L.pinned) s.release();
+    if (L.ll.arena) cudaFree(L.ll.arena);
+    if (L.ll.hashArena) cudaFree(L.ll.hashArena);
+    L.ll = LaneLL();
+    cudaStreamDestroy(c.stream);
+    cudaStreamDestroy(c.copyStream);
+    c.ready = false;
+  }
+  g_device.store(-1);
   return 0;
 }
+
+int mrp_set_lane(int lane_index) {
+  if (lane_index < 0 || lane_index >= kMaxLanes)
+    return fail(MRP_ERR_INVALID, "lane %d out of range (0..%d)", lane_index, kMaxLanes - 1);
+  t_lane = lane_index;
+  return 0;
+}
+
+int mrp_max_lanes(void) { return kMaxLanes; }
 
 int mrp_device_count(void) {
   int n = 0;
@@ -641,8 +693,10 @@ static int conflictsHost(const int32_t* cell, const int32_t* len, int B, int N, 
                                       d_res, d_ws, wsBytes, c.stream)
                     : launchConflictsBatch(d_cell, d_len, B, N, Tpad, mode, d_res, c.stream);
   if (rc) return rc;
-  std::vector<unsigned long long> res((size_t)4 * B);
-  MRP_CUDA(cudaMemcpyAsync(res.data(), d_res, res.size() * 8, cudaMemcpyDeviceToHost, c.stream));
+  void* hout = nullptr;
+  if (int rc2 = pinnedScratch(1, (size_t)4 * B * 8, &hout)) return rc2;
+  const unsigned long long* res = static_cast<const unsigned long long*>(hout);
+  MRP_CUDA(cudaMemcpyAsync(hout, d_res, (size_t)4 * B * 8, cudaMemcpyDeviceToHost, c.stream));
   MRP_CUDA(cudaStreamSynchronize(c.stream));
   for (int b = 0; b < B; ++b) {
     const int32_t* tc = cell + (size_t)b * N * Tpad;

@@ -43,8 +43,27 @@ struct Context {
   cudaStream_t copyStream = nullptr;
   std::string info;
 };
+// Every host thread works in a LANE: its own streams, scratch buffers, replan
+// arenas and API mutex, so that calls from different lanes overlap on the
+// device (mrp_set_lane, include/mrp_b200.h).  ctx() / apiMutex() are the
+// calling thread's lane's.
 Context& ctx();
 int ensureInit();
+constexpr int kMaxLanes = 32;
+struct LaneLL {  // grow-only device allocations of lowlevel.cu
+  void* arena = nullptr;
+  size_t arenaCap = 0;
+  unsigned long long* hashArena = nullptr;
+  size_t hashArenaEntries = 0;
+  uint32_t launchSerial = 0;
+};
+LaneLL& laneLL();
+// grow-only page-locked host staging buffers of the calling thread's lane.
+// The results of the per-iteration calls come back through them: an
+// asynchronous device-to-host copy into PAGEABLE memory makes the driver wait
+// for the stream's kernel while it holds a context-wide lock, which serialises
+// the lanes (measured: 16 lanes took 3x longer than one before this).
+int pinnedScratch(int slot, size_t bytes, void** out);
 extern std::atomic<long long> g_launches;
 inline void countLaunch(int n = 1) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 

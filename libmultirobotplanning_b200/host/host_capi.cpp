@@ -1,10 +1,16 @@
 // host_capi.cpp — C entry point of the batched high-level drivers
 // (libmrp_host.so), used by the Python tests and bench.py.
+#include <algorithm>
 #include <cstdint>
+#include <cstdlib>
 #include <map>
 #include <string>
+#include <thread>
 #include <utility>
 #include <vector>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
 
 #include "cli.hpp"
 #include "gpu_environment.hpp"
@@ -51,17 +57,59 @@ int mrph_solve_batch(int algo, int n_inst, const int32_t* dims, const int32_t* o
     opt.maxLlExpanded = max_ll;
     opt.maxSeconds = max_seconds;
     opt.maxTaskAssignments = max_ta;
-    // one lock-step batch per map size
+    // One lock-step batch per map size, cut into sub-batches that run in their
+    // own host thread and their own lane of the C ABI (own streams and replan
+    // workspace, mrp_set_lane): a lock-step iteration lasts as long as its
+    // slowest replan, so with one batch every instance waits for the slowest
+    // replan of all of them; sub-batches only wait for their own, and their
+    // launches overlap on the device.  Instances do not interact, so the
+    // results do not depend on the cut.  MRP_HOST_LANES=1 restores one batch.
     std::map<std::pair<int, int>, std::vector<int> > groups;
     for (int k = 0; k < n_inst; ++k) groups[{insts[k].dimx, insts[k].dimy}].push_back(k);
-    std::vector<SolveResult> results(n_inst);
+    int maxLanes = std::min(4, mrp_max_lanes());  // more lanes need CUDA_DEVICE_MAX_CONNECTIONS > 8 to overlap
+    if (const char* e = getenv("MRP_HOST_LANES")) maxLanes = std::max(1, std::min(atoi(e), mrp_max_lanes()));
+    int perLane = 48;  // instances per sub-batch the cut aims at
+    if (const char* e = getenv("MRP_HOST_LANE_SIZE")) perLane = std::max(1, atoi(e));
+    std::vector<std::vector<int> > parts;
     for (const auto& g : groups) {
-      std::vector<MapfInstance> sub;
-      for (int k : g.second) sub.push_back(insts[k]);
-      BatchSolver solver(static_cast<Algo>(algo), sub, opt);
-      std::vector<SolveResult> r = solver.run();
-      for (size_t j = 0; j < g.second.size(); ++j) results[g.second[j]] = std::move(r[j]);
+      const int n = (int)g.second.size();
+      const int L = std::max(1, std::min(maxLanes, n / perLane));
+      const size_t base = parts.size();
+      parts.resize(base + L);
+      for (int j = 0; j < n; ++j) parts[base + j % L].push_back(g.second[j]);  // round-robin: mixes difficulty
     }
+    std::vector<SolveResult> results(n_inst);
+    const int nThreads = std::min<int>(maxLanes, (int)parts.size());
+    std::vector<std::string> errors(nThreads);
+    auto work = [&](int t) {
+      try {
+        if (nThreads > 1) {
+          mrp_set_lane(t);
+#ifdef _OPENMP
+          omp_set_num_threads(std::max(1, omp_get_num_procs() / nThreads));
+#endif
+        }
+        for (size_t q = t; q < parts.size(); q += nThreads) {
+          std::vector<MapfInstance> sub;
+          for (int k : parts[q]) sub.push_back(insts[k]);
+          BatchSolver solver(static_cast<Algo>(algo), sub, opt);
+          std::vector<SolveResult> r = solver.run();
+          for (size_t j = 0; j < parts[q].size(); ++j) results[parts[q][j]] = std::move(r[j]);
+        }
+      } catch (const std::exception& e) {
+        errors[t] = e.what();
+        if (errors[t].empty()) errors[t] = "unknown error";
+      }
+    };
+    if (nThreads <= 1) {
+      work(0);
+    } else {
+      std::vector<std::thread> pool;
+      for (int t = 0; t < nThreads; ++t) pool.emplace_back(work, t);
+      for (auto& th : pool) th.join();
+    }
+    for (const std::string& e : errors)
+      if (!e.empty()) throw std::runtime_error(e);
     int64_t off = 0;
     for (int k = 0; k < n_inst; ++k) {
       const SolveResult& r = results[k];
