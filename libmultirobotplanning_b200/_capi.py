@@ -54,6 +54,7 @@ EXPORTS = [
     "mrp_focal_counts", "mrp_conflicts_dev", "mrp_decode_conflict",
     "mrp_lowlevel_batch", "mrp_launch_count", "mrp_fieldset_create",
     "mrp_fieldset_read", "mrp_fieldset_destroy", "mrp_lowlevel_batch_fs",
+    "mrp_set_lane", "mrp_max_lanes",
 ]
 
 _lib = None
@@ -100,6 +101,12 @@ def _p(a):
 
 def init(device=-1):
     check(lib().mrp_init(device))
+
+
+def set_lane(lane):
+    """Binds the calling thread to a lane of the library (own streams, staging
+    buffers and replan workspace); calls from different lanes overlap."""
+    check(lib().mrp_set_lane(int(lane)))
 
 
 def device_info():

@@ -304,3 +304,50 @@ def test_movingai_instance_cbs_and_ecbs(capi, orc, tmp_path):
     check_solution(inst, r["paths"], 0)
     e = solver.solve_batch(solver.ECBS, [inst], w=1.2, max_hl=20000)[0]
     assert e["status"] == 0 and want["cost"] <= e["cost"] <= np.float32(1.2) * np.float32(want["cost"])
+
+
+def test_lanes_give_the_same_answers(capi, set8, monkeypatch):
+    """Sub-batches in separate lanes (own streams, staging buffers and replan
+    workspace; mrp_set_lane) must not change a single result: instances do not
+    interact.  Same batch with one lane and with several."""
+    from libmultirobotplanning_b200 import solver
+    insts = [i for i in set8 if i.n_agents in (4, 6, 8)][:288]
+    out = {}
+    for lanes in ("1", "6"):
+        monkeypatch.setenv("MRP_HOST_LANES", lanes)
+        monkeypatch.setenv("MRP_HOST_LANE_SIZE", "16")
+        res = solver.solve_batch(solver.CBS, insts, max_hl=300, max_seconds=120)
+        out[lanes] = [(r["status"], r["cost"], r["makespan"], r["hl_expanded"], r["ll_expanded"]) for r in res]
+    assert out["1"] == out["6"]
+    assert sum(s == 0 for s, *_ in out["1"]) > 200
+
+
+def test_lanes_concurrent_calls(capi):
+    """Host threads in different lanes call the C ABI at the same time."""
+    import threading
+    rng = np.random.default_rng(5)
+    blocked = rng.random((48, 40)) < 0.2
+    ys, xs = np.nonzero(blocked)
+    obst = np.stack([xs, ys], 1).astype(np.int32)
+    goals = np.array([[x, y] for x, y in zip(rng.integers(0, 40, 24), rng.integers(0, 48, 24))], np.int32)
+    want = capi.bfs_fields(40, 48, obst, goals)
+    cell = rng.integers(0, 300, (64, 12)).astype(np.int32)
+    ln = np.full(64, 12, np.int32)
+    want_c = capi.count_conflicts(cell, ln, 0)
+    errors = []
+
+    def work(k):
+        try:
+            capi.set_lane(k)
+            for _ in range(6):
+                assert np.array_equal(capi.bfs_fields(40, 48, obst, goals), want)
+                assert capi.count_conflicts(cell, ln, 0) == want_c
+        except Exception as e:  # noqa: BLE001
+            errors.append(repr(e))
+
+    th = [threading.Thread(target=work, args=(k,)) for k in range(1, 6)]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    assert not errors, errors
