@@ -96,6 +96,13 @@ Context& ctx() { return lane().c; }
 std::mutex& apiMutex() { return lane().m; }
 LaneLL& laneLL() { return lane().ll; }
 int pinnedScratch(int slot, size_t bytes, void** out) { return lane().pinned[slot].get(bytes, out); }
+cudaError_t waitStream(cudaStream_t st) {
+  Context& c = ctx();
+  if (!c.doneEvent) return cudaStreamSynchronize(st);
+  cudaError_t e = cudaEventRecord(c.doneEvent, st);
+  if (e != cudaSuccess) return e;
+  return cudaEventSynchronize(c.doneEvent);
+}
 #define g_scratch (lane().scratch)
 
 static int initLocked(int device) {
@@ -125,6 +132,8 @@ static int initLocked(int device) {
   c.smemOptin = prop.sharedMemPerBlockOptin;
   MRP_CUDA(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
   MRP_CUDA(cudaStreamCreateWithFlags(&c.copyStream, cudaStreamNonBlocking));
+  if (!c.doneEvent)
+    MRP_CUDA(cudaEventCreateWithFlags(&c.doneEvent, cudaEventBlockingSync | cudaEventDisableTiming));
   char buf[256];
   snprintf(buf, sizeof buf, "%d.%d %s sm=%d smem_optin=%zu", prop.major, prop.minor,
            prop.name, prop.multiProcessorCount, (size_t)prop.sharedMemPerBlockOptin);
@@ -208,6 +217,8 @@ int mrp_shutdown(void) {
     L.ll = LaneLL();
     cudaStreamDestroy(c.stream);
     cudaStreamDestroy(c.copyStream);
+    if (c.doneEvent) cudaEventDestroy(c.doneEvent);
+    c.doneEvent = nullptr;
     c.ready = false;
   }
   g_device.store(-1);
@@ -697,7 +708,7 @@ static int conflictsHost(const int32_t* cell, const int32_t* len, int B, int N, 
   if (int rc2 = pinnedScratch(1, (size_t)4 * B * 8, &hout)) return rc2;
   const unsigned long long* res = static_cast<const unsigned long long*>(hout);
   MRP_CUDA(cudaMemcpyAsync(hout, d_res, (size_t)4 * B * 8, cudaMemcpyDeviceToHost, c.stream));
-  MRP_CUDA(cudaStreamSynchronize(c.stream));
+  MRP_CUDA(waitStream(c.stream));
   for (int b = 0; b < B; ++b) {
     const int32_t* tc = cell + (size_t)b * N * Tpad;
     const int32_t* tl = len + (size_t)b * N;

@@ -35,6 +35,7 @@ int fail(int code, const char* fmt, ...);
 
 // ---- context ----
 struct Context {
+  cudaEvent_t doneEvent = nullptr;  // blocking-sync event: waitStream() sleeps instead of spinning
   bool ready = false;
   int device = -1;
   int smCount = 0;
@@ -49,7 +50,7 @@ struct Context {
 // calling thread's lane's.
 Context& ctx();
 int ensureInit();
-constexpr int kMaxLanes = 32;
+constexpr int kMaxLanes = 64;
 struct LaneLL {  // grow-only device allocations of lowlevel.cu
   void* arena = nullptr;
   size_t arenaCap = 0;
@@ -64,6 +65,9 @@ LaneLL& laneLL();
 // for the stream's kernel while it holds a context-wide lock, which serialises
 // the lanes (measured: 16 lanes took 3x longer than one before this).
 int pinnedScratch(int slot, size_t bytes, void** out);
+// Waits for the lane's compute stream without spinning (the batched drivers
+// keep more host threads in flight than there are cores).
+cudaError_t waitStream(cudaStream_t st);
 extern std::atomic<long long> g_launches;
 inline void countLaunch(int n = 1) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
