@@ -276,6 +276,29 @@ def search_metrics(pkg, rank=0, world=1, dist=None, dev=None):
     t0 = time.perf_counter()
     orc.floyd_warshall(32, 32, s32[0].obstacles)
     out["floyd_warshall_32x32_cpu_seconds_per_map"] = time.perf_counter() - t0
+    # config C4: CBS-TA with every goal of the instance potential for every agent
+    # (all-agents x all-goals distance fields, cost matrix from the fields): the
+    # 10- and 20-agent files of the 32x32 set, one batch, next to the oracle
+    c4 = [i.with_all_goals_potential() for i in s32 if i.n_agents in (10, 20)]
+    cap_hl = 1000
+    pkg.solver.solve_batch(pkg.solver.CBS_TA, c4[:2], max_hl=20)  # warm
+    t0 = time.perf_counter()
+    res = pkg.solver.solve_batch(pkg.solver.CBS_TA, c4, max_hl=cap_hl, max_seconds=120)
+    dt = time.perf_counter() - t0
+    ok = [r for r in res if r["status"] == 0]
+    out["cbs_ta_c4_instances_per_s"] = len(ok) / dt
+    out["cbs_ta_c4_solved"] = "%d/%d" % (len(ok), len(c4))
+    out["cbs_ta_c4_seconds"] = dt
+    out["cbs_ta_c4_config"] = "32x32_obst204 files with 10 and 20 agents, potentialGoals = all goals of the " \
+                              "instance for every agent, cap %d high-level expansions" % cap_hl
+    sub = c4[::25]
+    t0 = time.perf_counter()
+    cres = [orc.cbs_ta(i.dimx, i.dimy, i.obstacles, i.starts, i.potential_goals, caps=(cap_hl, 0, 20.0))
+            for i in sub]
+    dt = time.perf_counter() - t0
+    out["cbs_ta_c4_cpu_instances_per_s_1core"] = sum(r["status"] == 0 for r in cres) / dt
+    out["cbs_ta_c4_cost_mismatches_vs_oracle"] = sum(
+        1 for a, b in zip(res[::25], cres) if a["status"] == 0 and b["status"] == 0 and a["cost"] != b["cost"])
     cap_hl = 500
     t0 = time.perf_counter()
     res = pkg.solver.solve_batch(pkg.solver.CBS, s8, max_hl=cap_hl, max_seconds=120)

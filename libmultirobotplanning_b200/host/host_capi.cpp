@@ -181,6 +181,36 @@ int mrph_environment_selftest(void) {
 
 }  // extern "C"
 
+// The host assignment module on its own (CPU only; tests and timing):
+// edges[n][3] = (agent, task, cost); enumerates up to max_solutions assignments
+// in non-decreasing cost (next_best_assignment.hpp:37-122 of the reference).
+// sol[k][a] = task of agent a in solution k or -1.  Returns the number of
+// solutions written.
+extern "C" int mrph_next_best_assignments(const int64_t* edges, int n_edges, int n_agents,
+                                          int n_tasks, int max_solutions, int64_t* costs,
+                                          int32_t* sol) {
+  try {
+    (void)n_tasks;
+    NextBestAssignment<int, int> nba;
+    for (int e = 0; e < n_edges; ++e)
+      nba.setCost((int)edges[3 * e], (int)edges[3 * e + 1], (long)edges[3 * e + 2]);
+    nba.solve();
+    int n = 0;
+    for (; n < max_solutions; ++n) {
+      std::map<int, int> s;
+      const long c = nba.nextSolution(s);
+      if (s.empty()) break;
+      costs[n] = c;
+      for (int a = 0; a < n_agents; ++a) sol[(size_t)n * n_agents + a] = -1;
+      for (const auto& kv : s) sol[(size_t)n * n_agents + kv.first] = kv.second;
+    }
+    return n;
+  } catch (const std::exception& e) {
+    g_err = e.what();
+    return -1;
+  }
+}
+
 // Parses an input YAML with the CLI's reader (CPU only; used by the tests).
 // Returns the number of agents, or -1.  Arrays must hold `cap` entries.
 extern "C" int mrph_load_instance(const char* path, int ta, int32_t* dims, int32_t* n_obst,

@@ -32,6 +32,22 @@ def lib():
     return _lib
 
 
+def next_best_assignments(edges, n_agents, n_tasks, max_solutions=1000):
+    """The host assignment module on its own (CPU only): edges [n][3] =
+    (agent, task, cost) -> (costs[k], assignment[k][agent] or -1) in
+    non-decreasing cost, as NextBestAssignment::nextSolution of the reference."""
+    e = np.ascontiguousarray(edges, dtype=np.int64).reshape(-1, 3)
+    costs = np.zeros(max_solutions, np.int64)
+    sol = np.full((max_solutions, max(n_agents, 1)), -1, np.int32)
+    if not os.path.exists(LIB_PATH):
+        raise _capi.MrpError(-1, "%s not found: run __graft_entry__.build()" % LIB_PATH)
+    h = C.CDLL(LIB_PATH) if _lib is None else _lib
+    n = h.mrph_next_best_assignments(_p(e), len(e), n_agents, n_tasks, max_solutions, _p(costs), _p(sol))
+    if n < 0:
+        raise RuntimeError("mrph_next_best_assignments failed")
+    return costs[:n], sol[:n, :n_agents]
+
+
 def _i32(a):
     return np.ascontiguousarray(a, dtype=np.int32)
 

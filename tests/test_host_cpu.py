@@ -112,3 +112,63 @@ def test_movingai_oracle_solves(tmp_path, orc):
     inst = I.movingai_instances(scen, mp, min_agents=4, agent_step=1)[0]
     r = orc.cbs(inst.dimx, inst.dimy, inst.obstacles, inst.starts, inst.goals)
     assert r["status"] == 0 and r["cost"] >= 12 + 12 + 2 + 7
+
+
+def test_host_assignment_reference_vectors():
+    """host/assignment.hpp (dense successive shortest paths, parallel Murty
+    partition) against the known answers of the reference's own tests
+    (test/test_next_best_assignment.py:19-110)."""
+    from libmultirobotplanning_b200 import solver
+    nba = solver.next_best_assignments
+    c, s = nba([], 0, 0)
+    assert len(c) == 0
+    c, s = nba([[0, 0, 2], [0, 1, 1]], 1, 2)
+    assert list(c) == [1, 2] and s[0][0] == 1 and s[1][0] == 0
+    c, s = nba([[0, 0, 2], [1, 0, 1]], 2, 1)
+    assert list(c) == [1, 2] and list(s[0]) == [-1, 0] and list(s[1]) == [0, -1]
+    c, s = nba([[0, 0, 90], [0, 1, 76], [1, 0, 35], [1, 1, 85]], 2, 2)
+    assert list(c) == [111, 175] and list(s[0]) == [1, 0] and list(s[1]) == [0, 1]
+    M = [[90, 76, 75, 80], [35, 85, 55, 65], [125, 95, 90, 105], [45, 110, 95, 115]]
+    E = [[i, j, M[i][j]] for i in range(4) for j in range(4)]
+    c, s = nba(E, 4, 4)
+    assert len(c) == 24 and c[0] == 275 and c[-1] == 400
+    assert list(s[0]) == [3, 2, 1, 0] and list(s[-1]) == [2, 1, 0, 3]
+    assert all(c[k] <= c[k + 1] for k in range(len(c) - 1))
+    assert len({tuple(r) for r in s}) == 24
+
+
+def test_host_assignment_matches_oracle(orc):
+    """Same cost sequence as the oracle's restatement of assignment.hpp /
+    next_best_assignment.hpp on random problems: square and rectangular, sparse
+    (missing edges, agents without any edge), many ties; every enumerated
+    solution is a valid matching of the announced cost, no solution twice."""
+    from libmultirobotplanning_b200 import solver
+    rng = np.random.default_rng(11)
+    for trial in range(40):
+        A, T = int(rng.integers(1, 9)), int(rng.integers(1, 9))
+        density = rng.choice([0.35, 0.7, 1.0])
+        hi = int(rng.choice([3, 20, 1000]))
+        cost = {}
+        for a in range(A):
+            for t in range(T):
+                if rng.random() < density:
+                    cost[(a, t)] = int(rng.integers(0, hi))
+        E = [[a, t, c] for (a, t), c in cost.items()]
+        K = 60
+        c1, s1 = solver.next_best_assignments(E, A, T, K)
+        c2, s2 = orc.next_best_assignments(E, A, T, K)
+        assert list(c1) == list(c2), (trial, E)
+        seen = set()
+        for c, s in zip(c1, s1):
+            used = [t for t in s if t >= 0]
+            assert len(used) == len(set(used))
+            assert all((a, int(t)) in cost for a, t in enumerate(s) if t >= 0)
+            assert sum(cost[(a, int(t))] for a, t in enumerate(s) if t >= 0) == c
+            assert tuple(s) not in seen
+            seen.add(tuple(s))
+    # a C4-sized problem: the first solutions of a 60 x 60 matrix
+    M = rng.integers(5, 60, (60, 60))
+    E = [[a, t, int(M[a, t])] for a in range(60) for t in range(60)]
+    c1, _ = solver.next_best_assignments(E, 60, 60, 3)
+    c2, _ = orc.next_best_assignments(E, 60, 60, 3)
+    assert list(c1) == list(c2)
