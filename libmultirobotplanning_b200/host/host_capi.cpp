@@ -66,7 +66,13 @@ int mrph_solve_batch(int algo, int n_inst, const int32_t* dims, const int32_t* o
     // results do not depend on the cut.  MRP_HOST_LANES=1 restores one batch.
     std::map<std::pair<int, int>, std::vector<int> > groups;
     for (int k = 0; k < n_inst; ++k) groups[{insts[k].dimx, insts[k].dimy}].push_back(k);
-    int maxLanes = std::min(4, mrp_max_lanes());  // more lanes need CUDA_DEVICE_MAX_CONNECTIONS > 8 to overlap
+    // Small instances are bound by the host bookkeeping of their trees (8x8 set:
+    // 2.4 s with 4 lanes, 1.0 s with 16), large ones by the longest replan of an
+    // iteration, and more than 8 lanes of long kernels need
+    // CUDA_DEVICE_MAX_CONNECTIONS > 8 to overlap.
+    long agents = 0;
+    for (int k = 0; k < n_inst; ++k) agents += (long)insts[k].starts.size();
+    int maxLanes = std::min(n_inst > 0 && agents / n_inst < 32 ? 16 : 4, mrp_max_lanes());
     if (const char* e = getenv("MRP_HOST_LANES")) maxLanes = std::max(1, std::min(atoi(e), mrp_max_lanes()));
     int perLane = 48;  // instances per sub-batch the cut aims at
     if (const char* e = getenv("MRP_HOST_LANE_SIZE")) perLane = std::max(1, atoi(e));
