@@ -431,6 +431,7 @@ def run_ours(args):
 
     # ---- also: conflict sweep of C5 (N = 4096 agents on their goal fields) ----
     also = {}
+    table = length = None
     if rank == 0 and not args.skip_conflicts:
         starts_cell = (inst.starts[:, 0] + DIM * inst.starts[:, 1]).astype(np.int64)
         N = G
@@ -463,6 +464,65 @@ def run_ours(args):
             "conflict_first_key": int(np.uint64(res[0])) if res[0] != -1 else None,
             "conflict_table_gbps": N * Tpad * 4 / (cms * 1e-3) / 1e9,
         })
+
+    # ---- conflict sweep sharded by time slab over the ranks:
+    # the path table is broadcast, every rank sweeps the steps of its slab, the
+    # first-conflict keys meet in an all-reduce(MIN), the counts in a SUM
+    if world > 1 and not args.skip_conflicts:
+        from libmultirobotplanning_b200 import sharding
+        shape = torch.zeros(2, dtype=torch.int64, device=dev)
+        if rank == 0:
+            shape[0], shape[1] = table.shape
+        dist.broadcast(shape, 0)
+        N, Tpad = int(shape[0].item()), int(shape[1].item())
+        torch.cuda.synchronize()
+        tp0 = time.perf_counter()
+        if rank != 0:
+            table = torch.empty((N, Tpad), dtype=torch.int32, device=dev)
+            length = torch.empty(N, dtype=torch.int32, device=dev)
+        dist.broadcast(table, 0)
+        dist.broadcast(length, 0)
+        t_end = sharding.conflict_time_range(length, 0)
+        t0s, t1s = sharding.shard_range(t_end, rank, world)
+        sub, sublen = sharding.slab_table(table, length, t0s, max(t1s, t0s + 1))
+        torch.cuda.synchronize()
+        prep_ms = (time.perf_counter() - tp0) * 1e3
+        d_res2 = torch.zeros(4, dtype=torch.int64, device=dev)
+        lib = capi.lib()
+
+        def sweep():
+            capi.check(lib.mrp_conflicts_dev(sub.data_ptr(), sublen.data_ptr(), N, sub.shape[1],
+                                             0, 1, 1, d_res2.data_ptr(), stream.cuda_stream))
+            r = d_res2.cpu()
+            key = sharding.shift_key(int(r[0].item()), t0s) if t1s > t0s else sharding.NO_CONFLICT
+            cnt = int(r[1].item()) if t1s > t0s else 0
+            return sharding.reduce_conflicts(key, cnt, dist, dev)
+        for _ in range(3):
+            sweep()
+        barrier()
+        ts0 = time.perf_counter()
+        reps = 5
+        for _ in range(reps):
+            gkey, gcount = sweep()
+        torch.cuda.synchronize()
+        sms = torch.tensor([(time.perf_counter() - ts0) / reps * 1e3], device=dev, dtype=torch.float64)
+        dist.all_reduce(sms, op=dist.ReduceOp.MAX)
+        if rank == 0:
+            want_key = also["conflict_first_key"] if also["conflict_first_key"] is not None else -1
+            assert gcount == also["conflict_count"] and gkey == want_key, \
+                "sharded conflict sweep differs from the single-GPU sweep"
+            also.update({
+                "conflict_sharded_ms": float(sms.item()),
+                "conflict_sharded_pair_steps_per_s":
+                    N * (N - 1) // 2 * also["conflict_max_t"] / (float(sms.item()) * 1e-3),
+                "conflict_sharded_prepare_ms": prep_ms,
+                "conflict_sharded_how": "time slabs over %d ranks: path table broadcast (prepare_ms), per-rank "
+                                        "slab sweep + device->host read + all-reduce MIN(key)/SUM(count) "
+                                        "(sharded_ms, wall clock, max over ranks); equals the single-GPU result"
+                                        % world,
+            })
+        del sub, sublen
+    if table is not None:
         del table, length
 
     # ---- also: the search metrics (m3): ECBS w=1.3 instances/s, CBS over 8x8 ---

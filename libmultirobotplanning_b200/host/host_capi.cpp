@@ -87,12 +87,15 @@ int mrph_solve_batch(int algo, int n_inst, const int32_t* dims, const int32_t* o
     std::vector<SolveResult> results(n_inst);
     const int nThreads = std::min<int>(maxLanes, (int)parts.size());
     std::vector<std::string> errors(nThreads);
+#ifdef _OPENMP
+    const int ompBudget = omp_get_max_threads();  // OMP_NUM_THREADS: ranks that share a host divide the cores
+#endif
     auto work = [&](int t) {
       try {
         if (nThreads > 1) {
           mrp_set_lane(t);
 #ifdef _OPENMP
-          omp_set_num_threads(std::max(1, omp_get_num_procs() / nThreads));
+          omp_set_num_threads(std::max(1, ompBudget / nThreads));
 #endif
         }
         for (size_t q = t; q < parts.size(); q += nThreads) {
