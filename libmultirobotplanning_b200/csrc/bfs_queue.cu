@@ -427,9 +427,15 @@ bool bfsQueueFits(const mrp_map_s* map) {
 
 typedef void (*QueueKernel)(BfsQueueParams);
 
-// the instance for this map: row strides as immediates for 1024-column maps
+// the instance for this map: row strides as immediates for the power-of-two
+// widths of the synthetic configurations, run-time strides for everything else
 static QueueKernel queueKernelFor(const mrp_map_s* map, const QueueGeom& q) {
-  if (map->dimx == 1024 && q.WPR == 33 && !getenv("MRP_BFS_GENERIC")) return bfs_queue_kernel<33, 1024>;
+  if (!getenv("MRP_BFS_GENERIC")) {
+    if (map->dimx == 1024 && q.WPR == 33) return bfs_queue_kernel<33, 1024>;
+    if (map->dimx == 512 && q.WPR == 17) return bfs_queue_kernel<17, 512>;
+    if (map->dimx == 256 && q.WPR == 9) return bfs_queue_kernel<9, 256>;
+    if (map->dimx == 2048 && q.WPR == 65) return bfs_queue_kernel<65, 2048>;
+  }
   return bfs_queue_kernel<0, 0>;
 }
 

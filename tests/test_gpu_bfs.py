@@ -40,7 +40,9 @@ def test_golden_crcs(capi, set8, set32, oracle_golden):
     (1, 1, 0.0), (1, 7, 0.0), (9, 1, 0.2), (5, 2, 0.3), (8, 8, 0.2), (31, 17, 0.25),
     (32, 32, 0.2), (33, 32, 0.2), (32, 33, 0.2), (40, 50, 0.3), (64, 64, 0.2),
     (100, 37, 0.35), (129, 65, 0.2), (257, 300, 0.25), (1100, 70, 0.2),
-    (70, 1100, 0.2)])
+    (70, 1100, 0.2),
+    # the queue kernel's compile-time instances (widths 256, 512, 1024, 2048)
+    (256, 90, 0.2), (512, 300, 0.25), (1024, 130, 0.2), (2048, 75, 0.3)])
 def test_random_maps(capi, orc, dimx, dimy, density):
     rng = np.random.default_rng(dimx * 1000 + dimy)
     obst = _rand_map(rng, dimx, dimy, density)
