@@ -193,7 +193,7 @@ conflict_pairs_kernel(const int32_t* __restrict__ cellAll,
 // transposed, already clamped copy of the table (coalesced), and are inserted
 // into an open-addressing table in shared memory (64-bit keys, atomicCAS).
 // ---------------------------------------------------------------------------
-constexpr int kHashThreads = 512;
+constexpr int kHashThreads = 1024;
 constexpr int kHashMaxN = 4096;          // table of 2*N slots x 16 B <= 128 KB
 constexpr int kHashMinN = 257;
 constexpr int kHashPerThread = kHashMaxN / kHashThreads;
