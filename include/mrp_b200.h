@@ -80,9 +80,22 @@ int mrp_map_destroy(mrp_map map);
  * Environment::computeHeuristic (example/cbs.cpp:445-557):
  *   out[g][x + dimx*y] = BFS distance from goal g, MRP_INF if unreachable or
  *   obstacle; a goal that is itself an obstacle yields 0 at the goal and
- *   MRP_INF elsewhere (the Floyd–Warshall row of an isolated vertex). */
+ *   MRP_INF elsewhere (the Floyd–Warshall row of an isolated vertex).
+ *
+ * Transfer: results of 16 Mi cells or more leave the device as uint16
+ * (0xFFFF = MRP_INF) and are expanded to int32 by host threads while the next
+ * batch is on the bus (the call is PCIe-bound at 4 B per cell); a batch with a
+ * finite distance >= 65535 is sent as int32.  `out` holds the same int32
+ * values either way.  Environment: MRP_BFS_PACK=0 never packs, =1 always
+ * packs; MRP_WIDEN_THREADS = host threads of the expansion (default: all
+ * cores, at most 16). */
 int mrp_bfs_fields(int dimx, int dimy, const int32_t* obst_xy, int n_obst,
                    const int32_t* goal_xy, int n_goals, int32_t* out);
+/* The host half of the packed transfer, exported for device-resident
+ * pipelines that copy uint16 fields themselves:
+ * dst[i] = src[i] == 0xFFFF ? MRP_INF : src[i] on `threads` host threads.
+ * Needs no device. */
+int mrp_widen_u16(const uint16_t* src, int32_t* dst, size_t n, int threads);
 /* Many small maps in one launch (configs C2/C4: every instance has its own
  * obstacle layout).  dims[m] = (dimx, dimy); obstacles and goals are CSR over
  * maps; fields are written back to back in goal order (field of goal k has

@@ -54,7 +54,7 @@ EXPORTS = [
     "mrp_focal_counts", "mrp_conflicts_dev", "mrp_decode_conflict",
     "mrp_lowlevel_batch", "mrp_launch_count", "mrp_fieldset_create",
     "mrp_fieldset_read", "mrp_fieldset_destroy", "mrp_lowlevel_batch_fs",
-    "mrp_set_lane", "mrp_max_lanes",
+    "mrp_set_lane", "mrp_max_lanes", "mrp_widen_u16",
 ]
 
 _lib = None
@@ -74,6 +74,7 @@ def lib():
         _lib.mrp_bfs_workspace_bytes.restype = C.c_size_t
         _lib.mrp_bfs_workspace_bytes.argtypes = [C.c_void_p, C.c_int]
         _lib.mrp_launch_count.restype = C.c_longlong
+        _lib.mrp_widen_u16.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int]
         _lib.mrp_map_destroy.argtypes = [C.c_void_p]
         _lib.mrp_bfs_fields_dev.argtypes = [C.c_void_p, C.c_void_p, C.c_int,
                                             C.c_void_p, C.c_void_p, C.c_void_p]
@@ -153,6 +154,15 @@ def bfs_fields(dimx, dimy, obst_xy, goal_xy, out=None):
         out = np.empty((len(goals), dimy * dimx), np.int32)
     check(lib().mrp_bfs_fields(dimx, dimy, _p(obst), len(obst), _p(goals),
                                len(goals), _p(out)))
+    return out
+
+
+def widen_u16(src, threads=4, out=None):
+    """Host half of the packed field transfer (needs no device)."""
+    src = np.ascontiguousarray(src, np.uint16)
+    if out is None:
+        out = np.empty(src.shape, np.int32)
+    check(lib().mrp_widen_u16(_p(src), _p(out), src.size, threads))
     return out
 
 

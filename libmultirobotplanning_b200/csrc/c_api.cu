@@ -3,8 +3,11 @@
 // copies around the kernels of bfs_small.cu / bfs_large.cu / conflicts.cu /
 // lowlevel.cu).  No CPU fallback anywhere: without a device every call fails.
 #include <algorithm>
+#include <condition_variable>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
+#include <thread>
 #include <vector>
 
 #include "common.cuh"
@@ -368,6 +371,224 @@ int mrp_bfs_fields_dev(mrp_map map, const int32_t* d_goal_cell, int n_goals,
                             static_cast<cudaStream_t>(stream));
 }
 
+// ---- packed device-to-host transfer of distance fields -----------------------
+// A field leaves the device as uint16 (0xFFFF = MRP_INF) whenever every finite
+// distance of the batch is below 0xFFFF, and is expanded to the ABI's int32 by
+// host threads (widen.cpp) while the next batch is on the bus: the host-pointer
+// call is PCIe-bound (4 B per cell), this halves the bytes.  A batch that does
+// not fit (a maze with paths of >= 65535 steps) is sent again as int32.
+__global__ void __launch_bounds__(256)
+pack_fields_u16_kernel(const int32_t* __restrict__ in, uint16_t* __restrict__ out,
+                       size_t n, int* __restrict__ overflow) {
+  const size_t n8 = n >> 3;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  bool ovf = false;
+  auto cvt = [&](int v) -> uint32_t {
+    if (v == MRP_INF) return 0xFFFFu;
+    if (v >= 0xFFFF) ovf = true;
+    return (uint32_t)v & 0xFFFFu;
+  };
+  for (size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x; k < n8; k += stride) {
+    const int4 a = __ldcs(reinterpret_cast<const int4*>(in) + 2 * k);
+    const int4 b = __ldcs(reinterpret_cast<const int4*>(in) + 2 * k + 1);
+    uint4 o;
+    o.x = cvt(a.x) | (cvt(a.y) << 16);
+    o.y = cvt(a.z) | (cvt(a.w) << 16);
+    o.z = cvt(b.x) | (cvt(b.y) << 16);
+    o.w = cvt(b.z) | (cvt(b.w) << 16);
+    reinterpret_cast<uint4*>(out)[k] = o;
+  }
+  for (size_t k = (n8 << 3) + (size_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += stride)
+    out[k] = (uint16_t)cvt(in[k]);
+  if (__syncthreads_or(ovf) && threadIdx.x == 0) atomicOr(overflow, 1);
+}
+
+extern "C++" {
+namespace mrp {
+void widenFieldU16(const uint16_t* src, int32_t* dst, size_t n, int threads);  // widen.cpp
+}
+}
+
+static int envInt(const char* name, int dflt) {
+  const char* v = getenv(name);
+  return (v && *v) ? atoi(v) : dflt;
+}
+
+// int32 fields straight into the caller's buffer: batch k+1 computes while batch
+// k is copied back on the copy stream (double-buffered device output).  `todo`
+// selects the batches (nullptr: all).
+static int bfsFieldsHostDirect(mrp_map map, const int32_t* d_goals, int n_goals, size_t batch,
+                               int32_t* out, const std::vector<char>* todo) {
+  Context& c = ctx();
+  const size_t cells = (size_t)map->dimx * map->dimy;
+  const size_t fieldBytes = cells * 4;
+  int rc = 0;
+  int32_t* d_out[2] = {nullptr, nullptr};
+  const bool twoBuffers = (size_t)n_goals > batch;
+  const size_t wsBytes = (map->W == 1 && map->S == 1) ? 16 * batch + 256
+                                                      : bfsLargeWorkspaceBytes(map, (int)batch);
+  cudaEvent_t done[2] = {nullptr, nullptr}, copied[2] = {nullptr, nullptr};
+  do {
+    if ((rc = scratch(1, batch * cells, &d_out[0]))) break;
+    if (twoBuffers && (rc = scratch(2, batch * cells, &d_out[1]))) break;
+    char* wsp = nullptr;
+    if ((rc = scratch(3, wsBytes, &wsp))) break;
+    for (int b = 0; b < 2; ++b) {
+      cudaEventCreateWithFlags(&done[b], cudaEventDisableTiming);
+      cudaEventCreateWithFlags(&copied[b], cudaEventDisableTiming);
+    }
+    int b = 0;
+    size_t k = 0;
+    for (size_t g0 = 0; g0 < (size_t)n_goals && rc == 0; g0 += batch, ++k) {
+      if (todo && !(*todo)[k]) continue;
+      const size_t n = std::min(batch, (size_t)n_goals - g0);
+      int32_t* dst = twoBuffers ? d_out[b] : d_out[0];
+      // the buffer must have been drained by its previous D2H copy
+      cudaStreamWaitEvent(c.stream, copied[b], 0);
+      rc = bfsFieldsDevLocked(map, d_goals + g0, (int)n, dst, wsp, c.stream);
+      if (rc) break;
+      cudaEventRecord(done[b], c.stream);
+      cudaStreamWaitEvent(c.copyStream, done[b], 0);
+      cudaError_t e = cudaMemcpyAsync(out + g0 * cells, dst, n * fieldBytes,
+                                      cudaMemcpyDeviceToHost, c.copyStream);
+      if (e != cudaSuccess) {
+        rc = fail(MRP_ERR_CUDA, "D2H copy failed: %s", cudaGetErrorString(e));
+        break;
+      }
+      cudaEventRecord(copied[b], c.copyStream);
+      b ^= 1;
+    }
+    cudaError_t e1 = cudaStreamSynchronize(c.stream);
+    cudaError_t e2 = cudaStreamSynchronize(c.copyStream);
+    if (rc == 0 && (e1 != cudaSuccess || e2 != cudaSuccess))
+      rc = fail(MRP_ERR_CUDA, "bfs fields failed: %s",
+                cudaGetErrorString(e1 != cudaSuccess ? e1 : e2));
+  } while (0);
+  for (int b = 0; b < 2; ++b) {
+    if (done[b]) cudaEventDestroy(done[b]);
+    if (copied[b]) cudaEventDestroy(copied[b]);
+  }
+  return rc;
+}
+
+// uint16 fields through page-locked staging slots, expanded by host threads.
+// Three slots: one being filled by the copy engine, one being expanded, one
+// in between.  overflowed[k] = 1 for the batches that must be sent as int32.
+static int bfsFieldsHostPacked(mrp_map map, const int32_t* d_goals, int n_goals, size_t batch,
+                               int32_t* out, std::vector<char>& overflowed) {
+  constexpr int NS = 3;
+  Context& c = ctx();
+  const size_t cells = (size_t)map->dimx * map->dimy;
+  const size_t nBatches = ((size_t)n_goals + batch - 1) / batch;
+  overflowed.assign(nBatches, 0);
+  const int threads = std::max(1, envInt("MRP_WIDEN_THREADS",
+                                         std::min(16, (int)std::thread::hardware_concurrency())));
+  const size_t wsBytes = (map->W == 1 && map->S == 1) ? 16 * batch + 256
+                                                      : bfsLargeWorkspaceBytes(map, (int)batch);
+  // staging slot: batch*cells uint16, then the overflow flag of the batch
+  const size_t slotBytes = ((batch * cells * 2 + 255) & ~(size_t)255) + 256;
+  int rc = 0;
+  int32_t* d_out = nullptr;
+  char* wsp = nullptr;
+  char* d_pack = nullptr;
+  void* h_pack = nullptr;
+  cudaEvent_t done[NS] = {}, copied[NS] = {};
+  if ((rc = scratch(1, batch * cells, &d_out))) return rc;
+  if ((rc = scratch(3, wsBytes, &wsp))) return rc;
+  if ((rc = scratch(4, NS * slotBytes, &d_pack))) return rc;
+  if ((rc = pinnedScratch(3, NS * slotBytes, &h_pack))) return rc;
+  for (int s = 0; s < NS; ++s) {
+    cudaEventCreateWithFlags(&done[s], cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&copied[s], cudaEventBlockingSync | cudaEventDisableTiming);
+  }
+  std::mutex m;
+  std::condition_variable cv;
+  size_t enqueued = 0, widened = 0;
+  bool stop = false;
+  cudaError_t workerErr = cudaSuccess;
+  const int device = c.device;
+  std::thread worker([&] {
+    cudaSetDevice(device);
+    for (size_t k = 0;; ++k) {
+      {
+        std::unique_lock<std::mutex> lk(m);
+        cv.wait(lk, [&] { return enqueued > k || stop; });
+        if (enqueued <= k) return;
+      }
+      const int s = (int)(k % NS);
+      cudaError_t e = cudaEventSynchronize(copied[s]);
+      if (e != cudaSuccess) workerErr = e;
+      const char* slot = static_cast<const char*>(h_pack) + (size_t)s * slotBytes;
+      const size_t g0 = k * batch, n = std::min(batch, (size_t)n_goals - g0);
+      if (e == cudaSuccess) {
+        if (*reinterpret_cast<const int*>(slot + slotBytes - 256))
+          overflowed[k] = 1;
+        else
+          widenFieldU16(reinterpret_cast<const uint16_t*>(slot), out + g0 * cells, n * cells,
+                        threads);
+      }
+      {
+        std::lock_guard<std::mutex> lk(m);
+        widened = k + 1;
+      }
+      cv.notify_all();
+    }
+  });
+  for (size_t k = 0; k < nBatches && rc == 0; ++k) {
+    const int s = (int)(k % NS);
+    const size_t g0 = k * batch, n = std::min(batch, (size_t)n_goals - g0);
+    if (k >= NS) {  // the slot's previous batch must have been expanded
+      std::unique_lock<std::mutex> lk(m);
+      cv.wait(lk, [&] { return widened + NS > k; });
+    }
+    rc = bfsFieldsDevLocked(map, d_goals + g0, (int)n, d_out, wsp, c.stream);
+    if (rc) break;
+    char* dslot = d_pack + (size_t)s * slotBytes;
+    int* dflag = reinterpret_cast<int*>(dslot + slotBytes - 256);
+    cudaMemsetAsync(dflag, 0, sizeof(int), c.stream);
+    const size_t total = n * cells;
+    const int grid = (int)std::min<size_t>((total / 8 + 255) / 256 + 1, (size_t)c.smCount * 16);
+    pack_fields_u16_kernel<<<grid, 256, 0, c.stream>>>(d_out, reinterpret_cast<uint16_t*>(dslot),
+                                                       total, dflag);
+    countLaunch();
+    cudaEventRecord(done[s], c.stream);
+    cudaStreamWaitEvent(c.copyStream, done[s], 0);
+    char* hslot = static_cast<char*>(h_pack) + (size_t)s * slotBytes;
+    cudaError_t e = cudaMemcpyAsync(hslot, dslot, total * 2, cudaMemcpyDeviceToHost, c.copyStream);
+    if (e == cudaSuccess)
+      e = cudaMemcpyAsync(hslot + slotBytes - 256, dflag, sizeof(int), cudaMemcpyDeviceToHost,
+                          c.copyStream);
+    if (e != cudaSuccess) {
+      rc = fail(MRP_ERR_CUDA, "D2H copy failed: %s", cudaGetErrorString(e));
+      break;
+    }
+    cudaEventRecord(copied[s], c.copyStream);
+    {
+      std::lock_guard<std::mutex> lk(m);
+      enqueued = k + 1;
+    }
+    cv.notify_all();
+  }
+  {
+    std::unique_lock<std::mutex> lk(m);
+    cv.wait(lk, [&] { return widened == enqueued; });
+    stop = true;
+  }
+  cv.notify_all();
+  worker.join();
+  cudaError_t e1 = cudaStreamSynchronize(c.stream);
+  cudaError_t e2 = cudaStreamSynchronize(c.copyStream);
+  if (rc == 0 && workerErr != cudaSuccess) e1 = workerErr;
+  if (rc == 0 && (e1 != cudaSuccess || e2 != cudaSuccess))
+    rc = fail(MRP_ERR_CUDA, "bfs fields failed: %s",
+              cudaGetErrorString(e1 != cudaSuccess ? e1 : e2));
+  for (int s = 0; s < NS; ++s) {
+    cudaEventDestroy(done[s]);
+    cudaEventDestroy(copied[s]);
+  }
+  return rc;
+}
+
 int mrp_bfs_fields(int dimx, int dimy, const int32_t* obst_xy, int n_obst,
                    const int32_t* goal_xy, int n_goals, int32_t* out) {
   MRP_CHECK(n_goals >= 0, MRP_ERR_INVALID, "n_goals < 0");
@@ -380,69 +601,46 @@ int mrp_bfs_fields(int dimx, int dimy, const int32_t* obst_xy, int n_obst,
     std::lock_guard<std::mutex> lk(apiMutex());
     Context& c = ctx();
     const size_t cells = (size_t)dimx * dimy;
-    const size_t fieldBytes = cells * 4;
-    // goals are processed in batches; batch k+1 computes while batch k is
-    // copied back on the copy stream (double-buffered device output)
-    size_t batch = std::max<size_t>(4 * (size_t)c.smCount, ((size_t)1 << 30) / fieldBytes);
-    batch = std::min<size_t>(batch, (size_t)n_goals);
     std::vector<int32_t> goalCell(n_goals);
     for (int k = 0; k < n_goals; ++k)
       goalCell[k] = goal_xy[2 * k] + dimx * goal_xy[2 * k + 1];
     int32_t* d_goals = nullptr;
-    int32_t* d_out[2] = {nullptr, nullptr};
-    void* d_ws = nullptr;
-    const bool twoBuffers = (size_t)n_goals > batch;
-    size_t wsBytes = (map->W == 1 && map->S == 1) ? 16 * batch + 256
-                                                  : bfsLargeWorkspaceBytes(map, (int)batch);
-    cudaEvent_t done[2] = {nullptr, nullptr}, copied[2] = {nullptr, nullptr};
     do {
       if ((rc = scratch(0, (size_t)std::max(n_goals, 1), &d_goals))) break;
-      if ((rc = scratch(1, batch * cells, &d_out[0]))) break;
-      if (twoBuffers && (rc = scratch(2, batch * cells, &d_out[1]))) break;
-      char* wsp = nullptr;
-      if ((rc = scratch(3, wsBytes, &wsp))) break;
-      d_ws = wsp;
-      for (int b = 0; b < 2; ++b) {
-        cudaEventCreateWithFlags(&done[b], cudaEventDisableTiming);
-        cudaEventCreateWithFlags(&copied[b], cudaEventDisableTiming);
-      }
       cudaError_t e = cudaMemcpyAsync(d_goals, goalCell.data(), (size_t)n_goals * 4,
                                       cudaMemcpyHostToDevice, c.stream);
       if (e != cudaSuccess) {
         rc = fail(MRP_ERR_CUDA, "H2D copy failed: %s", cudaGetErrorString(e));
         break;
       }
-      int b = 0;
-      for (size_t g0 = 0; g0 < (size_t)n_goals && rc == 0; g0 += batch, b ^= 1) {
-        const size_t n = std::min(batch, (size_t)n_goals - g0);
-        int32_t* dst = twoBuffers ? d_out[b] : d_out[0];
-        // the buffer must have been drained by its previous D2H copy
-        cudaStreamWaitEvent(c.stream, copied[b], 0);
-        rc = bfsFieldsDevLocked(map, d_goals + g0, (int)n, dst, d_ws, c.stream);
-        if (rc) break;
-        cudaEventRecord(done[b], c.stream);
-        cudaStreamWaitEvent(c.copyStream, done[b], 0);
-        e = cudaMemcpyAsync(out + g0 * cells, dst, n * fieldBytes,
-                            cudaMemcpyDeviceToHost, c.copyStream);
-        if (e != cudaSuccess) {
-          rc = fail(MRP_ERR_CUDA, "D2H copy failed: %s", cudaGetErrorString(e));
-          break;
-        }
-        cudaEventRecord(copied[b], c.copyStream);
+      // Large results travel packed (MRP_BFS_PACK=0 switches it off, =1 forces it).
+      const int packMode = envInt("MRP_BFS_PACK", -1);
+      const bool packed = packMode == 1 ||
+                          (packMode != 0 && (size_t)n_goals * cells >= ((size_t)16 << 20));
+      if (packed) {
+        // one wave of goals per batch for large maps, ~128 MiB of uint16 otherwise
+        size_t batch = std::max<size_t>((size_t)c.smCount, ((size_t)1 << 26) / cells);
+        if (envInt("MRP_BFS_BATCH", 0) > 0) batch = (size_t)envInt("MRP_BFS_BATCH", 0);  // tests
+        batch = std::min<size_t>(batch, (size_t)n_goals);
+        std::vector<char> overflowed;
+        rc = bfsFieldsHostPacked(map, d_goals, n_goals, batch, out, overflowed);
+        if (rc == 0 && std::find(overflowed.begin(), overflowed.end(), 1) != overflowed.end())
+          rc = bfsFieldsHostDirect(map, d_goals, n_goals, batch, out, &overflowed);
+      } else {
+        size_t batch = std::max<size_t>(4 * (size_t)c.smCount, ((size_t)1 << 28) / cells);
+        batch = std::min<size_t>(batch, (size_t)std::max(n_goals, 1));
+        rc = bfsFieldsHostDirect(map, d_goals, n_goals, batch, out, nullptr);
       }
-      cudaError_t e1 = cudaStreamSynchronize(c.stream);
-      cudaError_t e2 = cudaStreamSynchronize(c.copyStream);
-      if (rc == 0 && (e1 != cudaSuccess || e2 != cudaSuccess))
-        rc = fail(MRP_ERR_CUDA, "bfs fields failed: %s",
-                  cudaGetErrorString(e1 != cudaSuccess ? e1 : e2));
     } while (0);
-    for (int b = 0; b < 2; ++b) {
-      if (done[b]) cudaEventDestroy(done[b]);
-      if (copied[b]) cudaEventDestroy(copied[b]);
-    }
   }
   mrp_map_destroy(map);
   return rc;
+}
+
+int mrp_widen_u16(const uint16_t* src, int32_t* dst, size_t n, int threads) {
+  MRP_CHECK(n == 0 || (src && dst), MRP_ERR_INVALID, "NULL pointer");
+  widenFieldU16(src, dst, n, std::max(1, threads));
+  return 0;
 }
 
 int mrp_bfs_fields_batch(int n_maps, const int32_t* dims, const int32_t* obst_off,

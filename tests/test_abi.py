@@ -38,6 +38,26 @@ def test_no_cpu_fallback():
         capi.count_conflicts([[0, 1], [1, 0]], [2, 2])
 
 
+def test_widen_u16_host_half_of_packed_transfer():
+    """mrp_widen_u16 (no device needed): 0xFFFF -> MRP_INF, everything else
+    unchanged, for ragged sizes, unaligned buffers and any thread count."""
+    import numpy as np
+    from libmultirobotplanning_b200 import capi
+    rng = np.random.default_rng(3)
+    for n in (0, 1, 7, 15, 16, 17, 1000, 65536, 200003, 1 << 21):
+        for threads in (1, 5):
+            for off in (0, 1, 3):
+                src = rng.integers(0, 65536, n + off, dtype=np.uint16)[off:]
+                if n:
+                    src[rng.integers(0, n, max(1, n // 9))] = 0xFFFF
+                raw = np.full(n + off + 8, -7, np.int32)
+                dst = raw[off:off + n]
+                capi.widen_u16(src, threads, out=dst)
+                want = np.where(src == 0xFFFF, capi.INF, src.astype(np.int32))
+                assert np.array_equal(dst, want), (n, threads, off)
+                assert (raw[:off] == -7).all() and (raw[off + n:] == -7).all()
+
+
 def test_product_does_not_import_oracle():
     pkg = os.path.join(ROOT, "libmultirobotplanning_b200")
     for dirpath, _, files in os.walk(pkg):

@@ -99,6 +99,57 @@ def test_maze_deep(capi, orc):
     assert got[0][got[0] != capi.INF].max() > 2000
 
 
+def _with_env(env, fn):
+    try:
+        os.environ.update(env)
+        return fn()
+    finally:
+        for k in env:
+            os.environ.pop(k, None)
+
+
+@pytest.mark.parametrize("batch", ["1", "3", "0"])
+def test_packed_transfer(capi, orc, batch):
+    """Fields sent as uint16 and expanded on the host (mrp_bfs_fields for large
+    results) equal the int32 transfer and the oracle; many small batches cycle
+    through the three staging slots."""
+    rng = np.random.default_rng(5)
+    for dimx, dimy, density, ng in [(300, 200, 0.2, 40), (33, 7, 0.1, 11), (1, 1, 0.0, 1),
+                                    (1024, 40, 0.2, 7)]:
+        obst = _rand_map(rng, dimx, dimy, density)
+        cells = rng.choice(dimx * dimy, ng, replace=False)
+        goals = np.stack([cells % dimx, cells // dimx], 1)
+        want = orc.bfs_fields(dimx, dimy, obst, goals)
+        env = {"MRP_BFS_PACK": "1", "MRP_WIDEN_THREADS": "3"}
+        if batch != "0":
+            env["MRP_BFS_BATCH"] = batch
+        # an output buffer that is only 4-byte aligned
+        raw = np.empty(ng * dimx * dimy + 1, np.int32)
+        out = raw[1:].reshape(ng, dimx * dimy)
+        got = _with_env(env, lambda: capi.bfs_fields(dimx, dimy, obst, goals, out=out))
+        assert np.array_equal(got, want)
+        plain = _with_env({"MRP_BFS_PACK": "0"}, lambda: capi.bfs_fields(dimx, dimy, obst, goals))
+        assert np.array_equal(plain, want)
+
+
+def test_packed_transfer_overflow(capi, orc):
+    """A batch with a finite distance >= 65535 cannot travel as uint16 and is
+    sent again as int32; the other batches stay packed."""
+    dimx, dimy = 520, 261
+    obst = []
+    for y in range(1, dimy, 2):
+        gap = dimx - 1 if (y // 2) % 2 == 0 else 0
+        obst += [[x, y] for x in range(dimx) if x != gap]
+    goals = [[0, 0], [260, 130], [0, 0], [dimx - 1, dimy - 1], [3, 128]]
+    want = orc.bfs_fields(dimx, dimy, obst, goals)
+    assert want[0][want[0] != capi.INF].max() > 65535
+    assert want[1][want[1] != capi.INF].max() < 65535
+    for batch in ("1", "2", "5"):
+        got = _with_env({"MRP_BFS_PACK": "1", "MRP_BFS_BATCH": batch},
+                        lambda: capi.bfs_fields(dimx, dimy, obst, goals))
+        assert np.array_equal(got, want), batch
+
+
 def test_c5_map_sample(capi, orc):
     from libmultirobotplanning_b200 import instances
     inst = instances.synthetic_c5()
