@@ -574,22 +574,27 @@ def run_ours(args):
         return float(t.item())
 
     e2e_steps = max(1, min(args.steps, 3))
-    # the int32 transfer (4 B per cell over PCIe) for comparison, then the default:
-    # uint16 over the bus, expanded to the same int32 array by host threads
+    # the int32 transfer (4 B per cell over PCIe) and the uint16 one for comparison,
+    # then the default: detour bytes over the bus, expanded to the same int32 array
+    # by host threads
     os.environ["MRP_BFS_PACK"] = "0"
     te_plain = e2e_rate(1)
     os.environ.pop("MRP_BFS_PACK")
+    os.environ["MRP_BFS_FMT"] = "16"
+    te_u16 = e2e_rate(1)
+    os.environ.pop("MRP_BFS_FMT")
     h_out.zero_()
     te = e2e_rate(e2e_steps)
-    packed = Ge * cells >= (16 << 20)
     e2e = {"value": world * Ge * cells / te, "unit": "cells/s",
            "h2d_bytes_per_step": int(obst.nbytes + gxy.nbytes),
-           "d2h_bytes_per_step": int(Ge * cells * (2 if packed else 4)), "goals_per_step": Ge,
+           "d2h_bytes_per_step": capi.bfs_d2h_bytes(), "goals_per_step": Ge,
            "ms_per_step": te * 1e3,
            "host_result_bytes_per_step": int(Ge * cells * 4),
            "int32_transfer_cells_per_s": world * Ge * cells / te_plain,
-           "api": "mrp_bfs_fields (host pointers, pinned int32 output; fields cross PCIe as "
-                  "uint16 and are expanded by host threads, MRP_BFS_PACK=0 sends int32)"}
+           "uint16_transfer_cells_per_s": world * Ge * cells / te_u16,
+           "api": "mrp_bfs_fields (host pointers, pinned int32 output; fields cross PCIe as one "
+                  "detour byte per cell, (distance - Manhattan)/2, and are expanded by host "
+                  "threads; MRP_BFS_FMT=16 sends uint16, MRP_BFS_PACK=0 int32)"}
     # spot-check the e2e output against the oracle (checker only, 2 goals)
     if rank == 0:
         from oracle import orc

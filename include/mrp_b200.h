@@ -82,13 +82,17 @@ int mrp_map_destroy(mrp_map map);
  *   obstacle; a goal that is itself an obstacle yields 0 at the goal and
  *   MRP_INF elsewhere (the Floyd–Warshall row of an isolated vertex).
  *
- * Transfer: results of 16 Mi cells or more leave the device as uint16
- * (0xFFFF = MRP_INF) and are expanded to int32 by host threads while the next
- * batch is on the bus (the call is PCIe-bound at 4 B per cell); a batch with a
- * finite distance >= 65535 is sent as int32.  `out` holds the same int32
- * values either way.  Environment: MRP_BFS_PACK=0 never packs, =1 always
- * packs; MRP_WIDEN_THREADS = host threads of the expansion (default: all
- * cores, at most 16). */
+ * Transfer: results of 16 Mi cells or more leave the device packed and are
+ * expanded to int32 by host threads while the next batch is on the bus (the
+ * call is PCIe-bound at 4 B per cell).  Formats, narrowest first, chosen per
+ * batch of goals: one byte per cell, (distance - Manhattan distance to the
+ * goal) / 2, 255 = MRP_INF (the two distances have the same parity on a
+ * 4-connected grid); uint16, 0xFFFF = MRP_INF; int32.  A batch moves on to the
+ * next format when a value does not fit (detours of 510 steps or more, finite
+ * distances >= 65535).  `out` holds the same int32 values either way.
+ * Environment: MRP_BFS_PACK=0 never packs, =1 always packs; MRP_BFS_FMT=16
+ * starts at uint16; MRP_WIDEN_THREADS = host threads of the expansion
+ * (default: all cores, at most 16). */
 int mrp_bfs_fields(int dimx, int dimy, const int32_t* obst_xy, int n_obst,
                    const int32_t* goal_xy, int n_goals, int32_t* out);
 /* The host half of the packed transfer, exported for device-resident
@@ -96,6 +100,13 @@ int mrp_bfs_fields(int dimx, int dimy, const int32_t* obst_xy, int n_obst,
  * dst[i] = src[i] == 0xFFFF ? MRP_INF : src[i] on `threads` host threads.
  * Needs no device. */
 int mrp_widen_u16(const uint16_t* src, int32_t* dst, size_t n, int threads);
+/* Same for the one-byte format: dst[k][y][x] = src == 255 ? MRP_INF :
+ * 2*src + |x - gx_k| + |y - gy_k|, goal_cell[k] = gx_k + dimx*gy_k. */
+int mrp_widen_u8(const uint8_t* src, int32_t* dst, int dimx, int dimy,
+                 const int32_t* goal_cell, int n_fields, int threads);
+/* Bytes the last mrp_bfs_fields call moved from the device to the host
+ * (bench.py's `d2h_bytes_per_step`). */
+long long mrp_bfs_d2h_bytes(void);
 /* Many small maps in one launch (configs C2/C4: every instance has its own
  * obstacle layout).  dims[m] = (dimx, dimy); obstacles and goals are CSR over
  * maps; fields are written back to back in goal order (field of goal k has

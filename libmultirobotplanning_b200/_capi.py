@@ -54,7 +54,7 @@ EXPORTS = [
     "mrp_focal_counts", "mrp_conflicts_dev", "mrp_decode_conflict",
     "mrp_lowlevel_batch", "mrp_launch_count", "mrp_fieldset_create",
     "mrp_fieldset_read", "mrp_fieldset_destroy", "mrp_lowlevel_batch_fs",
-    "mrp_set_lane", "mrp_max_lanes", "mrp_widen_u16",
+    "mrp_set_lane", "mrp_max_lanes", "mrp_widen_u16", "mrp_widen_u8", "mrp_bfs_d2h_bytes",
 ]
 
 _lib = None
@@ -74,6 +74,9 @@ def lib():
         _lib.mrp_bfs_workspace_bytes.restype = C.c_size_t
         _lib.mrp_bfs_workspace_bytes.argtypes = [C.c_void_p, C.c_int]
         _lib.mrp_launch_count.restype = C.c_longlong
+        _lib.mrp_bfs_d2h_bytes.restype = C.c_longlong
+        _lib.mrp_widen_u8.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p,
+                                      C.c_int, C.c_int]
         _lib.mrp_widen_u16.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int]
         _lib.mrp_map_destroy.argtypes = [C.c_void_p]
         _lib.mrp_bfs_fields_dev.argtypes = [C.c_void_p, C.c_void_p, C.c_int,
@@ -155,6 +158,22 @@ def bfs_fields(dimx, dimy, obst_xy, goal_xy, out=None):
     check(lib().mrp_bfs_fields(dimx, dimy, _p(obst), len(obst), _p(goals),
                                len(goals), _p(out)))
     return out
+
+
+def widen_u8(src, dimx, dimy, goal_cell, threads=4, out=None):
+    """Host half of the one-byte field transfer (needs no device):
+    src [n_fields, dimy*dimx] uint8 detours -> int32 distances."""
+    src = np.ascontiguousarray(src, np.uint8)
+    goal_cell = np.ascontiguousarray(goal_cell, np.int32)
+    if out is None:
+        out = np.empty(src.shape, np.int32)
+    check(lib().mrp_widen_u8(_p(src), _p(out), dimx, dimy, _p(goal_cell), len(goal_cell), threads))
+    return out
+
+
+def bfs_d2h_bytes():
+    """Device-to-host bytes of the last bfs_fields call."""
+    return int(lib().mrp_bfs_d2h_bytes())
 
 
 def widen_u16(src, threads=4, out=None):

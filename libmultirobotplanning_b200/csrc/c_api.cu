@@ -403,11 +403,67 @@ pack_fields_u16_kernel(const int32_t* __restrict__ in, uint16_t* __restrict__ ou
   if (__syncthreads_or(ovf) && threadIdx.x == 0) atomicOr(overflow, 1);
 }
 
+// One byte per cell: h = (distance - Manhattan distance to the goal) / 2.  On a
+// 4-connected grid the two have the same parity and the BFS distance is never
+// the smaller one, so h is a non-negative integer: the detour, in pairs of
+// steps, that the obstacles force.  255 = MRP_INF; a batch with h >= 255
+// somewhere goes to the uint16 format.  VEC: dimx % 16 == 0, one thread packs
+// 16 cells of one row.
+extern "C++" {
+template <bool VEC>
+__global__ void __launch_bounds__(256)
+pack_fields_u8_kernel(const int32_t* __restrict__ in, uint8_t* __restrict__ out, size_t n,
+                      int dimx, int cells, const int32_t* __restrict__ goalCell,
+                      int* __restrict__ overflow) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  bool ovf = false;
+  auto cvt = [&](int v, int m) -> uint32_t {
+    if (v == MRP_INF) return 255u;
+    const int h = (v - m) >> 1;
+    if (h >= 255) ovf = true;
+    return (uint32_t)h & 255u;
+  };
+  if (VEC) {
+    const size_t n16 = n >> 4;  // cells % 16 == 0
+    for (size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x; k < n16; k += stride) {
+      const size_t i = k << 4;
+      const int f = (int)(i / (size_t)cells), cell = (int)(i - (size_t)f * cells);
+      const int g = __ldg(goalCell + f);
+      const int gx = g % dimx, gy = g / dimx, x0 = cell % dimx, y = cell / dimx;
+      const int base = abs(y - gy);
+      uint32_t w[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int4 a = __ldcs(reinterpret_cast<const int4*>(in) + 4 * k + q);
+        const int x = x0 + 4 * q;
+        w[q] = cvt(a.x, base + abs(x - gx)) | (cvt(a.y, base + abs(x + 1 - gx)) << 8) |
+               (cvt(a.z, base + abs(x + 2 - gx)) << 16) | (cvt(a.w, base + abs(x + 3 - gx)) << 24);
+      }
+      reinterpret_cast<uint4*>(out)[k] = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+  } else {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+      const int f = (int)(i / (size_t)cells), cell = (int)(i - (size_t)f * cells);
+      const int g = __ldg(goalCell + f);
+      const int m = abs(cell % dimx - g % dimx) + abs(cell / dimx - g / dimx);
+      out[i] = (uint8_t)cvt(in[i], m);
+    }
+  }
+  if (__syncthreads_or(ovf) && threadIdx.x == 0) atomicOr(overflow, 1);
+}
+}  // extern "C++"
+
 extern "C++" {
 namespace mrp {
-void widenFieldU16(const uint16_t* src, int32_t* dst, size_t n, int threads);  // widen.cpp
+// widen.cpp
+void widenFieldU16(const uint16_t* src, int32_t* dst, size_t n, int threads);
+void widenFieldU8(const uint8_t* src, int32_t* dst, int dimx, int dimy, const int32_t* goalCell,
+                  size_t n_fields, int threads);
 }
 }
+
+// device-to-host bytes of the last mrp_bfs_fields call (mrp_bfs_d2h_bytes)
+static std::atomic<long long> g_bfsD2hBytes{0};
 
 static int envInt(const char* name, int dflt) {
   const char* v = getenv(name);
@@ -455,6 +511,7 @@ static int bfsFieldsHostDirect(mrp_map map, const int32_t* d_goals, int n_goals,
         rc = fail(MRP_ERR_CUDA, "D2H copy failed: %s", cudaGetErrorString(e));
         break;
       }
+      g_bfsD2hBytes += (long long)(n * fieldBytes);
       cudaEventRecord(copied[b], c.copyStream);
       b ^= 1;
     }
@@ -471,22 +528,25 @@ static int bfsFieldsHostDirect(mrp_map map, const int32_t* d_goals, int n_goals,
   return rc;
 }
 
-// uint16 fields through page-locked staging slots, expanded by host threads.
-// Three slots: one being filled by the copy engine, one being expanded, one
-// in between.  overflowed[k] = 1 for the batches that must be sent as int32.
-static int bfsFieldsHostPacked(mrp_map map, const int32_t* d_goals, int n_goals, size_t batch,
-                               int32_t* out, std::vector<char>& overflowed) {
+// Packed fields (bpc = 1: detour bytes, bpc = 2: uint16) through page-locked
+// staging slots, expanded by host threads.  Three slots: one being filled by
+// the copy engine, one being expanded, one in between.  `order` lists the
+// batches to send; overflowed[k] = 1 for those that need a wider format.
+static int bfsFieldsHostPacked(mrp_map map, const int32_t* d_goals, const int32_t* h_goals,
+                               int n_goals, size_t batch, int bpc, int32_t* out,
+                               const std::vector<size_t>& order, std::vector<char>& overflowed) {
   constexpr int NS = 3;
   Context& c = ctx();
   const size_t cells = (size_t)map->dimx * map->dimy;
   const size_t nBatches = ((size_t)n_goals + batch - 1) / batch;
+  const size_t nOrder = order.size();
   overflowed.assign(nBatches, 0);
   const int threads = std::max(1, envInt("MRP_WIDEN_THREADS",
                                          std::min(16, (int)std::thread::hardware_concurrency())));
   const size_t wsBytes = (map->W == 1 && map->S == 1) ? 16 * batch + 256
                                                       : bfsLargeWorkspaceBytes(map, (int)batch);
-  // staging slot: batch*cells uint16, then the overflow flag of the batch
-  const size_t slotBytes = ((batch * cells * 2 + 255) & ~(size_t)255) + 256;
+  // staging slot: batch*cells packed values, then the overflow flag of the batch
+  const size_t slotBytes = ((batch * cells * (size_t)bpc + 255) & ~(size_t)255) + 256;
   int rc = 0;
   int32_t* d_out = nullptr;
   char* wsp = nullptr;
@@ -509,37 +569,42 @@ static int bfsFieldsHostPacked(mrp_map map, const int32_t* d_goals, int n_goals,
   const int device = c.device;
   std::thread worker([&] {
     cudaSetDevice(device);
-    for (size_t k = 0;; ++k) {
+    for (size_t j = 0;; ++j) {
       {
         std::unique_lock<std::mutex> lk(m);
-        cv.wait(lk, [&] { return enqueued > k || stop; });
-        if (enqueued <= k) return;
+        cv.wait(lk, [&] { return enqueued > j || stop; });
+        if (enqueued <= j) return;
       }
-      const int s = (int)(k % NS);
+      const int s = (int)(j % NS);
       cudaError_t e = cudaEventSynchronize(copied[s]);
       if (e != cudaSuccess) workerErr = e;
       const char* slot = static_cast<const char*>(h_pack) + (size_t)s * slotBytes;
+      const size_t k = order[j];
       const size_t g0 = k * batch, n = std::min(batch, (size_t)n_goals - g0);
       if (e == cudaSuccess) {
         if (*reinterpret_cast<const int*>(slot + slotBytes - 256))
           overflowed[k] = 1;
+        else if (bpc == 1)
+          widenFieldU8(reinterpret_cast<const uint8_t*>(slot), out + g0 * cells, map->dimx,
+                       map->dimy, h_goals + g0, n, threads);
         else
           widenFieldU16(reinterpret_cast<const uint16_t*>(slot), out + g0 * cells, n * cells,
                         threads);
       }
       {
         std::lock_guard<std::mutex> lk(m);
-        widened = k + 1;
+        widened = j + 1;
       }
       cv.notify_all();
     }
   });
-  for (size_t k = 0; k < nBatches && rc == 0; ++k) {
-    const int s = (int)(k % NS);
+  for (size_t j = 0; j < nOrder && rc == 0; ++j) {
+    const int s = (int)(j % NS);
+    const size_t k = order[j];
     const size_t g0 = k * batch, n = std::min(batch, (size_t)n_goals - g0);
-    if (k >= NS) {  // the slot's previous batch must have been expanded
+    if (j >= NS) {  // the slot's previous batch must have been expanded
       std::unique_lock<std::mutex> lk(m);
-      cv.wait(lk, [&] { return widened + NS > k; });
+      cv.wait(lk, [&] { return widened + NS > j; });
     }
     rc = bfsFieldsDevLocked(map, d_goals + g0, (int)n, d_out, wsp, c.stream);
     if (rc) break;
@@ -548,13 +613,24 @@ static int bfsFieldsHostPacked(mrp_map map, const int32_t* d_goals, int n_goals,
     cudaMemsetAsync(dflag, 0, sizeof(int), c.stream);
     const size_t total = n * cells;
     const int grid = (int)std::min<size_t>((total / 8 + 255) / 256 + 1, (size_t)c.smCount * 16);
-    pack_fields_u16_kernel<<<grid, 256, 0, c.stream>>>(d_out, reinterpret_cast<uint16_t*>(dslot),
-                                                       total, dflag);
+    if (bpc == 2)
+      pack_fields_u16_kernel<<<grid, 256, 0, c.stream>>>(
+          d_out, reinterpret_cast<uint16_t*>(dslot), total, dflag);
+    else if (map->dimx % 16 == 0)
+      pack_fields_u8_kernel<true><<<grid, 256, 0, c.stream>>>(
+          d_out, reinterpret_cast<uint8_t*>(dslot), total, map->dimx, (int)cells, d_goals + g0,
+          dflag);
+    else
+      pack_fields_u8_kernel<false><<<grid, 256, 0, c.stream>>>(
+          d_out, reinterpret_cast<uint8_t*>(dslot), total, map->dimx, (int)cells, d_goals + g0,
+          dflag);
     countLaunch();
     cudaEventRecord(done[s], c.stream);
     cudaStreamWaitEvent(c.copyStream, done[s], 0);
     char* hslot = static_cast<char*>(h_pack) + (size_t)s * slotBytes;
-    cudaError_t e = cudaMemcpyAsync(hslot, dslot, total * 2, cudaMemcpyDeviceToHost, c.copyStream);
+    cudaError_t e = cudaMemcpyAsync(hslot, dslot, total * (size_t)bpc, cudaMemcpyDeviceToHost,
+                                    c.copyStream);
+    g_bfsD2hBytes += (long long)(total * (size_t)bpc);
     if (e == cudaSuccess)
       e = cudaMemcpyAsync(hslot + slotBytes - 256, dflag, sizeof(int), cudaMemcpyDeviceToHost,
                           c.copyStream);
@@ -565,7 +641,7 @@ static int bfsFieldsHostPacked(mrp_map map, const int32_t* d_goals, int n_goals,
     cudaEventRecord(copied[s], c.copyStream);
     {
       std::lock_guard<std::mutex> lk(m);
-      enqueued = k + 1;
+      enqueued = j + 1;
     }
     cv.notify_all();
   }
@@ -605,6 +681,7 @@ int mrp_bfs_fields(int dimx, int dimy, const int32_t* obst_xy, int n_obst,
     for (int k = 0; k < n_goals; ++k)
       goalCell[k] = goal_xy[2 * k] + dimx * goal_xy[2 * k + 1];
     int32_t* d_goals = nullptr;
+    g_bfsD2hBytes = 0;
     do {
       if ((rc = scratch(0, (size_t)std::max(n_goals, 1), &d_goals))) break;
       cudaError_t e = cudaMemcpyAsync(d_goals, goalCell.data(), (size_t)n_goals * 4,
@@ -622,9 +699,20 @@ int mrp_bfs_fields(int dimx, int dimy, const int32_t* obst_xy, int n_obst,
         size_t batch = std::max<size_t>((size_t)c.smCount, ((size_t)1 << 26) / cells);
         if (envInt("MRP_BFS_BATCH", 0) > 0) batch = (size_t)envInt("MRP_BFS_BATCH", 0);  // tests
         batch = std::min<size_t>(batch, (size_t)n_goals);
+        // narrowest format first; the batches that do not fit move on to the next one
+        const size_t nBatches = ((size_t)n_goals + batch - 1) / batch;
+        std::vector<size_t> order(nBatches);
+        for (size_t k = 0; k < nBatches; ++k) order[k] = k;
         std::vector<char> overflowed;
-        rc = bfsFieldsHostPacked(map, d_goals, n_goals, batch, out, overflowed);
-        if (rc == 0 && std::find(overflowed.begin(), overflowed.end(), 1) != overflowed.end())
+        for (int bpc = envInt("MRP_BFS_FMT", 8) == 16 ? 2 : 1; bpc <= 2 && rc == 0 && !order.empty();
+             ++bpc) {
+          rc = bfsFieldsHostPacked(map, d_goals, goalCell.data(), n_goals, batch, bpc, out, order,
+                                   overflowed);
+          order.clear();
+          for (size_t k = 0; k < nBatches; ++k)
+            if (overflowed[k]) order.push_back(k);
+        }
+        if (rc == 0 && !order.empty())
           rc = bfsFieldsHostDirect(map, d_goals, n_goals, batch, out, &overflowed);
       } else {
         size_t batch = std::max<size_t>(4 * (size_t)c.smCount, ((size_t)1 << 28) / cells);
@@ -635,6 +723,19 @@ int mrp_bfs_fields(int dimx, int dimy, const int32_t* obst_xy, int n_obst,
   }
   mrp_map_destroy(map);
   return rc;
+}
+
+long long mrp_bfs_d2h_bytes(void) { return g_bfsD2hBytes.load(); }
+
+int mrp_widen_u8(const uint8_t* src, int32_t* dst, int dimx, int dimy, const int32_t* goal_cell,
+                 int n_fields, int threads) {
+  MRP_CHECK(dimx > 0 && dimy > 0 && n_fields >= 0, MRP_ERR_INVALID, "bad dimensions");
+  MRP_CHECK(n_fields == 0 || (src && dst && goal_cell), MRP_ERR_INVALID, "NULL pointer");
+  for (int k = 0; k < n_fields; ++k)
+    MRP_CHECK(goal_cell[k] >= 0 && (size_t)goal_cell[k] < (size_t)dimx * dimy, MRP_ERR_INVALID,
+              "goal cell outside the map");
+  widenFieldU8(src, dst, dimx, dimy, goal_cell, (size_t)n_fields, std::max(1, threads));
+  return 0;
 }
 
 int mrp_widen_u16(const uint16_t* src, int32_t* dst, size_t n, int threads) {

@@ -58,6 +58,39 @@ def test_widen_u16_host_half_of_packed_transfer():
                 assert (raw[:off] == -7).all() and (raw[off + n:] == -7).all()
 
 
+def test_widen_u8_host_half_of_packed_transfer():
+    """mrp_widen_u8 (no device needed): distance = 2*byte + Manhattan distance
+    to the field's goal, 255 -> MRP_INF, for ragged widths, unaligned buffers
+    and any thread count; round trip from oracle fields."""
+    import numpy as np
+    from libmultirobotplanning_b200 import capi
+    from oracle import orc
+    rng = np.random.default_rng(4)
+    for dimx, dimy, ng in [(1, 1, 1), (7, 5, 3), (16, 16, 4), (33, 9, 5), (300, 70, 6), (1024, 20, 3)]:
+        cells = dimx * dimy
+        free = rng.random(cells) > 0.2
+        obst = [[c % dimx, c // dimx] for c in np.flatnonzero(~free)]
+        goal_cell = rng.choice(cells, ng, replace=False).astype(np.int32)
+        goals = np.stack([goal_cell % dimx, goal_cell // dimx], 1)
+        want = orc.bfs_fields(dimx, dimy, obst, goals)
+        xs, ys = np.arange(cells) % dimx, np.arange(cells) // dimx
+        man = np.abs(xs[None] - goals[:, :1]) + np.abs(ys[None] - goals[:, 1:])
+        fin = want != capi.INF
+        det = np.where(fin, want - man, 0)
+        assert (det >= 0).all() and (det % 2 == 0).all()
+        assert det.max() // 2 < 255
+        src = np.where(fin, det // 2, 255).astype(np.uint8)
+        for threads in (1, 5):
+            for off in (0, 1, 3):
+                raw = np.full(ng * cells + off + 8, -7, np.int32)
+                dst = raw[off:off + ng * cells].reshape(ng, cells)
+                capi.widen_u8(src, dimx, dimy, goal_cell, threads, out=dst)
+                assert np.array_equal(dst, want), (dimx, dimy, threads, off)
+                assert (raw[:off] == -7).all() and (raw[off + ng * cells:] == -7).all()
+    with pytest.raises(capi.MrpError):
+        capi.widen_u8(np.zeros((1, 4), np.uint8), 2, 2, [4])
+
+
 def test_product_does_not_import_oracle():
     pkg = os.path.join(ROOT, "libmultirobotplanning_b200")
     for dirpath, _, files in os.walk(pkg):

@@ -108,19 +108,20 @@ def _with_env(env, fn):
             os.environ.pop(k, None)
 
 
+@pytest.mark.parametrize("fmt", ["8", "16"])
 @pytest.mark.parametrize("batch", ["1", "3", "0"])
-def test_packed_transfer(capi, orc, batch):
-    """Fields sent as uint16 and expanded on the host (mrp_bfs_fields for large
-    results) equal the int32 transfer and the oracle; many small batches cycle
-    through the three staging slots."""
+def test_packed_transfer(capi, orc, batch, fmt):
+    """Fields sent as detour bytes or uint16 and expanded on the host
+    (mrp_bfs_fields for large results) equal the int32 transfer and the oracle;
+    many small batches cycle through the three staging slots."""
     rng = np.random.default_rng(5)
     for dimx, dimy, density, ng in [(300, 200, 0.2, 40), (33, 7, 0.1, 11), (1, 1, 0.0, 1),
-                                    (1024, 40, 0.2, 7)]:
+                                    (1024, 40, 0.2, 7), (48, 31, 0.3, 9)]:
         obst = _rand_map(rng, dimx, dimy, density)
         cells = rng.choice(dimx * dimy, ng, replace=False)
         goals = np.stack([cells % dimx, cells // dimx], 1)
         want = orc.bfs_fields(dimx, dimy, obst, goals)
-        env = {"MRP_BFS_PACK": "1", "MRP_WIDEN_THREADS": "3"}
+        env = {"MRP_BFS_PACK": "1", "MRP_WIDEN_THREADS": "3", "MRP_BFS_FMT": fmt}
         if batch != "0":
             env["MRP_BFS_BATCH"] = batch
         # an output buffer that is only 4-byte aligned
@@ -128,26 +129,51 @@ def test_packed_transfer(capi, orc, batch):
         out = raw[1:].reshape(ng, dimx * dimy)
         got = _with_env(env, lambda: capi.bfs_fields(dimx, dimy, obst, goals, out=out))
         assert np.array_equal(got, want)
+        # random maps of this density have short detours: nothing is sent twice
+        assert capi.bfs_d2h_bytes() == ng * dimx * dimy * (1 if fmt == "8" else 2)
         plain = _with_env({"MRP_BFS_PACK": "0"}, lambda: capi.bfs_fields(dimx, dimy, obst, goals))
         assert np.array_equal(plain, want)
+        assert capi.bfs_d2h_bytes() == ng * dimx * dimy * 4
 
 
-def test_packed_transfer_overflow(capi, orc):
-    """A batch with a finite distance >= 65535 cannot travel as uint16 and is
-    sent again as int32; the other batches stay packed."""
-    dimx, dimy = 520, 261
+def _serpentine(dimx, dimy):
     obst = []
     for y in range(1, dimy, 2):
         gap = dimx - 1 if (y // 2) % 2 == 0 else 0
         obst += [[x, y] for x in range(dimx) if x != gap]
+    return obst
+
+
+def test_packed_transfer_overflow(capi, orc):
+    """A batch with a detour of 510 steps or more cannot travel as bytes and is
+    sent again as uint16; one with a finite distance >= 65535 is sent again as
+    int32; the other batches stay in the narrow format."""
+    dimx, dimy = 520, 261
+    obst = _serpentine(dimx, dimy)
     goals = [[0, 0], [260, 130], [0, 0], [dimx - 1, dimy - 1], [3, 128]]
     want = orc.bfs_fields(dimx, dimy, obst, goals)
     assert want[0][want[0] != capi.INF].max() > 65535
     assert want[1][want[1] != capi.INF].max() < 65535
-    for batch in ("1", "2", "5"):
+    for fmt in ("8", "16"):
+        for batch in ("1", "2", "5"):
+            got = _with_env({"MRP_BFS_PACK": "1", "MRP_BFS_BATCH": batch, "MRP_BFS_FMT": fmt},
+                            lambda: capi.bfs_fields(dimx, dimy, obst, goals))
+            assert np.array_equal(got, want), (fmt, batch)
+    # a small serpentine: detours beyond a byte, distances within uint16; the
+    # open map next to it in the same call stays in bytes when it has its own batch
+    dimx, dimy = 64, 33
+    obst = _serpentine(dimx, dimy)
+    goals = [[0, 0], [63, 32], [5, 16]]
+    want = orc.bfs_fields(dimx, dimy, obst, goals)
+    fin = want[0] != capi.INF
+    assert 510 < want[0][fin].max() < 65535
+    cells = dimx * dimy
+    for batch, nbytes in (("1", None), ("3", 3 * cells * (1 + 2))):
         got = _with_env({"MRP_BFS_PACK": "1", "MRP_BFS_BATCH": batch},
                         lambda: capi.bfs_fields(dimx, dimy, obst, goals))
         assert np.array_equal(got, want), batch
+        if nbytes is not None:
+            assert capi.bfs_d2h_bytes() == nbytes
 
 
 def test_c5_map_sample(capi, orc):
