@@ -649,6 +649,9 @@ def main():
         os.environ["OMP_NUM_THREADS"] = os.environ.get(
             "MRP_BENCH_OMP", str(max(1, (os.cpu_count() or 1) // world)))
         os.environ.setdefault("OMP_WAIT_POLICY", "passive")  # idle workers must not spin on shared cores
+        # same for the host threads that expand packed distance fields (mrp_bfs_fields)
+        os.environ.setdefault("MRP_WIDEN_THREADS",
+                              str(max(1, min(16, (os.cpu_count() or 1) // world))))
         # stdout carries exactly one JSON line: NCCL prints its version banner at every
         # debug level from VERSION up (WARN included), and to stdout unless redirected
         os.environ["NCCL_DEBUG"] = "NONE"
