@@ -391,6 +391,132 @@ conflict_hash_kernel(const int32_t* __restrict__ posT, int N, int mode, int H,
   }
 }
 
+// ---- one table, one atomic per agent ----------------------------------------
+// conflict_hash_kernel above spends three atomics per agent and phase on a
+// 16-byte slot (key, count, smallest id) and builds a second table for the
+// moves.  This version keeps ONE table of 64-bit entries (cell << 32 | agent)
+// per timestep:
+//   * an agent is inserted with a single atomicCAS per probe; every entry of
+//     its own cell that it walks past on the way to its free slot is an agent
+//     that got there first, i.e. one vertex-conflict pair (i, j), seen exactly
+//     once: by whichever of the two was inserted later;
+//   * a swap partner of agent i (cells a -> b) stood on b at time t, so it is
+//     one of the entries of cell b in the same table; its position at t + 1
+//     comes from the transposed table (rowB[j] == a).  Two agents resting on
+//     one cell match each other here as in the reference's test
+//     (cbs.cpp:363-382).  Every pair is seen from both sides.
+// 8 bytes per slot instead of 16 and 512 threads: three CTAs per SM at N = 4096.
+constexpr int kHash2Threads = 512;
+constexpr int kHash2PerThread = kHashMaxN / kHash2Threads;
+
+__device__ __forceinline__ uint32_t hash32(uint32_t k) {
+  k ^= k >> 16;
+  k *= 0x85ebca6bu;
+  k ^= k >> 13;
+  k *= 0xc2b2ae35u;
+  k ^= k >> 16;
+  return k;
+}
+
+template <bool kFirst, bool kCount>
+__global__ void __launch_bounds__(kHash2Threads)
+conflict_hash2_kernel(const int32_t* __restrict__ posT, int N, int mode, int H,
+                      unsigned long long* __restrict__ result) {
+  extern __shared__ unsigned long long tab[];  // [H]
+  __shared__ unsigned long long sBest[kHash2Threads / 32];
+  __shared__ unsigned long long sSum[kHash2Threads / 32];
+  const int t = blockIdx.x;
+  const int maxLen = (int)result[2];
+  const int max_t = maxLen - (mode == 0 ? 1 : 0);
+  if (t >= max_t) return;
+  if (kFirst && !kCount) {
+    const unsigned long long b = *(volatile unsigned long long*)&result[0];
+    if (b != kNoConflict && (int)(b >> 41) < t) return;
+  }
+  const uint32_t mask = (uint32_t)H - 1u;
+  const int32_t* rowA = posT + (size_t)t * N;
+  const int32_t* rowB = rowA + N;
+  const int tid = threadIdx.x;
+  constexpr unsigned long long kEmpty = ~0ull;  // no agent has id 2^32 - 1
+
+  int a[kHash2PerThread], b[kHash2PerThread];
+#pragma unroll
+  for (int k = 0; k < kHash2PerThread; ++k) {
+    const int i = tid + k * kHash2Threads;
+    a[k] = i < N ? rowA[i] : 0;
+    b[k] = i < N ? rowB[i] : 0;
+  }
+  {
+    ulonglong2* tab2 = reinterpret_cast<ulonglong2*>(tab);
+    for (int s = tid; s < H / 2; s += kHash2Threads) tab2[s] = make_ulonglong2(kEmpty, kEmpty);
+  }
+  __syncthreads();
+  unsigned long long best = kNoConflict;
+  unsigned int pairs2 = 0;  // 2 * vertex pairs + swap pairs seen from this side
+#pragma unroll
+  for (int k = 0; k < kHash2PerThread; ++k) {
+    const int i = tid + k * kHash2Threads;
+    if (i >= N) continue;
+    const unsigned long long entry = ((unsigned long long)(uint32_t)a[k] << 32) | (uint32_t)i;
+    uint32_t s = hash32((uint32_t)a[k]) & mask;
+    while (true) {
+      const unsigned long long prev = atomicCAS(&tab[s], kEmpty, entry);
+      if (prev == kEmpty) break;
+      if ((uint32_t)(prev >> 32) == (uint32_t)a[k]) {
+        const int j = (int)(uint32_t)prev;
+        pairs2 += 2;
+        if (kFirst) best = min(best, conflictKey(t, 0, min(i, j), max(i, j)));
+      }
+      s = (s + 1) & mask;
+    }
+  }
+  // the CAS results above were consumed (returning atomics): every entry is
+  // in the table before the barrier publishes it
+  __threadfence_block();
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < kHash2PerThread; ++k) {
+    const int i = tid + k * kHash2Threads;
+    if (i >= N) continue;
+    uint32_t s = hash32((uint32_t)b[k]) & mask;
+    while (true) {
+      const unsigned long long cur = tab[s];
+      if (cur == kEmpty) break;
+      if ((uint32_t)(cur >> 32) == (uint32_t)b[k]) {
+        const int j = (int)(uint32_t)cur;
+        if (j != i && __ldg(rowB + j) == a[k]) {
+          pairs2 += 1;
+          if (kFirst) best = min(best, conflictKey(t, 1, min(i, j), max(i, j)));
+        }
+      }
+      s = (s + 1) & mask;
+    }
+  }
+  if (kFirst) {
+    best = warpMin64Key(best);
+    if ((tid & 31) == 0) sBest[tid >> 5] = best;
+  }
+  if (kCount) {
+    unsigned long long sum = pairs2;
+#pragma unroll
+    for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    if ((tid & 31) == 0) sSum[tid >> 5] = sum;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    if (kFirst) {
+      unsigned long long bb = kNoConflict;
+      for (int w = 0; w < kHash2Threads / 32; ++w) bb = min(bb, sBest[w]);
+      if (bb != kNoConflict) atomicMin(&result[0], bb);
+    }
+    if (kCount) {
+      unsigned long long tot = 0;
+      for (int w = 0; w < kHash2Threads / 32; ++w) tot += sSum[w];
+      if (tot) atomicAdd(&result[1], tot / 2);
+    }
+  }
+}
+
 // focal counts: one warp per candidate move, lanes stride over the agents
 __global__ void focal_counts_kernel(const int32_t* __restrict__ cell,
                                     const int32_t* __restrict__ len, int N,
@@ -466,6 +592,22 @@ int launchConflicts(const int32_t* d_cell, const int32_t* d_len, int N, int Tpad
                                                            d_result, posT);
   int H = 512;
   while (H < 2 * N) H <<= 1;
+  if (!getenv("MRP_CONFLICTS_HASH1")) {  // default: one table of 8-byte entries per timestep
+    const size_t smem2 = (size_t)H * 8;
+    auto run2 = [&](auto kern) {
+      cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
+      kern<<<Tpad, kHash2Threads, smem2, st>>>(posT, N, mode, H, d_result);
+    };
+    if (wantFirst && wantCount)
+      run2(conflict_hash2_kernel<true, true>);
+    else if (wantFirst)
+      run2(conflict_hash2_kernel<true, false>);
+    else
+      run2(conflict_hash2_kernel<false, true>);
+    countLaunch(3);
+    MRP_CUDA(cudaGetLastError());
+    return 0;
+  }
   const size_t smem = (size_t)H * 16;
   auto run = [&](auto kern) {
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
