@@ -127,7 +127,9 @@ int mrp_bfs_fields_dev(mrp_map map, const int32_t* d_goal_cell, int n_goals,
  * positions past the end clamp to the last cell exactly like
  * Environment::getState (example/cbs.cpp:420-429).  Entries with t >= len are
  * never read.  mode 0: max_t = max(len)-1 (cbs/ecbs, example/cbs.cpp:338-341);
- * mode 1: max_t = max(len) (cbs_ta, example/cbs_ta.cpp:372-375). */
+ * mode 1: max_t = max(len) (cbs_ta, example/cbs_ta.cpp:372-375).  An agent with
+ * len = 0 (no path yet: the reference's getState asserts, only the focal
+ * counters skip such agents, example/ecbs.cpp:287) matches nothing. */
 typedef struct {
   int32_t time;
   int32_t agent1;

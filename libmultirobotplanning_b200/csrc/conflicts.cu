@@ -421,7 +421,8 @@ __device__ __forceinline__ uint32_t hash32(uint32_t k) {
 template <bool kFirst, bool kCount>
 __global__ void __launch_bounds__(kHash2Threads)
 conflict_hash2_kernel(const int32_t* __restrict__ posT, int N, int mode, int H,
-                      unsigned long long* __restrict__ result) {
+                      unsigned long long* __restrict__ result,
+                      const unsigned char* __restrict__ todo) {
   extern __shared__ unsigned long long tab[];  // [H]
   __shared__ unsigned long long sBest[kHash2Threads / 32];
   __shared__ unsigned long long sSum[kHash2Threads / 32];
@@ -429,6 +430,7 @@ conflict_hash2_kernel(const int32_t* __restrict__ posT, int N, int mode, int H,
   const int maxLen = (int)result[2];
   const int max_t = maxLen - (mode == 0 ? 1 : 0);
   if (t >= max_t) return;
+  if (todo && !todo[t]) return;  // only the timesteps the sieve kernel handed over
   if (kFirst && !kCount) {
     const unsigned long long b = *(volatile unsigned long long*)&result[0];
     if (b != kNoConflict && (int)(b >> 41) < t) return;
@@ -517,6 +519,156 @@ conflict_hash2_kernel(const int32_t* __restrict__ posT, int N, int mode, int H,
   }
 }
 
+// ---- sieve: most agents of a timestep cannot be in any conflict ----------------
+// Two hashed bitmaps per timestep (128 Ki bits each) sort the agents out before
+// anything exact happens: `occ` has the bit of every occupied cell, `multi`
+// the bits that were set twice.  An agent can only be part of a vertex
+// conflict if the `multi` bit of its cell is set, and of a swap if it moves and
+// the `occ` bit of its target cell is set (its partner stands there); both
+// partners of a real conflict pass their test, so the exact single-table
+// procedure of conflict_hash2_kernel restricted to these candidates (~6 % of
+// the agents at N = 4096: hash collisions plus the real ones) finds every
+// pair.  Setting a bit is a plain ATOMS.OR (4 wavefronts per warp instruction;
+// an ATOMS.CAS.64 takes one per lane) and the probing loops, whose length is
+// the maximum over the lanes of a warp, run over a compacted candidate list.
+// 41 KB of shared memory per CTA instead of 64 KB.  A timestep with more than
+// kSieveCand candidates (dense pile-ups) is handed to conflict_hash2_kernel
+// through `todo`.
+constexpr int kSieveThreads = 256;
+constexpr int kSieveBits = 1 << 17;  // 3 % of the cells of a timestep collide at N = 4096
+constexpr int kSieveCand = 512;
+constexpr int kSieveSlots = 1024;
+
+template <bool kFirst, bool kCount>
+__global__ void __launch_bounds__(kSieveThreads)
+conflict_sieve_kernel(const int32_t* __restrict__ posT, int N, int mode,
+                      unsigned long long* __restrict__ result, unsigned char* __restrict__ todo) {
+  __shared__ uint32_t occ[kSieveBits / 32];
+  __shared__ uint32_t multi[kSieveBits / 32];
+  __shared__ unsigned long long tab[kSieveSlots];
+  __shared__ uint16_t cand[kSieveCand];
+  __shared__ unsigned long long sBest[kSieveThreads / 32];
+  __shared__ unsigned long long sSum[kSieveThreads / 32];
+  __shared__ int sN;
+  const int t = blockIdx.x;
+  const int maxLen = (int)result[2];
+  const int max_t = maxLen - (mode == 0 ? 1 : 0);
+  if (t >= max_t) return;
+  if (kFirst && !kCount) {
+    const unsigned long long b = *(volatile unsigned long long*)&result[0];
+    if (b != kNoConflict && (int)(b >> 41) < t) return;
+  }
+  const int32_t* rowA = posT + (size_t)t * N;
+  const int32_t* rowB = rowA + N;
+  const int tid = threadIdx.x, lane = tid & 31;
+  constexpr unsigned long long kEmpty = ~0ull;
+  constexpr uint32_t kBitMask = kSieveBits - 1, kSlotMask = kSieveSlots - 1;
+
+  for (int s = tid; s < kSieveBits / 32; s += kSieveThreads) {
+    occ[s] = 0;
+    multi[s] = 0;
+  }
+  for (int s = tid; s < kSieveSlots; s += kSieveThreads) tab[s] = kEmpty;
+  if (tid == 0) sN = 0;
+  __syncthreads();
+  for (int i = tid; i < N; i += kSieveThreads) {
+    const int a = rowA[i];
+    if (a < 0) continue;  // an agent without a path
+    const uint32_t h = hash32((uint32_t)a) & kBitMask, bit = 1u << (h & 31);
+    if (atomicOr(&occ[h >> 5], bit) & bit) atomicOr(&multi[h >> 5], bit);
+  }
+  __syncthreads();
+  for (int i0 = tid - lane; i0 < N; i0 += kSieveThreads) {
+    const int i = i0 + lane;
+    bool c = false;
+    if (i < N) {
+      const int a = rowA[i], b = rowB[i];
+      if (a >= 0) {
+        const uint32_t ha = hash32((uint32_t)a) & kBitMask;
+        c = (multi[ha >> 5] >> (ha & 31)) & 1u;
+        if (!c && a != b) {
+          const uint32_t hb = hash32((uint32_t)b) & kBitMask;
+          c = (occ[hb >> 5] >> (hb & 31)) & 1u;
+        }
+      }
+    }
+    const uint32_t m = __ballot_sync(0xffffffffu, c);
+    if (m) {
+      int base = 0;
+      if (lane == 0) base = atomicAdd(&sN, __popc(m));
+      base = __shfl_sync(0xffffffffu, base, 0);
+      const int pos = base + __popc(m & ((1u << lane) - 1u));
+      if (c && pos < kSieveCand) cand[pos] = (uint16_t)i;
+    }
+  }
+  __syncthreads();
+  const int nc = sN;
+  if (nc > kSieveCand) {
+    if (tid == 0) todo[t] = 1;
+    return;
+  }
+  unsigned long long best = kNoConflict;
+  unsigned int pairs2 = 0;  // 2 * vertex pairs + swap pairs seen from this side
+  for (int c = tid; c < nc; c += kSieveThreads) {
+    const int i = cand[c];
+    const int a = rowA[i];
+    const unsigned long long entry = ((unsigned long long)(uint32_t)a << 32) | (uint32_t)i;
+    uint32_t s = (hash32((uint32_t)a) >> 16) & kSlotMask;
+    while (true) {
+      const unsigned long long prev = atomicCAS(&tab[s], kEmpty, entry);
+      if (prev == kEmpty) break;
+      if ((uint32_t)(prev >> 32) == (uint32_t)a) {
+        const int j = (int)(uint32_t)prev;
+        pairs2 += 2;
+        if (kFirst) best = min(best, conflictKey(t, 0, min(i, j), max(i, j)));
+      }
+      s = (s + 1) & kSlotMask;
+    }
+  }
+  __threadfence_block();
+  __syncthreads();
+  for (int c = tid; c < nc; c += kSieveThreads) {
+    const int i = cand[c];
+    const int a = rowA[i], b = rowB[i];
+    uint32_t s = (hash32((uint32_t)b) >> 16) & kSlotMask;
+    while (true) {
+      const unsigned long long cur = tab[s];
+      if (cur == kEmpty) break;
+      if ((uint32_t)(cur >> 32) == (uint32_t)b) {
+        const int j = (int)(uint32_t)cur;
+        if (j != i && __ldg(rowB + j) == a) {
+          pairs2 += 1;
+          if (kFirst) best = min(best, conflictKey(t, 1, min(i, j), max(i, j)));
+        }
+      }
+      s = (s + 1) & kSlotMask;
+    }
+  }
+  if (kFirst) {
+    best = warpMin64Key(best);
+    if (lane == 0) sBest[tid >> 5] = best;
+  }
+  if (kCount) {
+    unsigned long long sum = pairs2;
+#pragma unroll
+    for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    if (lane == 0) sSum[tid >> 5] = sum;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    if (kFirst) {
+      unsigned long long bb = kNoConflict;
+      for (int w = 0; w < kSieveThreads / 32; ++w) bb = min(bb, sBest[w]);
+      if (bb != kNoConflict) atomicMin(&result[0], bb);
+    }
+    if (kCount) {
+      unsigned long long tot = 0;
+      for (int w = 0; w < kSieveThreads / 32; ++w) tot += sSum[w];
+      if (tot) atomicAdd(&result[1], tot / 2);
+    }
+  }
+}
+
 // focal counts: one warp per candidate move, lanes stride over the agents
 __global__ void focal_counts_kernel(const int32_t* __restrict__ cell,
                                     const int32_t* __restrict__ len, int N,
@@ -574,7 +726,8 @@ static int launchPairs(const int32_t* d_cell, const int32_t* d_len, int B, int N
 
 size_t conflictsWorkspaceBytes(int N, int Tpad) {
   if (N < kHashMinN || N > kHashMaxN) return 0;
-  return (size_t)(Tpad + 1) * N * 4;
+  // transposed table, then one hand-over flag per timestep
+  return (size_t)(Tpad + 1) * N * 4 + (((size_t)Tpad + 255) & ~(size_t)255);
 }
 
 int launchConflicts(const int32_t* d_cell, const int32_t* d_len, int N, int Tpad,
@@ -592,11 +745,26 @@ int launchConflicts(const int32_t* d_cell, const int32_t* d_len, int N, int Tpad
                                                            d_result, posT);
   int H = 512;
   while (H < 2 * N) H <<= 1;
-  if (!getenv("MRP_CONFLICTS_HASH1")) {  // default: one table of 8-byte entries per timestep
+  if (!getenv("MRP_CONFLICTS_HASH1")) {
+    // default: sieve kernel, then the single-table kernel on the timesteps it
+    // handed over (MRP_CONFLICTS_HASH2: single-table kernel on every timestep)
+    const bool sieve = !getenv("MRP_CONFLICTS_HASH2");
+    unsigned char* todo = nullptr;
+    if (sieve) {
+      todo = static_cast<unsigned char*>(d_ws) + (size_t)(Tpad + 1) * N * 4;
+      MRP_CUDA(cudaMemsetAsync(todo, 0, (size_t)Tpad, st));
+      if (wantFirst && wantCount)
+        conflict_sieve_kernel<true, true><<<Tpad, kSieveThreads, 0, st>>>(posT, N, mode, d_result, todo);
+      else if (wantFirst)
+        conflict_sieve_kernel<true, false><<<Tpad, kSieveThreads, 0, st>>>(posT, N, mode, d_result, todo);
+      else
+        conflict_sieve_kernel<false, true><<<Tpad, kSieveThreads, 0, st>>>(posT, N, mode, d_result, todo);
+      countLaunch();
+    }
     const size_t smem2 = (size_t)H * 8;
     auto run2 = [&](auto kern) {
       cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
-      kern<<<Tpad, kHash2Threads, smem2, st>>>(posT, N, mode, H, d_result);
+      kern<<<Tpad, kHash2Threads, smem2, st>>>(posT, N, mode, H, d_result, todo);
     };
     if (wantFirst && wantCount)
       run2(conflict_hash2_kernel<true, true>);

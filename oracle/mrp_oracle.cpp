@@ -144,6 +144,10 @@ static inline int posAt(const std::vector<Plan>& sol, size_t i, int t) {
 static inline int posAtTable(const int32_t* cell, const int32_t* len, int Tpad,
                              int i, int t) {
   int L = len[i];
+  // An empty path is outside the reference's contract for these loops
+  // (getState asserts !states.empty(), example/cbs.cpp:420-429); the C ABI
+  // defines it as "matches nothing" (include/mrp_b200.h): a private cell.
+  if (L <= 0) return -2 - i;
   return cell[(size_t)i * Tpad + (t < L ? t : L - 1)];
 }
 

@@ -139,9 +139,44 @@ def test_hashed_path_equals_all_pairs(capi, orc, monkeypatch):
             c_p = capi.count_conflicts(cell, ln, mode)
             monkeypatch.delenv("MRP_CONFLICTS_ALLPAIRS")
             assert (f_h, c_h) == (f_p, c_p), (N, mode)
+            # the default is the sieve kernel (+ the single-table kernel for dense
+            # timesteps); the single-table and the three-atomics kernels on their own
+            for var in ("MRP_CONFLICTS_HASH2", "MRP_CONFLICTS_HASH1"):
+                monkeypatch.setenv(var, "1")
+                assert (capi.first_conflict(cell, ln, 32, mode),
+                        capi.count_conflicts(cell, ln, mode)) == (f_p, c_p), (N, mode, var)
+                monkeypatch.delenv(var)
             if N <= 1024:
                 assert f_h == orc.first_conflict(cell, ln, 32, mode)
                 assert c_h == orc.count_conflicts(cell, ln, mode)
+
+
+def test_sieve_sparse_and_dense_timesteps(capi, orc, monkeypatch):
+    """One table with sparse timesteps (a handful of candidates: the sieve
+    kernel's own exact table), timesteps where most agents share cells (handed
+    over to the single-table kernel) and agents without a path."""
+    rng = np.random.default_rng(21)
+    N, T, cells = 2048, 12, 1 << 20
+    cell = rng.integers(0, cells, (N, T)).astype(np.int32)
+    cell[:, 5] = rng.integers(0, 700, N)          # a dense timestep
+    cell[:, 6] = cell[:, 5]                       # everybody rests
+    cell[:, 7] = rng.integers(0, 700, N)
+    cell[100, 2], cell[101, 2] = 77, 77           # a lone vertex conflict
+    cell[200, 9], cell[200, 10] = 500000, 500001  # a lone swap
+    cell[201, 9], cell[201, 10] = 500001, 500000
+    cell[300, 3], cell[300, 4] = cells - 1, cells - 2   # the last cell of the map
+    cell[301, 3], cell[301, 4] = cells - 2, cells - 1
+    ln = np.full(N, T, np.int32)
+    ln[7] = 0
+    ln[8] = 3
+    for mode in (0, 1):
+        want = (orc.first_conflict(cell, ln, 1 << 10, mode), orc.count_conflicts(cell, ln, mode))
+        assert (capi.first_conflict(cell, ln, 1 << 10, mode), capi.count_conflicts(cell, ln, mode)) == want
+    # without the dense timesteps the first conflict is the lone one
+    cell[:, 5:8] = rng.integers(0, cells, (N, 3))
+    f = capi.first_conflict(cell, ln, 1 << 10, 0)
+    assert f == orc.first_conflict(cell, ln, 1 << 10, 0)
+    assert capi.count_conflicts(cell, ln, 0) == orc.count_conflicts(cell, ln, 0)
 
 
 def test_hashed_path_stress_high_load(capi, orc):
