@@ -198,29 +198,58 @@ constexpr int kHashMaxN = 4096;          // table of 2*N slots x 16 B <= 128 KB
 constexpr int kHashMinN = 257;
 constexpr int kHashPerThread = kHashMaxN / kHashThreads;
 
+// Row stride of the transposed table: rows start on 16-byte boundaries (the
+// sieve kernel reads four agents per thread with one load); the pad entries
+// are agents without a path.
+__host__ __device__ __forceinline__ int rowStride(int N) { return (N + 3) & ~3; }
+
+// Transposes and clamps the whole table (rows t = 0 .. Tpad; the sweep kernels
+// stop at max_t themselves) and, in its first block, does the work of
+// conflict_prep_kernel (result = {no conflict, 0, max len, 0}): one launch and
+// no dependency of the transposition on the maximum.
 __global__ void conflict_transpose_kernel(const int32_t* __restrict__ cell,
                                           const int32_t* __restrict__ len, int N, int Tpad,
-                                          int mode,
-                                          const unsigned long long* __restrict__ result,
+                                          unsigned long long* __restrict__ result,
                                           int32_t* __restrict__ posT) {
   __shared__ int32_t tile[32][33];
-  const int maxLen = (int)result[2];
-  const int rows = maxLen - (mode == 0 ? 1 : 0) + 1;  // t = 0 .. max_t
+  __shared__ int smax[32];
   const int t0 = blockIdx.y * 32, i0 = blockIdx.x * 32;
-  if (t0 >= rows) return;
-  {
-    const int i = i0 + threadIdx.y, t = t0 + threadIdx.x;
+  const int ld = rowStride(N);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int r = threadIdx.y + 8 * k;
+    const int i = i0 + r, t = t0 + threadIdx.x;
     int v = -2 - i;  // agents without a path never match anything
     if (i < N) {
       const int L = len[i];
       if (L > 0) v = cell[(size_t)i * Tpad + min(t, L - 1)];
     }
-    tile[threadIdx.y][threadIdx.x] = v;
+    tile[r][threadIdx.x] = v;
   }
   __syncthreads();
-  {
-    const int t = t0 + threadIdx.y, i = i0 + threadIdx.x;
-    if (t < rows && i < N) posT[(size_t)t * N + i] = tile[threadIdx.x][threadIdx.y];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int r = threadIdx.y + 8 * k;
+    const int t = t0 + r, i = i0 + threadIdx.x;
+    if (t <= Tpad && i < ld) posT[(size_t)t * ld + i] = tile[threadIdx.x][r];
+  }
+  if (blockIdx.x == 0 && blockIdx.y == 0) {
+    const int tid = threadIdx.y * 32 + threadIdx.x;
+    int m = 0;
+    for (int i = tid; i < N; i += 256) m = max(m, len[i]);
+    for (int o = 16; o; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if (threadIdx.x == 0) smax[threadIdx.y] = m;
+    __syncthreads();
+    if (threadIdx.y == 0) {
+      m = threadIdx.x < 8 ? smax[threadIdx.x] : 0;
+      for (int o = 16; o; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+      if (threadIdx.x == 0) {
+        result[0] = kNoConflict;
+        result[1] = 0ull;
+        result[2] = (unsigned long long)m;
+        result[3] = 0ull;
+      }
+    }
   }
 }
 
@@ -252,8 +281,8 @@ conflict_hash_kernel(const int32_t* __restrict__ posT, int N, int mode, int H,
     if (b != kNoConflict && (int)(b >> 41) < t) return;
   }
   const uint32_t mask = (uint32_t)H - 1u;
-  const int32_t* rowA = posT + (size_t)t * N;
-  const int32_t* rowB = rowA + N;
+  const int32_t* rowA = posT + (size_t)t * rowStride(N);
+  const int32_t* rowB = rowA + rowStride(N);
   const int tid = threadIdx.x;
   constexpr unsigned long long kEmpty = ~0ull;
 
@@ -436,8 +465,8 @@ conflict_hash2_kernel(const int32_t* __restrict__ posT, int N, int mode, int H,
     if (b != kNoConflict && (int)(b >> 41) < t) return;
   }
   const uint32_t mask = (uint32_t)H - 1u;
-  const int32_t* rowA = posT + (size_t)t * N;
-  const int32_t* rowB = rowA + N;
+  const int32_t* rowA = posT + (size_t)t * rowStride(N);
+  const int32_t* rowB = rowA + rowStride(N);
   const int tid = threadIdx.x;
   constexpr unsigned long long kEmpty = ~0ull;  // no agent has id 2^32 - 1
 
@@ -534,18 +563,18 @@ conflict_hash2_kernel(const int32_t* __restrict__ posT, int N, int mode, int H,
 // 41 KB of shared memory per CTA instead of 64 KB.  A timestep with more than
 // kSieveCand candidates (dense pile-ups) is handed to conflict_hash2_kernel
 // through `todo`.
-constexpr int kSieveThreads = 256;
+constexpr int kSieveThreads = 1024;  // 4 agents per thread and pass, two CTAs per SM
 constexpr int kSieveBits = 1 << 17;  // 3 % of the cells of a timestep collide at N = 4096
 constexpr int kSieveCand = 512;
 constexpr int kSieveSlots = 1024;
 
 template <bool kFirst, bool kCount>
-__global__ void __launch_bounds__(kSieveThreads)
+__global__ void __launch_bounds__(kSieveThreads, 2)
 conflict_sieve_kernel(const int32_t* __restrict__ posT, int N, int mode,
                       unsigned long long* __restrict__ result, unsigned char* __restrict__ todo) {
-  __shared__ uint32_t occ[kSieveBits / 32];
-  __shared__ uint32_t multi[kSieveBits / 32];
-  __shared__ unsigned long long tab[kSieveSlots];
+  __shared__ __align__(16) uint32_t occ[kSieveBits / 32];
+  __shared__ __align__(16) uint32_t multi[kSieveBits / 32];
+  __shared__ __align__(16) unsigned long long tab[kSieveSlots];
   __shared__ uint16_t cand[kSieveCand];
   __shared__ unsigned long long sBest[kSieveThreads / 32];
   __shared__ unsigned long long sSum[kSieveThreads / 32];
@@ -558,47 +587,78 @@ conflict_sieve_kernel(const int32_t* __restrict__ posT, int N, int mode,
     const unsigned long long b = *(volatile unsigned long long*)&result[0];
     if (b != kNoConflict && (int)(b >> 41) < t) return;
   }
-  const int32_t* rowA = posT + (size_t)t * N;
-  const int32_t* rowB = rowA + N;
+  const int ld = rowStride(N);
+  const int32_t* rowA = posT + (size_t)t * ld;
+  const int32_t* rowB = rowA + ld;
   const int tid = threadIdx.x, lane = tid & 31;
   constexpr unsigned long long kEmpty = ~0ull;
-  constexpr uint32_t kBitMask = kSieveBits - 1, kSlotMask = kSieveSlots - 1;
+  constexpr uint32_t kSlotMask = kSieveSlots - 1;
+  // multiplicative hashes: the top 17 bits of one product for the bitmaps, the
+  // top bits of another for the exact table
+  auto bitOf = [](int c) { return ((uint32_t)c * 0x9E3779B1u) >> 15; };
+  auto slotOf = [](int c) { return (((uint32_t)c * 0x85EBCA6Bu) >> 20) & kSlotMask; };
+  static_assert(kSieveBits == 1 << 17, "bitOf keeps 17 bits");
 
-  for (int s = tid; s < kSieveBits / 32; s += kSieveThreads) {
-    occ[s] = 0;
-    multi[s] = 0;
+  // thread tid owns the agents 4*tid .. 4*tid+3 of the (padded) row: one load
+  // per row, no loop (N <= 4 * kSieveThreads)
+  int a[4], b[4];
+  {
+    int4 A = make_int4(-1, -1, -1, -1), B = A;
+    if (4 * tid < ld) {
+      A = reinterpret_cast<const int4*>(rowA)[tid];
+      B = reinterpret_cast<const int4*>(rowB)[tid];
+    }
+    a[0] = A.x, a[1] = A.y, a[2] = A.z, a[3] = A.w;
+    b[0] = B.x, b[1] = B.y, b[2] = B.z, b[3] = B.w;
   }
-  for (int s = tid; s < kSieveSlots; s += kSieveThreads) tab[s] = kEmpty;
+  {
+    const uint4 z = make_uint4(0u, 0u, 0u, 0u), e = make_uint4(~0u, ~0u, ~0u, ~0u);
+    for (int s = tid; s < kSieveBits / 128; s += kSieveThreads) {
+      reinterpret_cast<uint4*>(occ)[s] = z;
+      reinterpret_cast<uint4*>(multi)[s] = z;
+    }
+    for (int s = tid; s < kSieveSlots / 2; s += kSieveThreads) reinterpret_cast<uint4*>(tab)[s] = e;
+  }
   if (tid == 0) sN = 0;
   __syncthreads();
-  for (int i = tid; i < N; i += kSieveThreads) {
-    const int a = rowA[i];
-    if (a < 0) continue;  // an agent without a path
-    const uint32_t h = hash32((uint32_t)a) & kBitMask, bit = 1u << (h & 31);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    if (a[k] < 0) continue;  // an agent without a path (or a pad entry)
+    const uint32_t h = bitOf(a[k]), bit = 1u << (h & 31);
     if (atomicOr(&occ[h >> 5], bit) & bit) atomicOr(&multi[h >> 5], bit);
   }
   __syncthreads();
-  for (int i0 = tid - lane; i0 < N; i0 += kSieveThreads) {
-    const int i = i0 + lane;
-    bool c = false;
-    if (i < N) {
-      const int a = rowA[i], b = rowB[i];
-      if (a >= 0) {
-        const uint32_t ha = hash32((uint32_t)a) & kBitMask;
-        c = (multi[ha >> 5] >> (ha & 31)) & 1u;
-        if (!c && a != b) {
-          const uint32_t hb = hash32((uint32_t)b) & kBitMask;
-          c = (occ[hb >> 5] >> (hb & 31)) & 1u;
-        }
+  {
+    uint32_t cm = 0;  // candidates among this thread's four agents
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if (a[k] < 0) continue;
+      const uint32_t ha = bitOf(a[k]);
+      uint32_t c = (multi[ha >> 5] >> (ha & 31)) & 1u;
+      if (!c && a[k] != b[k]) {
+        const uint32_t hb = bitOf(b[k]);
+        c = (occ[hb >> 5] >> (hb & 31)) & 1u;
       }
+      cm |= c << k;
     }
-    const uint32_t m = __ballot_sync(0xffffffffu, c);
-    if (m) {
+    if (__any_sync(0xffffffffu, cm != 0)) {
+      const int cnt = __popc(cm);
+      int incl = cnt;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += v;
+      }
       int base = 0;
-      if (lane == 0) base = atomicAdd(&sN, __popc(m));
-      base = __shfl_sync(0xffffffffu, base, 0);
-      const int pos = base + __popc(m & ((1u << lane) - 1u));
-      if (c && pos < kSieveCand) cand[pos] = (uint16_t)i;
+      if (lane == 31) base = atomicAdd(&sN, incl);
+      base = __shfl_sync(0xffffffffu, base, 31);
+      int pos = base + incl - cnt;
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        if ((cm >> k) & 1u) {
+          if (pos < kSieveCand) cand[pos] = (uint16_t)(4 * tid + k);
+          ++pos;
+        }
     }
   }
   __syncthreads();
@@ -613,7 +673,7 @@ conflict_sieve_kernel(const int32_t* __restrict__ posT, int N, int mode,
     const int i = cand[c];
     const int a = rowA[i];
     const unsigned long long entry = ((unsigned long long)(uint32_t)a << 32) | (uint32_t)i;
-    uint32_t s = (hash32((uint32_t)a) >> 16) & kSlotMask;
+    uint32_t s = slotOf(a);
     while (true) {
       const unsigned long long prev = atomicCAS(&tab[s], kEmpty, entry);
       if (prev == kEmpty) break;
@@ -630,7 +690,7 @@ conflict_sieve_kernel(const int32_t* __restrict__ posT, int N, int mode,
   for (int c = tid; c < nc; c += kSieveThreads) {
     const int i = cand[c];
     const int a = rowA[i], b = rowB[i];
-    uint32_t s = (hash32((uint32_t)b) >> 16) & kSlotMask;
+    uint32_t s = slotOf(b);
     while (true) {
       const unsigned long long cur = tab[s];
       if (cur == kEmpty) break;
@@ -727,7 +787,7 @@ static int launchPairs(const int32_t* d_cell, const int32_t* d_len, int B, int N
 size_t conflictsWorkspaceBytes(int N, int Tpad) {
   if (N < kHashMinN || N > kHashMaxN) return 0;
   // transposed table, then one hand-over flag per timestep
-  return (size_t)(Tpad + 1) * N * 4 + (((size_t)Tpad + 255) & ~(size_t)255);
+  return (size_t)(Tpad + 1) * rowStride(N) * 4 + (((size_t)Tpad + 255) & ~(size_t)255);
 }
 
 int launchConflicts(const int32_t* d_cell, const int32_t* d_len, int N, int Tpad,
@@ -739,10 +799,8 @@ int launchConflicts(const int32_t* d_cell, const int32_t* d_len, int N, int Tpad
     return launchPairs(d_cell, d_len, 1, N, Tpad, mode, wantFirst, wantCount, d_result, st);
   // hashed path: prep (max len) -> transpose + clamp -> one CTA per timestep
   int32_t* posT = static_cast<int32_t*>(d_ws);
-  conflict_prep_kernel<<<1, 256, 0, st>>>(d_len, N, d_result);
-  dim3 tg((N + 31) / 32, (Tpad + 1 + 31) / 32);
-  conflict_transpose_kernel<<<tg, dim3(32, 32), 0, st>>>(d_cell, d_len, N, Tpad, mode,
-                                                           d_result, posT);
+  dim3 tg((rowStride(N) + 31) / 32, (Tpad + 1 + 31) / 32);
+  conflict_transpose_kernel<<<tg, dim3(32, 8), 0, st>>>(d_cell, d_len, N, Tpad, d_result, posT);
   int H = 512;
   while (H < 2 * N) H <<= 1;
   if (!getenv("MRP_CONFLICTS_HASH1")) {
@@ -751,7 +809,7 @@ int launchConflicts(const int32_t* d_cell, const int32_t* d_len, int N, int Tpad
     const bool sieve = !getenv("MRP_CONFLICTS_HASH2");
     unsigned char* todo = nullptr;
     if (sieve) {
-      todo = static_cast<unsigned char*>(d_ws) + (size_t)(Tpad + 1) * N * 4;
+      todo = static_cast<unsigned char*>(d_ws) + (size_t)(Tpad + 1) * rowStride(N) * 4;
       MRP_CUDA(cudaMemsetAsync(todo, 0, (size_t)Tpad, st));
       if (wantFirst && wantCount)
         conflict_sieve_kernel<true, true><<<Tpad, kSieveThreads, 0, st>>>(posT, N, mode, d_result, todo);
@@ -772,7 +830,7 @@ int launchConflicts(const int32_t* d_cell, const int32_t* d_len, int N, int Tpad
       run2(conflict_hash2_kernel<true, false>);
     else
       run2(conflict_hash2_kernel<false, true>);
-    countLaunch(3);
+    countLaunch(2);
     MRP_CUDA(cudaGetLastError());
     return 0;
   }
@@ -787,7 +845,7 @@ int launchConflicts(const int32_t* d_cell, const int32_t* d_len, int N, int Tpad
     run(conflict_hash_kernel<true, false>);
   else
     run(conflict_hash_kernel<false, true>);
-  countLaunch(3);
+  countLaunch(2);
   MRP_CUDA(cudaGetLastError());
   return 0;
 }
