@@ -210,7 +210,8 @@ __host__ __device__ __forceinline__ int rowStride(int N) { return (N + 3) & ~3; 
 __global__ void conflict_transpose_kernel(const int32_t* __restrict__ cell,
                                           const int32_t* __restrict__ len, int N, int Tpad,
                                           unsigned long long* __restrict__ result,
-                                          int32_t* __restrict__ posT) {
+                                          int32_t* __restrict__ posT,
+                                          unsigned char* __restrict__ todo) {
   __shared__ int32_t tile[32][33];
   __shared__ int smax[32];
   const int t0 = blockIdx.y * 32, i0 = blockIdx.x * 32;
@@ -233,6 +234,8 @@ __global__ void conflict_transpose_kernel(const int32_t* __restrict__ cell,
     const int t = t0 + r, i = i0 + threadIdx.x;
     if (t <= Tpad && i < ld) posT[(size_t)t * ld + i] = tile[threadIdx.x][r];
   }
+  // the hand-over flags of the sieve kernel start out clear
+  if (todo && blockIdx.x == 0 && threadIdx.y == 0 && t0 + threadIdx.x < Tpad) todo[t0 + threadIdx.x] = 0;
   if (blockIdx.x == 0 && blockIdx.y == 0) {
     const int tid = threadIdx.y * 32 + threadIdx.x;
     int m = 0;
@@ -800,7 +803,9 @@ int launchConflicts(const int32_t* d_cell, const int32_t* d_len, int N, int Tpad
   // hashed path: prep (max len) -> transpose + clamp -> one CTA per timestep
   int32_t* posT = static_cast<int32_t*>(d_ws);
   dim3 tg((rowStride(N) + 31) / 32, (Tpad + 1 + 31) / 32);
-  conflict_transpose_kernel<<<tg, dim3(32, 8), 0, st>>>(d_cell, d_len, N, Tpad, d_result, posT);
+  // hand-over flags of the sieve kernel, cleared by the transposition
+  unsigned char* todoAll = static_cast<unsigned char*>(d_ws) + (size_t)(Tpad + 1) * rowStride(N) * 4;
+  conflict_transpose_kernel<<<tg, dim3(32, 8), 0, st>>>(d_cell, d_len, N, Tpad, d_result, posT, todoAll);
   int H = 512;
   while (H < 2 * N) H <<= 1;
   if (!getenv("MRP_CONFLICTS_HASH1")) {
@@ -809,8 +814,7 @@ int launchConflicts(const int32_t* d_cell, const int32_t* d_len, int N, int Tpad
     const bool sieve = !getenv("MRP_CONFLICTS_HASH2");
     unsigned char* todo = nullptr;
     if (sieve) {
-      todo = static_cast<unsigned char*>(d_ws) + (size_t)(Tpad + 1) * rowStride(N) * 4;
-      MRP_CUDA(cudaMemsetAsync(todo, 0, (size_t)Tpad, st));
+      todo = todoAll;
       if (wantFirst && wantCount)
         conflict_sieve_kernel<true, true><<<Tpad, kSieveThreads, 0, st>>>(posT, N, mode, d_result, todo);
       else if (wantFirst)
