@@ -566,22 +566,25 @@ conflict_hash2_kernel(const int32_t* __restrict__ posT, int N, int mode, int H,
 // 41 KB of shared memory per CTA instead of 64 KB.  A timestep with more than
 // kSieveCand candidates (dense pile-ups) is handed to conflict_hash2_kernel
 // through `todo`.
-constexpr int kSieveThreads = 1024;  // 4 agents per thread and pass, two CTAs per SM
+#ifndef MRP_SIEVE_PER
+#define MRP_SIEVE_PER 8
+#endif
+constexpr int kSievePer = MRP_SIEVE_PER;                // agents per thread (4 or 8)
+constexpr int kSieveThreads = kHashMaxN / kSievePer;    // 512 threads, four CTAs per SM (4 per thread: 0.068 ms, 8: 0.064 ms)
 constexpr int kSieveBits = 1 << 17;  // 3 % of the cells of a timestep collide at N = 4096
 constexpr int kSieveCand = 512;
 constexpr int kSieveSlots = 1024;
 
 template <bool kFirst, bool kCount>
-__global__ void __launch_bounds__(kSieveThreads, 2)
+__global__ void __launch_bounds__(kSieveThreads, 2048 / kSieveThreads)
 conflict_sieve_kernel(const int32_t* __restrict__ posT, int N, int mode,
                       unsigned long long* __restrict__ result, unsigned char* __restrict__ todo) {
   __shared__ __align__(16) uint32_t occ[kSieveBits / 32];
   __shared__ __align__(16) uint32_t multi[kSieveBits / 32];
   __shared__ __align__(16) unsigned long long tab[kSieveSlots];
   __shared__ uint16_t cand[kSieveCand];
-  __shared__ unsigned long long sBest[kSieveThreads / 32];
-  __shared__ unsigned long long sSum[kSieveThreads / 32];
   __shared__ int sN;
+  __shared__ unsigned int sPairs2;
   const int t = blockIdx.x;
   const int maxLen = (int)result[2];
   const int max_t = maxLen - (mode == 0 ? 1 : 0);
@@ -602,17 +605,18 @@ conflict_sieve_kernel(const int32_t* __restrict__ posT, int N, int mode,
   auto slotOf = [](int c) { return (((uint32_t)c * 0x85EBCA6Bu) >> 20) & kSlotMask; };
   static_assert(kSieveBits == 1 << 17, "bitOf keeps 17 bits");
 
-  // thread tid owns the agents 4*tid .. 4*tid+3 of the (padded) row: one load
-  // per row, no loop (N <= 4 * kSieveThreads)
-  int a[4], b[4];
-  {
+  // thread tid owns kSievePer consecutive agents of the (padded) row: 16-byte
+  // loads, no loop (N <= kSievePer * kSieveThreads)
+  int a[kSievePer], b[kSievePer];
+#pragma unroll
+  for (int q = 0; q < kSievePer / 4; ++q) {
     int4 A = make_int4(-1, -1, -1, -1), B = A;
-    if (4 * tid < ld) {
-      A = reinterpret_cast<const int4*>(rowA)[tid];
-      B = reinterpret_cast<const int4*>(rowB)[tid];
+    if (kSievePer * tid + 4 * q < ld) {
+      A = reinterpret_cast<const int4*>(rowA)[(kSievePer / 4) * tid + q];
+      B = reinterpret_cast<const int4*>(rowB)[(kSievePer / 4) * tid + q];
     }
-    a[0] = A.x, a[1] = A.y, a[2] = A.z, a[3] = A.w;
-    b[0] = B.x, b[1] = B.y, b[2] = B.z, b[3] = B.w;
+    a[4 * q] = A.x, a[4 * q + 1] = A.y, a[4 * q + 2] = A.z, a[4 * q + 3] = A.w;
+    b[4 * q] = B.x, b[4 * q + 1] = B.y, b[4 * q + 2] = B.z, b[4 * q + 3] = B.w;
   }
   {
     const uint4 z = make_uint4(0u, 0u, 0u, 0u), e = make_uint4(~0u, ~0u, ~0u, ~0u);
@@ -622,19 +626,22 @@ conflict_sieve_kernel(const int32_t* __restrict__ posT, int N, int mode,
     }
     for (int s = tid; s < kSieveSlots / 2; s += kSieveThreads) reinterpret_cast<uint4*>(tab)[s] = e;
   }
-  if (tid == 0) sN = 0;
+  if (tid == 0) {
+    sN = 0;
+    sPairs2 = 0;
+  }
   __syncthreads();
 #pragma unroll
-  for (int k = 0; k < 4; ++k) {
+  for (int k = 0; k < kSievePer; ++k) {
     if (a[k] < 0) continue;  // an agent without a path (or a pad entry)
     const uint32_t h = bitOf(a[k]), bit = 1u << (h & 31);
     if (atomicOr(&occ[h >> 5], bit) & bit) atomicOr(&multi[h >> 5], bit);
   }
   __syncthreads();
   {
-    uint32_t cm = 0;  // candidates among this thread's four agents
+    uint32_t cm = 0;  // candidates among this thread's agents
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
+    for (int k = 0; k < kSievePer; ++k) {
       if (a[k] < 0) continue;
       const uint32_t ha = bitOf(a[k]);
       uint32_t c = (multi[ha >> 5] >> (ha & 31)) & 1u;
@@ -657,9 +664,9 @@ conflict_sieve_kernel(const int32_t* __restrict__ posT, int N, int mode,
       base = __shfl_sync(0xffffffffu, base, 31);
       int pos = base + incl - cnt;
 #pragma unroll
-      for (int k = 0; k < 4; ++k)
+      for (int k = 0; k < kSievePer; ++k)
         if ((cm >> k) & 1u) {
-          if (pos < kSieveCand) cand[pos] = (uint16_t)(4 * tid + k);
+          if (pos < kSieveCand) cand[pos] = (uint16_t)(kSievePer * tid + k);
           ++pos;
         }
     }
@@ -707,28 +714,21 @@ conflict_sieve_kernel(const int32_t* __restrict__ posT, int N, int mode,
       s = (s + 1) & kSlotMask;
     }
   }
-  if (kFirst) {
-    best = warpMin64Key(best);
-    if (lane == 0) sBest[tid >> 5] = best;
-  }
-  if (kCount) {
-    unsigned long long sum = pairs2;
-#pragma unroll
-    for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-    if (lane == 0) sSum[tid >> 5] = sum;
-  }
-  __syncthreads();
-  if (tid == 0) {
+  // only the warps that held candidates have anything to report; the doubled
+  // pair counts of a timestep meet in shared memory before they are halved
+  if ((tid & ~31) < nc) {
     if (kFirst) {
-      unsigned long long bb = kNoConflict;
-      for (int w = 0; w < kSieveThreads / 32; ++w) bb = min(bb, sBest[w]);
-      if (bb != kNoConflict) atomicMin(&result[0], bb);
+      best = warpMin64Key(best);
+      if (lane == 0 && best != kNoConflict) atomicMin(&result[0], best);
     }
     if (kCount) {
-      unsigned long long tot = 0;
-      for (int w = 0; w < kSieveThreads / 32; ++w) tot += sSum[w];
-      if (tot) atomicAdd(&result[1], tot / 2);
+      const unsigned int s2 = __reduce_add_sync(0xffffffffu, pairs2);
+      if (lane == 0 && s2) atomicAdd(&sPairs2, s2);
     }
+  }
+  if (kCount) {
+    __syncthreads();
+    if (tid == 0 && sPairs2) atomicAdd(&result[1], (unsigned long long)(sPairs2 / 2));
   }
 }
 
