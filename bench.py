@@ -460,12 +460,29 @@ def run_ours(args):
         e1.record(stream)
         torch.cuda.synchronize()
         cms = e0.elapsed_time(e1) / reps
+        # first conflict only (what a high-level expansion asks for, cbs.hpp:127):
+        # timesteps behind the earliest conflict found so far exit at once
+        d_res1 = torch.zeros(4, dtype=torch.int64, device=dev)
+
+        def fstep():
+            capi.check(lib.mrp_conflicts_dev(table.data_ptr(), length.data_ptr(), N, Tpad,
+                                             0, 1, 0, d_res1.data_ptr(), stream.cuda_stream))
+        fstep()
+        torch.cuda.synchronize()
+        e0.record(stream)
+        for _ in range(reps):
+            fstep()
+        e1.record(stream)
+        torch.cuda.synchronize()
+        fms = e0.elapsed_time(e1) / reps
+        assert int(d_res1[0].item()) == int(d_res[0].item()), "first-conflict key differs"
         max_t = int(length.max().item()) - 1
         pair_steps = N * (N - 1) // 2 * max_t
         res = d_res.cpu().numpy()
         also.update({
             "conflict_pair_steps_per_s": pair_steps / (cms * 1e-3),
-            "conflict_ms": cms, "conflict_agents": N, "conflict_max_t": max_t,
+            "conflict_ms": cms, "conflict_first_only_ms": fms,
+            "conflict_agents": N, "conflict_max_t": max_t,
             "conflict_count": int(res[1]),
             "conflict_first_key": int(np.uint64(res[0])) if res[0] != -1 else None,
             "conflict_table_gbps": N * Tpad * 4 / (cms * 1e-3) / 1e9,
