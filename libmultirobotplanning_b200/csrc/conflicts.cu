@@ -212,30 +212,45 @@ __global__ void conflict_transpose_kernel(const int32_t* __restrict__ cell,
                                           unsigned long long* __restrict__ result,
                                           int32_t* __restrict__ posT,
                                           unsigned char* __restrict__ todo) {
-  __shared__ int32_t tile[32][33];
+  // tile: 32 agents x 64 timesteps, 256 threads, eight elements per thread
+  // (all eight loads are issued before the first one is used)
+  __shared__ int32_t tile[32][65];
   __shared__ int smax[32];
-  const int t0 = blockIdx.y * 32, i0 = blockIdx.x * 32;
+  const int t0 = blockIdx.y * 64, i0 = blockIdx.x * 32;
   const int ld = rowStride(N);
+  {
+    int L[4], v[8];
 #pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    const int r = threadIdx.y + 8 * k;
-    const int i = i0 + r, t = t0 + threadIdx.x;
-    int v = -2 - i;  // agents without a path never match anything
-    if (i < N) {
-      const int L = len[i];
-      if (L > 0) v = cell[(size_t)i * Tpad + min(t, L - 1)];
+    for (int k = 0; k < 4; ++k) {
+      const int i = i0 + threadIdx.y + 8 * k;
+      L[k] = i < N ? len[i] : 0;
     }
-    tile[r][threadIdx.x] = v;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int i = i0 + threadIdx.y + 8 * k;
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int t = t0 + 32 * h + threadIdx.x;
+        // agents without a path never match anything
+        v[2 * k + h] = L[k] > 0 ? cell[(size_t)i * Tpad + min(t, L[k] - 1)] : -2 - i;
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      tile[threadIdx.y + 8 * k][threadIdx.x] = v[2 * k];
+      tile[threadIdx.y + 8 * k][threadIdx.x + 32] = v[2 * k + 1];
+    }
   }
   __syncthreads();
 #pragma unroll
-  for (int k = 0; k < 4; ++k) {
+  for (int k = 0; k < 8; ++k) {
     const int r = threadIdx.y + 8 * k;
     const int t = t0 + r, i = i0 + threadIdx.x;
     if (t <= Tpad && i < ld) posT[(size_t)t * ld + i] = tile[threadIdx.x][r];
   }
   // the hand-over flags of the sieve kernel start out clear
-  if (todo && blockIdx.x == 0 && threadIdx.y == 0 && t0 + threadIdx.x < Tpad) todo[t0 + threadIdx.x] = 0;
+  if (todo && blockIdx.x == 0 && threadIdx.y < 2 && t0 + 32 * threadIdx.y + threadIdx.x < Tpad)
+    todo[t0 + 32 * threadIdx.y + threadIdx.x] = 0;
   if (blockIdx.x == 0 && blockIdx.y == 0) {
     const int tid = threadIdx.y * 32 + threadIdx.x;
     int m = 0;
@@ -802,7 +817,7 @@ int launchConflicts(const int32_t* d_cell, const int32_t* d_len, int N, int Tpad
     return launchPairs(d_cell, d_len, 1, N, Tpad, mode, wantFirst, wantCount, d_result, st);
   // hashed path: prep (max len) -> transpose + clamp -> one CTA per timestep
   int32_t* posT = static_cast<int32_t*>(d_ws);
-  dim3 tg((rowStride(N) + 31) / 32, (Tpad + 1 + 31) / 32);
+  dim3 tg((rowStride(N) + 31) / 32, (Tpad + 1 + 63) / 64);
   // hand-over flags of the sieve kernel, cleared by the transposition
   unsigned char* todoAll = static_cast<unsigned char*>(d_ws) + (size_t)(Tpad + 1) * rowStride(N) * 4;
   conflict_transpose_kernel<<<tg, dim3(32, 8), 0, st>>>(d_cell, d_len, N, Tpad, d_result, posT, todoAll);
