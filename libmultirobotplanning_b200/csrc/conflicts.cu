@@ -466,21 +466,22 @@ __device__ __forceinline__ uint32_t hash32(uint32_t k) {
 }
 
 template <bool kFirst, bool kCount>
-__global__ void __launch_bounds__(kHash2Threads)
+__global__ void __launch_bounds__(kHash2Threads, 3)
 conflict_hash2_kernel(const int32_t* __restrict__ posT, int N, int mode, int H,
                       unsigned long long* __restrict__ result,
                       const unsigned char* __restrict__ todo) {
   extern __shared__ unsigned long long tab[];  // [H]
   __shared__ unsigned long long sBest[kHash2Threads / 32];
   __shared__ unsigned long long sSum[kHash2Threads / 32];
-  const int t = blockIdx.x;
   const int maxLen = (int)result[2];
   const int max_t = maxLen - (mode == 0 ? 1 : 0);
-  if (t >= max_t) return;
-  if (todo && !todo[t]) return;  // only the timesteps the sieve kernel handed over
+  // One CTA per timestep, or (behind the sieve kernel) a small grid whose CTAs
+  // stride over the timesteps and redo the ones that were handed over.
+  for (int t = blockIdx.x; t < max_t; t += gridDim.x) {
+  if (todo && !todo[t]) continue;
   if (kFirst && !kCount) {
     const unsigned long long b = *(volatile unsigned long long*)&result[0];
-    if (b != kNoConflict && (int)(b >> 41) < t) return;
+    if (b != kNoConflict && (int)(b >> 41) < t) continue;
   }
   const uint32_t mask = (uint32_t)H - 1u;
   const int32_t* rowA = posT + (size_t)t * rowStride(N);
@@ -563,6 +564,8 @@ conflict_hash2_kernel(const int32_t* __restrict__ posT, int N, int mode, int H,
       for (int w = 0; w < kHash2Threads / 32; ++w) tot += sSum[w];
       if (tot) atomicAdd(&result[1], tot / 2);
     }
+  }
+  __syncthreads();  // the table and the reduction slots are reused by the next timestep
   }
 }
 
@@ -841,7 +844,9 @@ int launchConflicts(const int32_t* d_cell, const int32_t* d_len, int N, int Tpad
     const size_t smem2 = (size_t)H * 8;
     auto run2 = [&](auto kern) {
       cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
-      kern<<<Tpad, kHash2Threads, smem2, st>>>(posT, N, mode, H, d_result, todo);
+      // behind the sieve kernel only a few timesteps (usually none) are left
+      const int grid = todo ? std::min(Tpad, 2 * 148) : Tpad;
+      kern<<<grid, kHash2Threads, smem2, st>>>(posT, N, mode, H, d_result, todo);
     };
     if (wantFirst && wantCount)
       run2(conflict_hash2_kernel<true, true>);
