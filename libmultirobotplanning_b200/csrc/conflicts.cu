@@ -17,6 +17,15 @@
 // The first conflict is the minimum of the packed key (t, type, i, j) — the
 // exact iteration order of the reference loops — reduced with a 64-bit
 // atomicMin; counts are reduced per CTA and added with one atomic.
+//
+// hashed kernels (256 < N <= 4096, O(N*T) instead of O(N^2*T)): the table is
+// transposed and clamped once, then one CTA per timestep; three generations
+// with identical answers, newest = default:
+//   conflict_hash_kernel   16-byte slots, three atomics per agent, two tables
+//   conflict_hash2_kernel  one table of (cell, agent) entries, one CAS per probe
+//   conflict_sieve_kernel  hashed occupancy bitmaps pick the few agents that
+//                          can be in a conflict; exact pass over those only
+#include <algorithm>
 #include <cstdlib>
 
 #include "common.cuh"
