@@ -220,12 +220,20 @@ __global__ void conflict_transpose_kernel(const int32_t* __restrict__ cell,
                                           const int32_t* __restrict__ len, int N, int Tpad,
                                           unsigned long long* __restrict__ result,
                                           int32_t* __restrict__ posT,
-                                          unsigned char* __restrict__ todo) {
+                                          unsigned char* __restrict__ todo, int tBase, int tEnd,
+                                          int firstOnly) {
   // tile: 32 agents x 64 timesteps, 256 threads, eight elements per thread
   // (all eight loads are issued before the first one is used)
   __shared__ int32_t tile[32][65];
   __shared__ int smax[32];
-  const int t0 = blockIdx.y * 64, i0 = blockIdx.x * 32;
+  // rows tBase .. tEnd of the transposed table (a first-conflict-only sweep
+  // goes through the table in windows of growing size: once a window has
+  // found a conflict, the blocks of the later ones have nothing to do)
+  if (firstOnly && tBase > 0) {
+    const unsigned long long b = *(volatile unsigned long long*)&result[0];
+    if (b != kNoConflict && (int)(b >> 41) < tBase) return;
+  }
+  const int t0 = tBase + blockIdx.y * 64, i0 = blockIdx.x * 32;
   const int ld = rowStride(N);
   {
     int L[4], v[8];
@@ -255,12 +263,12 @@ __global__ void conflict_transpose_kernel(const int32_t* __restrict__ cell,
   for (int k = 0; k < 8; ++k) {
     const int r = threadIdx.y + 8 * k;
     const int t = t0 + r, i = i0 + threadIdx.x;
-    if (t <= Tpad && i < ld) posT[(size_t)t * ld + i] = tile[threadIdx.x][r];
+    if (t <= tEnd && i < ld) posT[(size_t)t * ld + i] = tile[threadIdx.x][r];
   }
   // the hand-over flags of the sieve kernel start out clear
   if (todo && blockIdx.x == 0 && threadIdx.y < 2 && t0 + 32 * threadIdx.y + threadIdx.x < Tpad)
     todo[t0 + 32 * threadIdx.y + threadIdx.x] = 0;
-  if (blockIdx.x == 0 && blockIdx.y == 0) {
+  if (tBase == 0 && blockIdx.x == 0 && blockIdx.y == 0) {
     const int tid = threadIdx.y * 32 + threadIdx.x;
     int m = 0;
     for (int i = tid; i < N; i += 256) m = max(m, len[i]);
@@ -600,19 +608,21 @@ constexpr int kSievePer = MRP_SIEVE_PER;                // agents per thread (4 
 constexpr int kSieveThreads = kHashMaxN / kSievePer;    // 512 threads, four CTAs per SM (4 per thread: 0.068 ms, 8: 0.064 ms)
 constexpr int kSieveBits = 1 << 17;  // 3 % of the cells of a timestep collide at N = 4096
 constexpr int kSieveCand = 512;
+constexpr int kFirstWindow = 128;  // first-conflict-only sweeps: see launchConflicts
 constexpr int kSieveSlots = 1024;
 
 template <bool kFirst, bool kCount>
 __global__ void __launch_bounds__(kSieveThreads, 2048 / kSieveThreads)
 conflict_sieve_kernel(const int32_t* __restrict__ posT, int N, int mode,
-                      unsigned long long* __restrict__ result, unsigned char* __restrict__ todo) {
+                      unsigned long long* __restrict__ result, unsigned char* __restrict__ todo,
+                      int tBase) {
   __shared__ __align__(16) uint32_t occ[kSieveBits / 32];
   __shared__ __align__(16) uint32_t multi[kSieveBits / 32];
   __shared__ __align__(16) unsigned long long tab[kSieveSlots];
   __shared__ uint16_t cand[kSieveCand];
   __shared__ int sN;
   __shared__ unsigned int sPairs2;
-  const int t = blockIdx.x;
+  const int t = tBase + blockIdx.x;
   const int maxLen = (int)result[2];
   const int max_t = maxLen - (mode == 0 ? 1 : 0);
   if (t >= max_t) return;
@@ -829,25 +839,49 @@ int launchConflicts(const int32_t* d_cell, const int32_t* d_len, int N, int Tpad
     return launchPairs(d_cell, d_len, 1, N, Tpad, mode, wantFirst, wantCount, d_result, st);
   // hashed path: prep (max len) -> transpose + clamp -> one CTA per timestep
   int32_t* posT = static_cast<int32_t*>(d_ws);
-  dim3 tg((rowStride(N) + 31) / 32, (Tpad + 1 + 63) / 64);
   // hand-over flags of the sieve kernel, cleared by the transposition
   unsigned char* todoAll = static_cast<unsigned char*>(d_ws) + (size_t)(Tpad + 1) * rowStride(N) * 4;
-  conflict_transpose_kernel<<<tg, dim3(32, 8), 0, st>>>(d_cell, d_len, N, Tpad, d_result, posT, todoAll);
+  const bool hash1 = getenv("MRP_CONFLICTS_HASH1") != nullptr;
+  const bool sieve = !hash1 && !getenv("MRP_CONFLICTS_HASH2");
+  auto transpose = [&](int tBase, int tEnd, int firstOnly) {
+    dim3 tg((rowStride(N) + 31) / 32, (tEnd - tBase + 1 + 63) / 64);
+    conflict_transpose_kernel<<<tg, dim3(32, 8), 0, st>>>(d_cell, d_len, N, Tpad, d_result, posT,
+                                                            todoAll, tBase, tEnd, firstOnly);
+  };
   int H = 512;
   while (H < 2 * N) H <<= 1;
-  if (!getenv("MRP_CONFLICTS_HASH1")) {
+  if (!hash1) {
     // default: sieve kernel, then the single-table kernel on the timesteps it
     // handed over (MRP_CONFLICTS_HASH2: single-table kernel on every timestep)
-    const bool sieve = !getenv("MRP_CONFLICTS_HASH2");
     unsigned char* todo = nullptr;
     if (sieve) {
       todo = todoAll;
-      if (wantFirst && wantCount)
-        conflict_sieve_kernel<true, true><<<Tpad, kSieveThreads, 0, st>>>(posT, N, mode, d_result, todo);
-      else if (wantFirst)
-        conflict_sieve_kernel<true, false><<<Tpad, kSieveThreads, 0, st>>>(posT, N, mode, d_result, todo);
-      else
-        conflict_sieve_kernel<false, true><<<Tpad, kSieveThreads, 0, st>>>(posT, N, mode, d_result, todo);
+      auto sweep = [&](int tBase, int tEnd) {
+        const int grid = tEnd - tBase;
+        if (wantFirst && wantCount)
+          conflict_sieve_kernel<true, true><<<grid, kSieveThreads, 0, st>>>(posT, N, mode, d_result, todo, tBase);
+        else if (wantFirst)
+          conflict_sieve_kernel<true, false><<<grid, kSieveThreads, 0, st>>>(posT, N, mode, d_result, todo, tBase);
+        else
+          conflict_sieve_kernel<false, true><<<grid, kSieveThreads, 0, st>>>(posT, N, mode, d_result, todo, tBase);
+        countLaunch(2);
+      };
+      if (wantFirst && !wantCount) {
+        // first conflict only: the first kFirstWindow timesteps, then the rest
+        // (whose blocks exit at once if the first window found a conflict; more
+        // windows cost more in launches than they save: four windows took
+        // 0.055 ms on the C5 table against 0.045-0.050 ms for a single sweep)
+        for (int t0 = 0, w = kFirstWindow; t0 < Tpad; t0 += w, w = Tpad) {
+          const int t1 = std::min(Tpad, t0 + w);
+          transpose(t0, t1, 1);
+          sweep(t0, t1);
+        }
+      } else {
+        transpose(0, Tpad, 0);
+        sweep(0, Tpad);
+      }
+    } else {
+      transpose(0, Tpad, 0);
       countLaunch();
     }
     const size_t smem2 = (size_t)H * 8;
@@ -863,10 +897,11 @@ int launchConflicts(const int32_t* d_cell, const int32_t* d_len, int N, int Tpad
       run2(conflict_hash2_kernel<true, false>);
     else
       run2(conflict_hash2_kernel<false, true>);
-    countLaunch(2);
+    countLaunch();
     MRP_CUDA(cudaGetLastError());
     return 0;
   }
+  transpose(0, Tpad, 0);
   const size_t smem = (size_t)H * 16;
   auto run = [&](auto kern) {
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

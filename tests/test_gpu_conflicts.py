@@ -179,6 +179,40 @@ def test_sieve_sparse_and_dense_timesteps(capi, orc, monkeypatch):
     assert capi.count_conflicts(cell, ln, 0) == orc.count_conflicts(cell, ln, 0)
 
 
+def test_first_conflict_windows(capi, orc):
+    """A first-conflict-only call sweeps the first 128 timesteps, then the rest:
+    conflicts on both sides of the window boundary (and of other multiples of
+    64), in the last step, none at all, and stale hand-over flags from a dense
+    table swept just before."""
+    N, T, cells = 600, 1500, 1 << 20
+    base = np.zeros((N, T), np.int32)
+    tt = np.arange(T)
+    for i in range(N):
+        base[i] = 1000 + 8 * i + (tt + i) % 2      # everybody shuttles between two private cells
+    ln = np.full(N, T, np.int32)
+    rng = np.random.default_rng(5)
+    dense = rng.integers(0, 300, (N, T)).astype(np.int32)   # every timestep is handed over
+    assert capi.first_conflict(base, ln, 1024, 0) is None
+    assert capi.count_conflicts(base, ln, 0) == 0
+    for k, tc in enumerate([0, 63, 64, 126, 127, 128, 129, 320, 1344, T - 2]):
+        cell = base.copy()
+        i, j = 17 + k, 400 + 3 * k
+        if k % 2 == 0:      # vertex conflict at tc
+            cell[j, tc] = cell[i, tc]
+        else:               # swap between tc and tc + 1
+            cell[j, tc], cell[j, tc + 1] = cell[i, tc + 1], cell[i, tc]
+        if k == 4:
+            capi.count_conflicts(dense, ln, 0)
+            assert capi.first_conflict(dense, ln, 1024, 0) == orc.first_conflict(dense, ln, 1024, 0)
+        want = orc.first_conflict(cell, ln, 1024, 0)
+        assert want is not None and want[0] == tc
+        assert capi.first_conflict(cell, ln, 1024, 0) == want, tc
+        # a later conflict does not change the answer
+        cell[5, min(tc + 70, T - 1)] = cell[6, min(tc + 70, T - 1)]
+        assert capi.first_conflict(cell, ln, 1024, 0) == want, tc
+    assert capi.first_conflict(base, ln, 1024, 1) is None
+
+
 def test_hashed_path_stress_high_load(capi, orc):
     """The hashed tables run at a load factor of ~0.5 when N approaches 4096;
     an early version lost table updates there (fire-and-forget shared-memory
