@@ -494,6 +494,7 @@ conflict_hash2_kernel(const int32_t* __restrict__ posT, int N, int mode, int H,
   const int max_t = maxLen - (mode == 0 ? 1 : 0);
   // One CTA per timestep, or (behind the sieve kernel) a small grid whose CTAs
   // stride over the timesteps and redo the ones that were handed over.
+  if (todo && *(volatile unsigned long long*)&result[3] == 0ull) return;  // nothing was handed over
   for (int t = blockIdx.x; t < max_t; t += gridDim.x) {
   if (todo && !todo[t]) continue;
   if (kFirst && !kCount) {
@@ -711,7 +712,10 @@ conflict_sieve_kernel(const int32_t* __restrict__ posT, int N, int mode,
   __syncthreads();
   const int nc = sN;
   if (nc > kSieveCand) {
-    if (tid == 0) todo[t] = 1;
+    if (tid == 0) {
+      todo[t] = 1;
+      atomicAdd(&result[3], 1ull);  // number of timesteps handed over (0: the next kernel exits at once)
+    }
     return;
   }
   unsigned long long best = kNoConflict;
