@@ -412,6 +412,7 @@ static size_t tilesWorkspaceBytes(const mrp_map_s* map) {
 size_t bfsLargeWorkspaceBytes(const mrp_map_s* map, int n_goals) {
   size_t bytes = tilesWorkspaceBytes(map);
   if (bfsQueueFits(map)) bytes += bfsQueueWorkspaceWords(n_goals) * 4;
+  if (bfsSweepFits(map)) bytes += bfsSweepWorkspaceWords(n_goals) * 4;
   return bytes;
 }
 
@@ -419,18 +420,28 @@ static int launchBfsTiles(const mrp_map_s* map, const int32_t* d_goal_cell, int 
                           int32_t* d_out, void* d_ws, const uint32_t* d_goalList,
                           const uint32_t* d_goalListCount, cudaStream_t st);
 
-// Maps whose bitmap fits shared memory run the queue kernel; the goals it
-// hands over (a level larger than its queues) and all larger maps run the
-// tiled kernel.
+// Maps of up to 1024 columns run the detour-level sweep (bfs_sweep.cu); the
+// goals it hands over (more detour levels than it holds: mazes) run the queue
+// kernel if the bitmap fits shared memory; the goals that one hands over (a
+// level larger than its queues) and all larger maps run the tiled kernel.
 int launchBfsLarge(const mrp_map_s* map, const int32_t* d_goal_cell, int n_goals,
                    int32_t* d_out, void* d_ws, cudaStream_t st) {
   if (n_goals <= 0) return 0;
-  if (!bfsQueueFits(map))
-    return launchBfsTiles(map, d_goal_cell, n_goals, d_out, d_ws, nullptr, nullptr, st);
-  if (int rc = launchBfsQueue(map, d_goal_cell, n_goals, d_out, d_ws, st)) return rc;
-  uint32_t* qws = static_cast<uint32_t*>(d_ws);
-  return launchBfsTiles(map, d_goal_cell, n_goals, d_out, qws + bfsQueueWorkspaceWords(n_goals),
-                        qws + 64, qws + 2, st);
+  uint32_t* ws = static_cast<uint32_t*>(d_ws);
+  const uint32_t *list = nullptr, *listCount = nullptr;
+  if (bfsSweepFits(map)) {
+    if (int rc = launchBfsSweep(map, d_goal_cell, n_goals, d_out, ws, st)) return rc;
+    list = ws + 64;
+    listCount = ws + 2;
+    ws += bfsSweepWorkspaceWords(n_goals);
+  }
+  if (bfsQueueFits(map)) {
+    if (int rc = launchBfsQueue(map, d_goal_cell, n_goals, d_out, ws, st, list, listCount)) return rc;
+    list = ws + 64;
+    listCount = ws + 2;
+    ws += bfsQueueWorkspaceWords(n_goals);
+  }
+  return launchBfsTiles(map, d_goal_cell, n_goals, d_out, ws, list, listCount, st);
 }
 
 static int launchBfsTiles(const mrp_map_s* map, const int32_t* d_goal_cell, int n_goals,

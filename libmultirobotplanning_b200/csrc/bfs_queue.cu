@@ -47,6 +47,10 @@ struct BfsQueueParams {
   const int32_t* __restrict__ goals;     // goal cells
   int32_t* __restrict__ out;             // [n_goals][cells]
   uint32_t* ws;  // [0] goal counter, [2] number of overflowed goals, [64..] their indices
+  // goals handed over by the sweep kernel (bfs_sweep.cu): indices into goals[] /
+  // out[]; NULL = all n_goals goals
+  const uint32_t* goalList;
+  const uint32_t* goalListCount;
   int n_goals;
   int dimx, dimy;
   int WPR;       // words per bitmap row (odd)
@@ -232,8 +236,9 @@ __global__ void __launch_bounds__(1024, 1) bfs_queue_kernel(BfsQueueParams p) {
     __syncthreads();
     if (tid == 0) sGoal = (int)atomicAdd(p.ws, 1u);
     __syncthreads();
-    const int gidx = sGoal;
-    if (gidx >= p.n_goals) break;
+    const int nWork = p.goalList ? (int)*p.goalListCount : p.n_goals;
+    if (sGoal >= nWork) break;
+    const int gidx = p.goalList ? (int)p.goalList[sGoal] : sGoal;
 #ifdef MRP_BFS_TIMING
     if (blockIdx.x == 0 && tid == 0) g_bfsqLevels[0][0] = (unsigned)clock64();
 #endif
@@ -457,7 +462,8 @@ size_t bfsQueueWorkspaceWords(int n_goals) {
 }
 
 int launchBfsQueue(const mrp_map_s* map, const int32_t* d_goal_cell, int n_goals,
-                   int32_t* d_out, void* d_ws, cudaStream_t st) {
+                   int32_t* d_out, void* d_ws, cudaStream_t st, const uint32_t* d_goalList,
+                   const uint32_t* d_goalListCount) {
   const QueueGeom q = queueGeometry(map);
   BfsQueueParams p;
   p.rowbits = map->d_rowbits;
@@ -465,6 +471,8 @@ int launchBfsQueue(const mrp_map_s* map, const int32_t* d_goal_cell, int n_goals
   p.out = d_out;
   p.ws = static_cast<uint32_t*>(d_ws);
   p.n_goals = n_goals;
+  p.goalList = d_goalList;
+  p.goalListCount = d_goalListCount;
   p.dimx = map->dimx;
   p.dimy = map->dimy;
   p.WPR = q.WPR;

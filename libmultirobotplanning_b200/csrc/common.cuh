@@ -134,6 +134,12 @@ int launchBfsLarge(const mrp_map_s* map, const int32_t* d_goal_cell,
 bool bfsQueueFits(const mrp_map_s* map);
 size_t bfsQueueWorkspaceWords(int n_goals);
 int launchBfsQueue(const mrp_map_s* map, const int32_t* d_goal_cell,
+                   int n_goals, int32_t* d_out, void* d_ws, cudaStream_t st,
+                   const uint32_t* d_goalList = nullptr,
+                   const uint32_t* d_goalListCount = nullptr);
+bool bfsSweepFits(const mrp_map_s* map);
+size_t bfsSweepWorkspaceWords(int n_goals);
+int launchBfsSweep(const mrp_map_s* map, const int32_t* d_goal_cell,
                    int n_goals, int32_t* d_out, void* d_ws, cudaStream_t st);
 size_t conflictsWorkspaceBytes(int N, int Tpad);
 int launchConflicts(const int32_t* d_cell, const int32_t* d_len, int N,
