@@ -48,15 +48,19 @@
 namespace mrp {
 
 constexpr int kSwLmax = 96;    // detour levels per goal (C5: max 83 over 512 goals)
-constexpr int kSwDense = 8;    // levels with a warp of their own per half
+constexpr int kSwDense = 4;    // levels swept row by row, one warp per (level, half)
 constexpr int kSwRO = 200;     // rows of the open ring per half (>= 2*kSwLmax - 1)
-constexpr int kSwRP = 20;      // rows of the plane ring per half (>= 2*kSwDense + 1)
-constexpr int kSwPlanes = 3;   // bits of a dense level
+constexpr int kSwRP = 12;      // rows of the plane ring per half (>= 2*kSwDense + 1)
+constexpr int kSwPlanes = 2;   // bits of a dense level
 constexpr int kSwThreads = 1024;
 constexpr int kSwWarps = kSwThreads / 32;
-constexpr int kSwSparseWarps = kSwWarps - 2 * kSwDense - 2;
-static_assert((1 << kSwPlanes) >= kSwDense, "planes");
+constexpr int kSwWriterWarps = 4;  // (half, part of the row)
+constexpr int kSwSparseWarps = kSwWarps - 2 * kSwDense - kSwWriterWarps;
+constexpr int kSwSparseLevels = kSwLmax - kSwDense;
+constexpr int kSwListCap = 2048;   // word items per step
+static_assert((1 << kSwPlanes) >= kSwDense && kSwPlanes <= 3, "planes");
 static_assert(kSwRO >= 2 * kSwLmax - 1 && kSwRP >= 2 * kSwDense + 1, "rings");
+static_assert(kSwSparseLevels <= 128, "item encoding");
 
 struct BfsSweepParams {
   const uint32_t* __restrict__ rowbits;  // bordered free mask (see mrp_map_s)
@@ -97,10 +101,10 @@ __device__ __forceinline__ uint32_t resolveCarries(uint32_t g, uint32_t p) {
   return (((m2 + t) ^ m2) & m2) | t;
 }
 
-// One (level, row) step.  sp = S_{k-1}[row], spu = the inward vertical sources
-// (S_{k-1} of the next row out), npv = S_k of the previous row (outward
-// vertical), op = open cells of the row.  mR / mL: cells right / left of the
-// goal column, cb: the goal column.
+// One (level, row) step of a dense level, a row = the 32 lanes of the warp.
+// sp = S_{k-1}[row], spu = the inward vertical sources (S_{k-1} of the next row
+// out), npv = S_k of the previous row (outward vertical), op = open cells of
+// the row.  mR / mL: cells right / left of the goal column, cb: the goal column.
 __device__ __forceinline__ uint32_t sweepRowStep(uint32_t sp, uint32_t spu, uint32_t npv, uint32_t op,
                                                  uint32_t mR, uint32_t mL, uint32_t cb, int lane) {
   const uint32_t spR = sp & mR, spL = sp & mL;
@@ -109,7 +113,6 @@ __device__ __forceinline__ uint32_t sweepRowStep(uint32_t sp, uint32_t spu, uint
   if (lane == 31) hi = 0u;
   if (lane == 0) lo = 0u;
   const uint32_t seed = (__funnelshift_r(spR, hi, 1) | __funnelshift_l(lo, spL, 1) | spu | npv) & op;
-  if (__ballot_sync(kFull, seed != 0u) == 0u) return 0u;
   const uint32_t sc = seed & cb;
   const uint32_t mU = (op & mR) | sc, sU = seed & (mR | cb);
   const uint32_t mD = __brev((op & mL) | sc), sD = __brev(seed & (mL | cb));
@@ -117,46 +120,183 @@ __device__ __forceinline__ uint32_t sweepRowStep(uint32_t sp, uint32_t spu, uint
   addCarry(mU, sU, sumU, cU);
   addCarry(mD, sD, sumD, cD);
   const uint32_t gU = __ballot_sync(kFull, cU != 0u), gD = __ballot_sync(kFull, cD != 0u);
-  if (gU | gD) {
-    const uint32_t qU = __ballot_sync(kFull, sumU == kFull), qD = __ballot_sync(kFull, sumD == kFull);
-    const uint32_t u = resolveCarries(gU, qU), d = resolveCarries(__brev(gD), __brev(qD));
-    sumU += (u >> lane) & 1u;
-    sumD += (d >> (31 - lane)) & 1u;
-  }
+  const uint32_t qU = __ballot_sync(kFull, sumU == kFull), qD = __ballot_sync(kFull, sumD == kFull);
+  const uint32_t u = resolveCarries(gU, qU), d = resolveCarries(__brev(gD), __brev(qD));
+  sumU += (u >> lane) & 1u;
+  sumD += (d >> (31 - lane)) & 1u;
   return (((sumU ^ mU) & mU) | sU) | __brev(((sumD ^ mD) & mD) | sD);
 }
 
+// ---- sparse levels: word items ------------------------------------------------
+// A sparse level is not swept: the cells a step reaches in one word of a row
+// post their consequences as seed bits for the words they can reach next
+//   outward vertical   -> same level, next row out, same word      (step + 1)
+//   inward vertical    -> next level, next row in, same word       (step + 1)
+//   inward horizontal  -> next level, same row, shifted one cell   (step + 2)
+// into an accumulator word per (level, half, word) and step; whoever finds the
+// accumulator empty also appends the word to the item list of that step.  A
+// thread per item takes the seeds (exchange with 0), floods them through the
+// open cells of its word (the addition trick inside one word; a carry makes the
+// thread go on with the next word), claims the cells with an atomic AND on the
+// open ring (exactly one winner per cell), stores their distances and posts
+// their consequences.  Idle levels cost nothing.
+struct SweepShared {
+  uint32_t* ring;    // [2][kSwRO][32] open cells of the rows in flight
+  uint32_t* acc;     // [kSwSparseLevels][2][3][32] seeds per step % 3
+  uint16_t* list;    // [4][kSwListCap] items of step % 4: (level - kSwDense) << 6 | half << 5 | word
+  uint32_t* cnt;     // [4]
+  int* handOver;
+};
+
 struct SweepGoal {
-  int gx, gy, dimx, dimy;
-  uint32_t mR, mL, cb;
+  int gx, gy, jg, dimx, dimy;
+  uint32_t hiG, loG, cbG;  // masks of the goal word: right of / left of / the goal column
   int32_t* out;
 };
 
-// stores the cells of `nw` (row y, offset r, level k) one word at a time, lane = cell
-__device__ __forceinline__ void sweepStoreCells(const SweepGoal& g, uint32_t nzb, uint32_t nw, int y, int r, int k,
-                                                int lane) {
-  int32_t* row = g.out + (size_t)y * g.dimx;
-  while (nzb) {
-    const int j = __ffs(nzb) - 1;
-    nzb &= nzb - 1u;
-    const uint32_t w = __shfl_sync(kFull, nw, j);
-    if ((w >> lane) & 1u) {
-      const int x = 32 * j + lane;
-      row[x] = abs(x - g.gx) + r + 2 * k;
+// One seed word for (level k, half h, word j) at `step`.  The accumulator update
+// is issued at once; whether this was the first seed of the word (and the word
+// therefore needs an item) is told by the returned old value.
+struct SweepPost {
+  uint32_t old;   // accumulator before the update (valid if code != 0xffff)
+  uint32_t code;  // item code, 0xffff = nothing posted
+};
+__device__ __forceinline__ SweepPost sweepPost(const SweepShared& sh, int step3, int k, int h, int j, uint32_t bits,
+                                               bool cond) {
+  SweepPost r;
+  r.old = 1u;
+  r.code = 0xffffu;
+  if (cond && bits != 0u) {
+    if (k >= kSwLmax) {
+      *sh.handOver = 1;
+    } else {
+      const int kk = k - kSwDense;
+      r.old = atomicOr(&sh.acc[((kk * 2 + h) * 3 + step3) * 32 + j], bits);
+      r.code = (uint32_t)((kk << 6) | (h << 5) | j);
     }
+  }
+  return r;
+}
+// appends the words of `a`, `b`, `c` that had no seed before to the item list
+__device__ __forceinline__ void sweepAppend(const SweepShared& sh, int step, const SweepPost& a, const SweepPost& b,
+                                            const SweepPost& c) {
+  const uint32_t fa = a.old == 0u, fb = b.old == 0u, fc = c.old == 0u;
+  const uint32_t n = fa + fb + fc;
+  if (n) {
+    uint32_t pos = atomicAdd(&sh.cnt[step & 3], n);
+    if (pos + n > (uint32_t)kSwListCap) {
+      *sh.handOver = 1;
+      return;
+    }
+    uint16_t* l = sh.list + (step & 3) * kSwListCap;
+    if (fa) l[pos++] = (uint16_t)a.code;
+    if (fb) l[pos++] = (uint16_t)b.code;
+    if (fc) l[pos] = (uint16_t)c.code;
+  }
+}
+
+// consequences of the cells `won` reached in word j of row (h, r) at level k during step tau
+__device__ __forceinline__ void sweepPostAll(const SweepShared& sh, const SweepGoal& g, int tau, int k, int h, int r,
+                                             int j, uint32_t won, uint32_t mR, uint32_t mL, bool outward) {
+  const int s1 = (tau + 1) % 3, s2 = (tau + 2) % 3;
+  // step + 1: outward vertical (same level, next row out; the goal row feeds both halves), inward vertical
+  const int yOut = h ? g.gy - (r + 1) : g.gy + (r + 1);
+  const SweepPost o0 = sweepPost(sh, s1, k, r == 0 ? 0 : h, j, won,
+                                 outward && (r == 0 ? g.gy + 1 < g.dimy : (yOut >= 0 && yOut < g.dimy)));
+  const SweepPost o1 = sweepPost(sh, s1, k, 1, j, won, outward && r == 0 && g.gy >= 1);
+  const SweepPost iv = sweepPost(sh, s1, k + 1, r == 1 ? 0 : h, j, won, r >= 1);
+  // step + 2: inward horizontal (next level, same row, one cell towards the goal column)
+  const uint32_t wR = won & mR, wL = won & mL;
+  const SweepPost h0 = sweepPost(sh, s2, k + 1, h, j, (wR >> 1) | (wL << 1), true);
+  const SweepPost h1 = sweepPost(sh, s2, k + 1, h, j - 1, 0x80000000u, (wR & 1u) != 0u);  // j > jg >= 0 here
+  const SweepPost h2 = sweepPost(sh, s2, k + 1, h, j + 1, 1u, (wL >> 31) != 0u);          // j < jg <= 31 here
+  sweepAppend(sh, tau + 1, o0, o1, iv);
+  sweepAppend(sh, tau + 2, h0, h1, h2);
+}
+
+__device__ __forceinline__ void sweepItem(const SweepShared& sh, const SweepGoal& g, int tau, uint32_t item) {
+  const int kk = item >> 6, h = (item >> 5) & 1, k = kk + kSwDense;
+  int j = item & 31;
+  const int r = tau - 2 * k;
+  const int y = h ? g.gy - r : g.gy + r;
+  uint32_t* const ringRow = sh.ring + (h * kSwRO + r % kSwRO) * 32;
+  uint32_t* const accRow = sh.acc + ((kk * 2 + h) * 3 + tau % 3) * 32;
+  int32_t* const row = g.out + (size_t)y * g.dimx;
+  const int base = r + 2 * k;
+  const int j0 = j;
+  uint32_t extra = 0u, leftCarry0 = 0u;
+  int phase = 0;  // 0: the item's own word, 1: following a carry to the right, 2: to the left
+  while (true) {
+    const uint32_t seed = atomicExch(&accRow[j], 0u) | extra;
+    const uint32_t op = ringRow[j];
+    const uint32_t s = seed & op;
+    uint32_t cU = 0u, cD = 0u;
+    if (s) {
+      const uint32_t mR = j > g.jg ? kFull : (j == g.jg ? g.hiG : 0u);
+      const uint32_t mL = j < g.jg ? kFull : (j == g.jg ? g.loG : 0u);
+      const uint32_t cb = j == g.jg ? g.cbG : 0u;
+      const uint32_t sc = s & cb;
+      const uint32_t mU = (op & mR) | sc, sU = s & (mR | cb);
+      const uint32_t mD = __brev((op & mL) | sc), sD = __brev(s & (mL | cb));
+      uint32_t sumU, sumD;
+      addCarry(mU, sU, sumU, cU);
+      addCarry(mD, sD, sumD, cD);
+      const uint32_t cand = (((sumU ^ mU) & mU) | sU) | __brev(((sumD ^ mD) & mD) | sD);
+      const uint32_t won = atomicAnd(&ringRow[j], ~cand) & cand;
+      if (won) {
+        uint32_t w = won;
+        while (w) {
+          const int b = __ffs(w) - 1;
+          w &= w - 1u;
+          const int x = 32 * j + b;
+          row[x] = abs(x - g.gx) + base;
+        }
+        sweepPostAll(sh, g, tau, k, h, r, j, won, mR, mL, true);
+      }
+    }
+    // a flood that reached the end of the word goes on in the next one: first
+    // to the right, then (only the goal word can do both) to the left
+    if (phase == 0) {
+      leftCarry0 = cD;
+      phase = 1;
+    }
+    if (phase == 1) {
+      if (cU && j < 31) {
+        ++j;
+        extra = 1u;
+        continue;
+      }
+      phase = 2;
+      j = j0;
+      cD = leftCarry0;
+    }
+    if (cD && j > 0) {
+      --j;
+      extra = 0x80000000u;
+      continue;
+    }
+    break;
   }
 }
 
 template <bool kVec>
 __global__ void __launch_bounds__(kSwThreads, 1) bfs_sweep_kernel(BfsSweepParams p) {
   extern __shared__ uint32_t smem[];
-  uint32_t* const S = smem;                                    // [kSwLmax][2][3][32]
-  uint32_t* const ring = S + kSwLmax * 2 * 3 * 32;             // [2][kSwRO][32]
-  uint32_t* const planes = ring + 2 * kSwRO * 32;              // [2][kSwRP][kSwPlanes][32]
-  uint32_t* const nz = planes + 2 * kSwRP * kSwPlanes * 32;    // [kSwLmax][2][4]
+  uint32_t* const Sd = smem;                                    // [kSwDense][2][3][32]
+  uint32_t* const ring = Sd + kSwDense * 2 * 3 * 32;            // [2][kSwRO][32]
+  uint32_t* const planes = ring + 2 * kSwRO * 32;               // [2][kSwRP][kSwPlanes][32]
+  uint32_t* const acc = planes + 2 * kSwRP * kSwPlanes * 32;    // [kSwSparseLevels][2][3][32]
+  uint32_t* const cnt = acc + kSwSparseLevels * 2 * 3 * 32;     // [4] (+ padding to 8)
+  uint16_t* const list = reinterpret_cast<uint16_t*>(cnt + 8);  // [4][kSwListCap]
   __shared__ int sGoal, sHandOver;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int dimx = p.dimx, dimy = p.dimy;
+  SweepShared sh;
+  sh.ring = ring;
+  sh.acc = acc;
+  sh.list = list;
+  sh.cnt = cnt;
+  sh.handOver = &sHandOver;
 
   while (true) {
     __syncthreads();
@@ -164,9 +304,9 @@ __global__ void __launch_bounds__(kSwThreads, 1) bfs_sweep_kernel(BfsSweepParams
       sGoal = (int)atomicAdd(p.ws, 1u);
       sHandOver = 0;
     }
-    for (int i = tid; i < kSwLmax * 2 * 3 * 32; i += kSwThreads) S[i] = 0u;
-    for (int i = tid; i < 2 * kSwRP * kSwPlanes * 32; i += kSwThreads) planes[i] = 0u;
-    for (int i = tid; i < kSwLmax * 2 * 4; i += kSwThreads) nz[i] = 0u;
+    for (int i = tid; i < kSwDense * 2 * 3 * 32; i += kSwThreads) Sd[i] = 0u;
+    for (int i = tid; i < kSwSparseLevels * 2 * 3 * 32; i += kSwThreads) acc[i] = 0u;
+    if (tid < 8) cnt[tid] = 0u;
     __syncthreads();
     const int gidx = sGoal;
     if (gidx >= p.n_goals) break;
@@ -176,24 +316,28 @@ __global__ void __launch_bounds__(kSwThreads, 1) bfs_sweep_kernel(BfsSweepParams
     g.dimy = dimy;
     g.gy = goal / dimx;
     g.gx = goal - g.gy * dimx;
+    g.jg = g.gx >> 5;
     g.out = p.out + (size_t)gidx * dimx * dimy;
-    const int gx = g.gx, gy = g.gy;
-    const int jg = gx >> 5, bg = gx & 31;
-    g.mR = lane > jg ? kFull : (lane == jg ? (bg == 31 ? 0u : kFull << (bg + 1)) : 0u);
-    g.mL = lane < jg ? kFull : (lane == jg ? (1u << bg) - 1u : 0u);
-    g.cb = lane == jg ? 1u << bg : 0u;
+    const int gx = g.gx, gy = g.gy, jg = g.jg, bg = gx & 31;
+    g.hiG = bg == 31 ? 0u : kFull << (bg + 1);
+    g.loG = (1u << bg) - 1u;
+    g.cbG = 1u << bg;
+    const uint32_t mR = lane > jg ? kFull : (lane == jg ? g.hiG : 0u);
+    const uint32_t mL = lane < jg ? kFull : (lane == jg ? g.loG : 0u);
+    const uint32_t cb = lane == jg ? g.cbG : 0u;
     const int maxr = max(gy, dimy - 1 - gy);
-    const int writerEnd = maxr + 2 * kSwDense;  // the writer puts out row maxr at step writerEnd - 1
+    const int writerEnd = maxr + 2 * kSwDense;  // the writers put out row maxr at step writerEnd - 1
     const bool goalFree = (sweepFreeWord(p.rowbits, p.WPR, dimy, gy, jg) >> bg) & 1u;
 
     // ---- roles ----
     const bool isDense = warp < 2 * kSwDense;
-    const bool isWriter = !isDense && warp < 2 * kSwDense + 2;
-    const int dk = warp >> 1, dh = warp & 1;          // dense: level, half
-    const int wh = warp - 2 * kSwDense;                // writer: half
-    const int sw = warp - 2 * kSwDense - 2;            // sparse warp index
-    uint32_t pf = 0u;                                  // prefetched free word (level 0, writer)
-    if (isDense && dk == 0) pf = dh == 0 ? sweepFreeWord(p.rowbits, p.WPR, dimy, gy, lane) : 0u;
+    const bool isWriter = !isDense && warp < 2 * kSwDense + kSwWriterWarps;
+    const int dk = warp >> 1, dh = warp & 1;                       // dense: level, half
+    const int wh = (warp - 2 * kSwDense) & 1, wp = (warp - 2 * kSwDense) >> 1;  // writer: half, part
+    const int st = tid - (2 * kSwDense + kSwWriterWarps) * 32;     // sparse thread index
+    uint32_t pf = 0u;      // prefetched free word (level 0, writers)
+    uint32_t prevNw = 0u;  // dense: this level's cells of the previous row
+    if (isDense && dk == 0 && dh == 0) pf = sweepFreeWord(p.rowbits, p.WPR, dimy, gy, lane);
 
     int idle = 0;
 #ifdef MRP_SWEEP_TIMING
@@ -210,45 +354,43 @@ __global__ void __launch_bounds__(kSwThreads, 1) bfs_sweep_kernel(BfsSweepParams
         const int k = dk, h = dh, r = tau - 2 * k;
         if (r >= 0 && !(h == 1 && r == 0)) {
           const int y = h ? gy - r : gy + r;
+          const bool inRange = y >= 0 && y < dimy;
           const int slot = r % 3;
-          uint32_t* const Sk = S + (k * 2 + h) * 3 * 32;
-          if (y >= 0 && y < dimy) {
-            uint32_t op, sp = 0u, spu = 0u, npv = 0u;
-            uint32_t* const ringRow = ring + (h * kSwRO + r % kSwRO) * 32;
-            if (k == 0) {
-              op = pf;
-              if (r == 0) npv = g.cb;
+          uint32_t* const Sk = Sd + (k * 2 + h) * 3 * 32;
+          uint32_t* const ringRow = ring + (h * kSwRO + r % kSwRO) * 32;
+          uint32_t op, sp = 0u, spu = 0u, npv = prevNw;
+          if (k == 0) {
+            op = pf;
+            if (r == 0) npv = cb;
+          } else {
+            op = inRange ? ringRow[lane] : 0u;
+            const uint32_t* Sp = Sd + ((k - 1) * 2 + h) * 3 * 32;
+            if (r == 0) {
+              sp = Sp[lane];
+              spu = Sp[32 + lane] | Sp[3 * 32 + 32 + lane];  // row 1 of both halves
             } else {
-              op = ringRow[lane];
-              const uint32_t* Sp = S + ((k - 1) * 2 + h) * 3 * 32;
-              if (r == 0) {
-                sp = Sp[lane];
-                spu = Sp[32 + lane] | Sp[3 * 32 + 32 + lane];  // row 1 of both halves
-              } else {
-                sp = Sp[slot * 32 + lane];
-                spu = Sp[((r + 1) % 3) * 32 + lane];
-              }
+              sp = Sp[slot * 32 + lane];
+              spu = Sp[((r + 1) % 3) * 32 + lane];
             }
-            if (r == 1)
-              npv = S[(k * 2) * 3 * 32 + lane];  // the goal row of this level (half 0, slot 0)
-            else if (r > 1)
-              npv = Sk[((r - 1) % 3) * 32 + lane];
-            const uint32_t nw = sweepRowStep(sp, spu, npv, op, g.mR, g.mL, g.cb, lane);
-            Sk[slot * 32 + lane] = nw;
+          }
+          if (r == 1 && h == 1) npv = Sd[(k * 2) * 3 * 32 + lane];  // the goal row of this level (half 0, slot 0)
+          const uint32_t nw = sweepRowStep(sp, spu, npv, op, mR, mL, cb, lane);
+          prevNw = nw;
+          Sk[slot * 32 + lane] = nw;
+          if (inRange) {
             if (k == 0 || nw) ringRow[lane] = op & ~nw;
-            const uint32_t nzb = __ballot_sync(kFull, nw != 0u);
-            if (lane == 0) nz[(k * 2 + h) * 4 + slot] = nzb;
-            if (nw) {
-              uint32_t* pl = planes + ((h * kSwRP + r % kSwRP) * kSwPlanes) * 32 + lane;
+            uint32_t* pl = planes + ((h * kSwRP + r % kSwRP) * kSwPlanes) * 32 + lane;
+            if (k == 0) {
+#pragma unroll
+              for (int b = 0; b < kSwPlanes; ++b) pl[b * 32] = 0u;
+            } else if (nw) {
 #pragma unroll
               for (int b = 0; b < kSwPlanes; ++b)
                 if ((k >> b) & 1) pl[b * 32] |= nw;
             }
-            act = nzb != 0u;
-          } else {
-            Sk[slot * 32 + lane] = 0u;
-            if (lane == 0) nz[(k * 2 + h) * 4 + slot] = 0u;
+            if (k == kSwDense - 1 && nw && !(p.dbg & 1)) sweepPostAll(sh, g, tau, k, h, r, lane, nw, mR, mL, false);
           }
+          act = nw != 0u;
         }
         // free word of the next row of this half (level 0 only)
         if (k == 0) pf = sweepFreeWord(p.rowbits, p.WPR, dimy, h ? gy - (r + 1) : gy + (r + 1), lane);
@@ -258,11 +400,8 @@ __global__ void __launch_bounds__(kSwThreads, 1) bfs_sweep_kernel(BfsSweepParams
         if (r >= 0 && !(h == 1 && r == 0) && y >= 0 && y < dimy) {
           const uint32_t fr = pf;
           const uint32_t op = ring[(h * kSwRO + r % kSwRO) * 32 + lane];
-          uint32_t* pl = planes + ((h * kSwRP + r % kSwRP) * kSwPlanes) * 32 + lane;
-          uint32_t n0 = pl[0], n1 = pl[32], n2 = pl[64], n3 = fr & ~op;
-          pl[0] = 0u;
-          pl[32] = 0u;
-          pl[64] = 0u;
+          const uint32_t* pl = planes + ((h * kSwRP + r % kSwRP) * kSwPlanes) * 32 + lane;
+          uint32_t n0 = pl[0], n1 = kSwPlanes > 1 ? pl[32] : 0u, n2 = kSwPlanes > 2 ? pl[64] : 0u, n3 = fr & ~op;
           // 4x4 bit transposition: nibble i of n_w = (visited, delta bits 2..0) of cell 4i + w
           uint32_t t;
           t = ((n0 >> 2) ^ n2) & 0x33333333u; n2 ^= t; n0 ^= t << 2;
@@ -271,11 +410,12 @@ __global__ void __launch_bounds__(kSwThreads, 1) bfs_sweep_kernel(BfsSweepParams
           t = ((n2 >> 1) ^ n3) & 0x55555555u; n3 ^= t; n2 ^= t << 1;
           int32_t* row = g.out + (size_t)y * dimx;
           const int xb = 32 * lane - gx;
+          const uint32_t nn[4] = {n0, n1, n2, n3};
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
+          for (int ii = 0; ii < 8 / (kSwWriterWarps / 2); ++ii) {
+            const int i = wp * (8 / (kSwWriterWarps / 2)) + ii;
             const int x0 = 32 * lane + 4 * i;
             int v[4];
-            const uint32_t nn[4] = {n0, n1, n2, n3};
 #pragma unroll
             for (int w = 0; w < 4; ++w) {
               const uint32_t nib = nn[w] >> (4 * i);
@@ -297,52 +437,14 @@ __global__ void __launch_bounds__(kSwThreads, 1) bfs_sweep_kernel(BfsSweepParams
           pf = (rn >= 0 && !(h == 1 && rn == 0)) ? sweepFreeWord(p.rowbits, p.WPR, dimy, h ? gy - rn : gy + rn, lane)
                                                  : 0u;
         }
-      } else if (!(p.dbg & 1)) {
-        // sparse levels: (level, half) pairs dealt round-robin to the sparse warps
-        for (int q = sw; q < (kSwLmax - kSwDense) * 2; q += kSwSparseWarps) {
-          const int k = kSwDense + (q >> 1), h = q & 1, r = tau - 2 * k;
-          if (r < 0) break;  // deeper levels have not started either
-          if (h == 1 && r == 0) continue;
-          const int y = h ? gy - r : gy + r;
-          const int slot = r % 3;
-          uint32_t* const Sk = S + (k * 2 + h) * 3 * 32;
-          uint32_t nw = 0u, nzb = 0u;
-          if (y >= 0 && y < dimy) {
-            const int bp = ((k - 1) * 2 + h) * 4, bk = (k * 2 + h) * 4;
-            uint32_t live;
-            if (r == 0)
-              live = nz[bp] | nz[bp + 1] | nz[bp + 4 + 1];
-            else
-              live = nz[bp + slot] | nz[bp + (r + 1) % 3] | (r == 1 ? nz[(k * 2) * 4] : nz[bk + (r - 1) % 3]);
-            if (live) {
-              uint32_t* const ringRow = ring + (h * kSwRO + r % kSwRO) * 32;
-              const uint32_t op = ringRow[lane];
-              const uint32_t* Sp = S + ((k - 1) * 2 + h) * 3 * 32;
-              uint32_t sp, spu, npv = 0u;
-              if (r == 0) {
-                sp = Sp[lane];
-                spu = Sp[32 + lane] | Sp[3 * 32 + 32 + lane];
-              } else {
-                sp = Sp[slot * 32 + lane];
-                spu = Sp[((r + 1) % 3) * 32 + lane];
-              }
-              if (r == 1)
-                npv = S[(k * 2) * 3 * 32 + lane];
-              else if (r > 1)
-                npv = Sk[((r - 1) % 3) * 32 + lane];
-              nw = sweepRowStep(sp, spu, npv, op, g.mR, g.mL, g.cb, lane);
-              nzb = __ballot_sync(kFull, nw != 0u);
-              if (nzb) {
-                if (nw) ringRow[lane] = op & ~nw;
-                sweepStoreCells(g, nzb, nw, y, r, k, lane);
-                act = true;
-                if (k == kSwLmax - 1) sHandOver = 1;
-              }
-            }
-          }
-          Sk[slot * 32 + lane] = nw;
-          if (lane == 0) nz[(k * 2 + h) * 4 + slot] = nzb;
-        }
+      } else {
+        // sparse levels: one thread per word item of this step
+        const int n = min((int)cnt[tau & 3], kSwListCap);
+        act = n > 0;
+        // item i goes to lane i / #warps of sparse warp i % #warps: few items per warp, short divergent paths
+        for (int i = (st >> 5) + kSwSparseWarps * (st & 31); i < n; i += kSwSparseWarps * 32)
+          sweepItem(sh, g, tau, list[(tau & 3) * kSwListCap + i]);
+        if (st == 0) cnt[(tau + 3) & 3] = 0u;  // the list of the previous step
       }
 #ifdef MRP_SWEEP_TIMING
       busy += clock64() - t0;
@@ -370,11 +472,16 @@ __global__ void __launch_bounds__(kSwThreads, 1) bfs_sweep_kernel(BfsSweepParams
   }
 }
 
-constexpr size_t kSwSmemBytes =
-    4 * ((size_t)kSwLmax * 2 * 3 * 32 + 2 * kSwRO * 32 + 2 * kSwRP * kSwPlanes * 32 + kSwLmax * 2 * 4);
+constexpr size_t kSwSmemBytes = 4 * ((size_t)kSwDense * 2 * 3 * 32 + 2 * kSwRO * 32 + 2 * kSwRP * kSwPlanes * 32 +
+                                     kSwSparseLevels * 2 * 3 * 32 + 8) +
+                                2 * (size_t)4 * kSwListCap;
 
 bool bfsSweepFits(const mrp_map_s* map) {
-  if (getenv("MRP_BFS_NOSWEEP")) return false;
+  // Opt-in: bit-exact, but measured 2.2-2.6x slower than the queue kernel on the
+  // C5 map (profiles/README.md, round 2): the ~900 steps of a goal are a chain of
+  // CTA-wide barriers, and a word item of a sparse level is a chain of four
+  // shared-memory atomics.
+  if (!getenv("MRP_BFS_SWEEP")) return false;
   return map->dimx <= 1024 && map->dimy < 32768 && kSwSmemBytes + 1024 <= ctx().smemOptin;
 }
 

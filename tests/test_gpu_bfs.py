@@ -74,6 +74,31 @@ def test_queue_overflow_and_tiled_fallback(capi, orc, env):
             os.environ.pop(k, None)
 
 
+@pytest.mark.parametrize("dimx,dimy,density", [
+    (33, 32, 0.2), (100, 37, 0.35), (257, 300, 0.25), (1000, 70, 0.2), (70, 1100, 0.2),
+    (1024, 130, 0.2), (640, 200, 0.45), (96, 67, -1.0)])
+def test_detour_sweep_kernel(capi, orc, dimx, dimy, density):
+    """MRP_BFS_SWEEP=1: the detour-level sweep (bfs_sweep.cu), opt-in because it is slower than the
+    queue kernel; goals that need more detour levels than it holds (the serpentine maze, the 45 %
+    map) are handed to the queue kernel.  Same bytes as the oracle either way."""
+    rng = np.random.default_rng(dimx * 7 + dimy)
+    if density < 0:
+        obst = []
+        for y in range(1, dimy, 2):
+            gap = dimx - 1 if (y // 2) % 2 == 0 else 0
+            obst += [[x, y] for x in range(dimx) if x != gap]
+        obst = np.asarray(obst, np.int32)
+    else:
+        obst = _rand_map(rng, dimx, dimy, density)
+    cells = rng.choice(dimx * dimy, 10, replace=False)
+    goals = np.stack([cells % dimx, cells // dimx], 1)  # may sit on obstacles
+    goals[0] = (0, 0)
+    goals[1] = (dimx - 1, dimy - 1)
+    got = _with_env({"MRP_BFS_SWEEP": "1"}, lambda: capi.bfs_fields(dimx, dimy, obst, goals))
+    want = orc.bfs_fields(dimx, dimy, obst, goals)
+    assert np.array_equal(got, want)
+
+
 def test_empty_and_errors(capi):
     assert capi.bfs_fields(8, 8, [], np.zeros((0, 2))).shape == (0, 64)
     with pytest.raises(capi.MrpError):
