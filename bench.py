@@ -254,6 +254,15 @@ def search_metrics(pkg, rank=0, world=1, dist=None, dev=None):
     out["ecbs_seconds"] = dt_max
     out["ecbs_seconds_runs_rank0"] = runs
     out["ecbs_max_cost_over_lb"] = ratio if n_ok else None
+    # every solved instance of the batch through the solution checker (validate.py: starts, goals,
+    # unit moves on free cells, no vertex conflict / edge swap inside the reference's loop bound)
+    invalid = [(i.name, pkg.validate.validate_paths(i, r["paths"], 0))
+               for i, r in zip(insts, res) if r["status"] == 0]
+    invalid = [b for b in invalid if b[1]]
+    out["ecbs_solutions_checked"] = len(ok)  # this rank's
+    out["ecbs_invalid_solutions"] = len(invalid)
+    assert not invalid, "invalid ECBS solutions: %s" % invalid[:3]
+    out["ecbs_unsolved"] = [i.name for i, r in zip(insts, res) if r["status"] != 0][:40]
     n_cpu = 6
     t0 = time.perf_counter()
     cres = [orc.ecbs(i.dimx, i.dimy, i.obstacles, i.starts, i.goals, 1.3, (cap_hl, 0, 30.0))
@@ -267,6 +276,8 @@ def search_metrics(pkg, rank=0, world=1, dist=None, dev=None):
         out["ecbs_reference_binary"] = ("unmodified example/ecbs.cpp + stand-in Boost/yaml-cpp "
                                         "headers (oracle/_ref), statistics.runtime convention")
     out["ecbs_cost_gpu_vs_cpu"] = [[a["cost"], b["cost"]] for a, b in zip(res, cres)]
+    out.update(c1_datapoint(pkg, s32))
+    out.update(c3_scaled(pkg, s32))
     # smem-resident maps: all goals of all 1000 32x32 instances / 2000 8x8 instances
     import torch
     for tag, sset in (("32x32", s32), ("8x8", s8)):
@@ -323,6 +334,66 @@ def search_metrics(pkg, rank=0, world=1, dist=None, dev=None):
             if a["status"] == 0 and b["status"] == 0 and a["cost"] != b["cost"]]
     out["cbs_8x8_cost_mismatches_vs_oracle"] = len(mism)
     return out
+
+
+def c1_datapoint(pkg, s32):
+    """Config C1: ECBS w = 1.3 on map_32by32_obst204_agents10_ex1, one instance (a latency datapoint:
+    a 10-agent instance cannot fill a GPU), next to the unmodified reference binary (oracle/_ref/ecbs,
+    output format of example/ecbs.cpp:584-617) and the oracle port on one host core."""
+    import tempfile
+    import yaml
+    from oracle import orc
+    inst = next(i for i in s32 if i.name == "map_32by32_obst204_agents10_ex1")
+    pkg.solver.solve_batch(pkg.solver.ECBS, [inst], w=1.3, max_hl=2000)
+    t0 = time.perf_counter()
+    r = pkg.solver.solve_batch(pkg.solver.ECBS, [inst], w=1.3, max_hl=2000)[0]
+    wall = time.perf_counter() - t0
+    assert r["status"] == 0 and pkg.validate.validate_paths(inst, r["paths"], 0) is None
+    assert 236 <= r["cost"] <= 306  # optimal sum of costs 236 (BASELINE.md), w = 1.3
+    d = {"gpu": {"cost": r["cost"], "makespan": r["makespan"], "lower_bound": r["lower_bound"],
+                 "runtime_s": r["runtime"], "wall_s": wall, "highLevelExpanded": r["hl_expanded"],
+                 "lowLevelExpanded": r["ll_expanded"]}}
+    t0 = time.perf_counter()
+    o = orc.ecbs(inst.dimx, inst.dimy, inst.obstacles, inst.starts, inst.goals, 1.3, (2000, 0, 30.0))
+    d["oracle_port_1core"] = {"cost": o["cost"], "makespan": o["makespan"], "runtime_s": time.perf_counter() - t0,
+                              "highLevelExpanded": o["hl_expanded"], "lowLevelExpanded": o["ll_expanded"]}
+    exe = os.path.join(ROOT, "oracle", "_ref", "ecbs")
+    if os.path.exists(exe):
+        with tempfile.TemporaryDirectory() as td:
+            inp, outp = os.path.join(td, "i.yaml"), os.path.join(td, "o.yaml")
+            pkg.instances.save_yaml(inst, inp)
+            subprocess.run([exe, "-i", inp, "-o", outp, "-w", "1.3"], stdout=subprocess.DEVNULL,
+                           stderr=subprocess.DEVNULL, timeout=60, check=True)
+            with open(outp) as f:
+                st = yaml.safe_load(f)["statistics"]
+        d["reference_binary_1core"] = {"cost": st["cost"], "makespan": st["makespan"], "runtime_s": st["runtime"],
+                                       "highLevelExpanded": st["highLevelExpanded"],
+                                       "lowLevelExpanded": st["lowLevelExpanded"]}
+    return {"c1_ecbs_w1.3_agents10_ex1": d}
+
+
+def c3_scaled(pkg, s32, sizes=(120, 160, 200), batch=100, seconds=60.0):
+    """Config C3 at its stated sizes: the obstacle layouts of the 100-agent files scaled to N agents
+    (instances.synthetic_c3), ECBS w = 1.3, one batch of `batch` instances per N under a
+    wall-clock cap; solved / cost over lower bound / validity per N."""
+    base = [i for i in s32 if i.n_agents == 100][:batch]
+    rows = {}
+    for n in sizes:
+        insts = [pkg.instances.synthetic_c3(b, k, n) for k, b in enumerate(base)]
+        t0 = time.perf_counter()
+        res = pkg.solver.solve_batch(pkg.solver.ECBS, insts, w=1.3, max_hl=2000, max_seconds=seconds)
+        dt = time.perf_counter() - t0
+        ok = [(i, r) for i, r in zip(insts, res) if r["status"] == 0]
+        bad = [i.name for i, r in ok if pkg.validate.validate_paths(i, r["paths"], 0)]
+        assert not bad, "invalid ECBS solutions at %d agents: %s" % (n, bad[:3])
+        rows[str(n)] = {"solved": "%d/%d" % (len(ok), len(insts)), "seconds": dt,
+                        "instances_per_s": len(ok) / dt,
+                        "max_cost_over_lb": max((r["cost"] / r["lower_bound"] for _, r in ok), default=None),
+                        "invalid_solutions": 0}
+    return {"ecbs_c3_scaled": rows,
+            "ecbs_c3_scaled_config": "32x32_obst204 layouts of the 100-agent files, %d instances per N, agents "
+                                     "appended by instances.synthetic_c3, w = 1.3, cap 2000 high-level "
+                                     "expansions / %.0f s per batch" % (batch, seconds)}
 
 
 def reference_binary_rate(tool, insts, extra, timeout=60.0):
@@ -480,6 +551,17 @@ def run_ours(args):
         max_t = int(length.max().item()) - 1
         pair_steps = N * (N - 1) // 2 * max_t
         res = d_res.cpu().numpy()
+        # the answer of the CPU oracle for this very table (tests/golden/make_c5_conflict_golden.py)
+        gp = os.path.join(ROOT, "tests", "golden", "c5_conflicts.json")
+        golden_ok = None
+        if os.path.exists(gp) and world == 1:
+            import zlib
+            with open(gp) as f:
+                gold = json.load(f)
+            assert zlib.crc32(table.cpu().numpy().tobytes()) == gold["table_crc32"], "C5 path table differs"
+            assert int(res[1]) == gold["count"] and int(np.uint64(res[0])) == gold["first_key"], \
+                "C5 conflict sweep differs from the oracle: %s vs %s" % (res[:2], gold)
+            golden_ok = True
         also.update({
             "conflict_pair_steps_per_s": pair_steps / (cms * 1e-3),
             "conflict_ms": cms, "conflict_first_only_ms": fms,
@@ -487,6 +569,9 @@ def run_ours(args):
             "conflict_count": int(res[1]),
             "conflict_first_key": int(np.uint64(res[0])) if res[0] != -1 else None,
             "conflict_table_gbps": N * Tpad * 4 / (cms * 1e-3) / 1e9,
+            "conflict_equals_oracle_golden": golden_ok,
+            "conflict_pair_steps_note": "pair-steps/s is an EQUIVALENT-work figure: N(N-1)/2 * max_t pair tests "
+                                        "of the reference's loops divided by the time of the O(N*T) hashed sweep",
         })
 
     # ---- conflict sweep sharded by time slab over the ranks:
@@ -670,10 +755,9 @@ def main():
         # same for the host threads that expand packed distance fields (mrp_bfs_fields)
         os.environ.setdefault("MRP_WIDEN_THREADS",
                               str(max(1, min(16, (os.cpu_count() or 1) // world))))
-        # stdout carries exactly one JSON line: NCCL prints its version banner at every
-        # debug level from VERSION up (WARN included), and to stdout unless redirected
-        os.environ["NCCL_DEBUG"] = "NONE"
-        os.environ["NCCL_DEBUG_FILE"] = "/dev/stderr"
+        # stdout carries exactly one JSON line: whatever NCCL prints (its banner at NCCL_DEBUG >=
+        # VERSION, set by the caller if wanted) goes to stderr
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -202,7 +202,10 @@ typedef struct {
 typedef struct {
   int32_t variant;      /* 0: cbs/ecbs moves (all cost 1); 1: cbs_ta (waiting
                            on the goal is free, example/cbs_ta.cpp:329-339) */
-  float w;              /* <= 0 or == 1.0: A*; > 1: A*-epsilon focal search */
+  float w;              /* < 1 (e.g. 0): A*.  >= 1: A*-epsilon focal search; w == 1.0
+                           is the focal search among the nodes with f == fmin, i.e.
+                           optimal cost with the fewest conflicts, what `ecbs -w 1.0`
+                           runs in the reference (a_star_epsilon.hpp:240) */
   int32_t max_expanded; /* per job cap (the reference has none) */
   int32_t path_cap;     /* rows available per job in out_cells / out_g */
 } mrp_lowlevel_params;

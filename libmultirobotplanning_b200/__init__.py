@@ -6,3 +6,4 @@ cbs / ecbs / cbs_ta command lines live in host/."""
 from . import _capi as capi  # noqa: F401
 from . import instances  # noqa: F401
 from . import solver  # noqa: F401
+from . import validate  # noqa: F401

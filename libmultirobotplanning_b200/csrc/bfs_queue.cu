@@ -58,7 +58,30 @@ struct BfsQueueParams {
   int cap;       // queue capacity (entries, a power of two)
   uint32_t wprMagic;  // row of bitmap word w = umulhi(w, wprMagic) >> wprShift  (= w / WPR)
   int wprShift;
+  int tma;  // 1: the free mask of a goal arrives by one bulk-async copy (MRP_BFS_TMA=0 for the load loop)
 };
+
+// ---- bulk-async (TMA, 1-D) copy global -> shared, completion on an mbarrier ----
+__device__ __forceinline__ void mbarInit(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void bulkLoad(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  // earlier generic-proxy accesses to the destination (the claims of the last goal) before the async-proxy write
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void mbarWait(uint32_t bar, uint32_t phase) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@!p bra WAIT_%=;\n\t}" ::"r"(bar),
+      "r"(phase)
+      : "memory");
+}
 
 #ifdef MRP_BFS_TIMING
 // per-level log of CTA 0: frontier size and clock (tools/bfsq_timing.py)
@@ -200,6 +223,7 @@ __global__ void __launch_bounds__(1024, 1) bfs_queue_kernel(BfsQueueParams p) {
   __shared__ int sCount[3];
   __shared__ int sGoal;
   __shared__ uint32_t sScratch[32];
+  __shared__ __align__(8) unsigned long long sBar;
   const int tid = threadIdx.x, lane = tid & 31;
   const int nThreads = blockDim.x;
   const uint32_t ltMask = (1u << lane) - 1u;
@@ -228,6 +252,12 @@ __global__ void __launch_bounds__(1024, 1) bfs_queue_kernel(BfsQueueParams p) {
   const int ringFirst = nThreads >= 256 ? nThreads - 128 : nThreads - 32;
   const uint32_t firstOff = 4u * (uint32_t)min(tid, cap - 1);
   if (tid < 32) sScratch[tid] = 0;
+  const uint32_t barS = (uint32_t)__cvta_generic_to_shared(&sBar);
+  uint32_t barPhase = 0;
+  if (p.tma && tid == 0) {
+    mbarInit(barS, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
 #ifdef MRP_BFS_TIMING
   if (tid == 0 && blockIdx.x < 1024) g_bfsqBlocks[blockIdx.x][0] = globalTimer();
 #endif
@@ -242,7 +272,12 @@ __global__ void __launch_bounds__(1024, 1) bfs_queue_kernel(BfsQueueParams p) {
 #ifdef MRP_BFS_TIMING
     if (blockIdx.x == 0 && tid == 0) g_bfsqLevels[0][0] = (unsigned)clock64();
 #endif
-    for (int i = tid; i < p.nOpenWords; i += nThreads) open[i] = __ldg(&p.rowbits[i]);
+    if (p.tma) {
+      // one bulk-async copy of the whole bitmap (16-byte granules; the allocation is padded)
+      if (tid == 0) bulkLoad(openS, p.rowbits, (uint32_t)(((p.nOpenWords + 3) & ~3) * 4), barS);
+    } else {
+      for (int i = tid; i < p.nOpenWords; i += nThreads) open[i] = __ldg(&p.rowbits[i]);
+    }
     if (tid == 0) {
       sCount[0] = 0;
       sCount[1] = 0;
@@ -253,6 +288,10 @@ __global__ void __launch_bounds__(1024, 1) bfs_queue_kernel(BfsQueueParams p) {
     const int gy = goal / dimx, gx = goal - gy * dimx;
     const int gw = (gy + 1) * WPR + ((gx + 1) >> 5);
     const uint32_t gbit = 1u << ((gx + 1) & 31);
+    if (p.tma) {
+      mbarWait(barS, barPhase);
+      barPhase ^= 1u;
+    }
     __syncthreads();
     const bool goalFree = (open[gw] & gbit) != 0;
     // largest Manhattan distance from the goal to a cell of the map
@@ -483,6 +522,9 @@ int launchBfsQueue(const mrp_map_s* map, const int32_t* d_goal_cell, int n_goals
   while ((2 << sh) <= q.WPR) ++sh;
   p.wprShift = sh;
   p.wprMagic = (uint32_t)((((unsigned long long)1 << (32 + sh)) + (unsigned)q.WPR - 1) / (unsigned)q.WPR);
+  const char* tma = getenv("MRP_BFS_TMA");
+  p.tma = tma ? atoi(tma) : 1;
+  if ((reinterpret_cast<uintptr_t>(map->d_rowbits) & 15) != 0) p.tma = 0;
   MRP_CUDA(cudaMemsetAsync(d_ws, 0, 64 * 4, st));
   const QueueKernel fn = queueKernelFor(map, q);
   int blocks = queueBlocks(fn, q);

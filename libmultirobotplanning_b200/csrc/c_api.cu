@@ -287,7 +287,8 @@ int mrp_map_create(int dimx, int dimy, const int32_t* obst_xy, int n_obst,
     std::vector<uint32_t> bits84((size_t)TW8 * TH4, 0u);
     // third layout: row-major with a zero border for the queue BFS kernel
     const int WPR = ((dimx + 2 + 31) / 32) | 1;
-    std::vector<uint32_t> rowbits((size_t)(dimy + 4) * WPR, 0u);
+    // (+ 4 words: the queue kernel's bulk copy moves whole 16-byte granules)
+    std::vector<uint32_t> rowbits((size_t)(dimy + 4) * WPR + 4, 0u);
     for (int y = 0; y < dimy; ++y)
       for (int x = 0; x < dimx; ++x)
         if ((bits[((size_t)(y >> 5) * W + (x >> 5)) * 32 + (y & 31)] >> (x & 31)) & 1u) {

@@ -19,9 +19,8 @@
 // atomicMin; counts are reduced per CTA and added with one atomic.
 //
 // hashed kernels (256 < N <= 4096, O(N*T) instead of O(N^2*T)): the table is
-// transposed and clamped once, then one CTA per timestep; three generations
-// with identical answers, newest = default:
-//   conflict_hash_kernel   16-byte slots, three atomics per agent, two tables
+// transposed and clamped once, then one CTA per timestep; two kernels with
+// identical answers, the second one is the default:
 //   conflict_hash2_kernel  one table of (cell, agent) entries, one CAS per probe
 //   conflict_sieve_kernel  hashed occupancy bitmaps pick the few agents that
 //                          can be in a conflict; exact pass over those only
@@ -297,169 +296,11 @@ __device__ __forceinline__ uint32_t hash64(unsigned long long k) {
   return (uint32_t)k;
 }
 
-template <bool kFirst, bool kCount>
-__global__ void __launch_bounds__(kHashThreads)
-conflict_hash_kernel(const int32_t* __restrict__ posT, int N, int mode, int H,
-                     unsigned long long* __restrict__ result) {
-  extern __shared__ unsigned long long hsm[];
-  unsigned long long* key = hsm;                                   // [H]
-  uint32_t* cnt = reinterpret_cast<uint32_t*>(hsm + H);            // [H]
-  uint32_t* minId = cnt + H;                                       // [H]
-  __shared__ unsigned long long sBest[kHashThreads / 32];
-  __shared__ unsigned long long sSum[kHashThreads / 32];
-  const int t = blockIdx.x;
-  const int maxLen = (int)result[2];
-  const int max_t = maxLen - (mode == 0 ? 1 : 0);
-  if (t >= max_t) return;
-  if (kFirst && !kCount) {
-    const unsigned long long b = *(volatile unsigned long long*)&result[0];
-    if (b != kNoConflict && (int)(b >> 41) < t) return;
-  }
-  const uint32_t mask = (uint32_t)H - 1u;
-  const int32_t* rowA = posT + (size_t)t * rowStride(N);
-  const int32_t* rowB = rowA + rowStride(N);
-  const int tid = threadIdx.x;
-  constexpr unsigned long long kEmpty = ~0ull;
-
-  int a[kHashPerThread], b[kHashPerThread], slot[kHashPerThread];
-#pragma unroll
-  for (int k = 0; k < kHashPerThread; ++k) {
-    const int i = tid + k * kHashThreads;
-    a[k] = i < N ? rowA[i] : 0;
-    b[k] = i < N ? rowB[i] : 0;
-  }
-  unsigned long long best = kNoConflict, sum = 0;
-  unsigned int published = 0;  // keeps the returning atomics alive
-
-  // ---------------- vertex conflicts ----------------
-  for (int s = tid; s < H; s += kHashThreads) {
-    key[s] = kEmpty;
-    cnt[s] = 0;
-    minId[s] = 0xffffffffu;
-  }
-  __syncthreads();
-#pragma unroll
-  for (int k = 0; k < kHashPerThread; ++k) {
-    const int i = tid + k * kHashThreads;
-    if (i >= N) continue;
-    const unsigned long long kk = (unsigned long long)(uint32_t)a[k];
-    uint32_t s = hash64(kk) & mask;
-    while (true) {
-      const unsigned long long prev = atomicCAS(&key[s], kEmpty, kk);
-      if (prev == kEmpty || prev == kk) break;
-      s = (s + 1) & mask;
-    }
-    published += atomicAdd(&cnt[s], 1u);
-    published += atomicMin(&minId[s], (uint32_t)i);
-    slot[k] = (int)s;
-  }
-  // returning atomics + fence: every update of the table has been performed
-  // before the barrier publishes it (a run with fire-and-forget reductions
-  // here was observed to lose updates under heavy probing)
-  __threadfence_block();
-  __syncthreads();
-  if (kCount)
-    for (int s = tid; s < H; s += kHashThreads) {
-      const unsigned long long c = cnt[s];
-      sum += c * (c - 1) / 2;
-    }
-  if (kFirst) {
-#pragma unroll
-    for (int k = 0; k < kHashPerThread; ++k) {
-      const int i = tid + k * kHashThreads;
-      if (i >= N) continue;
-      const uint32_t m = minId[slot[k]];
-      if (cnt[slot[k]] >= 2 && m != (uint32_t)i)
-        best = min(best, conflictKey(t, 0, (int)m, i));
-    }
-  }
-  __syncthreads();
-  // ---------------- edge (swap) conflicts ----------------
-  for (int s = tid; s < H; s += kHashThreads) {
-    key[s] = kEmpty;
-    cnt[s] = 0;
-    minId[s] = 0xffffffffu;
-  }
-  __syncthreads();
-#pragma unroll
-  for (int k = 0; k < kHashPerThread; ++k) {
-    const int i = tid + k * kHashThreads;
-    if (i >= N) continue;
-    const unsigned long long kk =
-        ((unsigned long long)(uint32_t)a[k] << 32) | (unsigned long long)(uint32_t)b[k];
-    uint32_t s = hash64(kk) & mask;
-    while (true) {
-      const unsigned long long prev = atomicCAS(&key[s], kEmpty, kk);
-      if (prev == kEmpty || prev == kk) break;
-      s = (s + 1) & mask;
-    }
-    published += atomicAdd(&cnt[s], 1u);
-    published += atomicMin(&minId[s], (uint32_t)i);
-  }
-  __threadfence_block();
-  __syncthreads();
-  unsigned long long partners = 0;
-#pragma unroll
-  for (int k = 0; k < kHashPerThread; ++k) {
-    const int i = tid + k * kHashThreads;
-    if (i >= N) continue;
-    const unsigned long long rk =
-        ((unsigned long long)(uint32_t)b[k] << 32) | (unsigned long long)(uint32_t)a[k];
-    uint32_t s = hash64(rk) & mask;
-    while (true) {
-      const unsigned long long cur = *(volatile unsigned long long*)&key[s];
-      if (cur == kEmpty) break;
-      if (cur == rk) {
-        const uint32_t r = cnt[s];
-        if (a[k] == b[k]) {
-          partners += r - 1;  // resting agents on this cell, minus the agent itself
-        } else {
-          partners += r;
-          if (kFirst) {
-            const int m = (int)minId[s];
-            best = min(best, conflictKey(t, 1, min(i, m), max(i, m)));
-          }
-        }
-        break;
-      }
-      s = (s + 1) & mask;
-    }
-  }
-  // every unordered pair was seen from both sides
-  // ---------------- reductions ----------------
-  if (kFirst) {
-    best = warpMin64Key(best);
-    if ((tid & 31) == 0) sBest[tid >> 5] = best;
-  }
-  if (kCount) {
-#pragma unroll
-    for (int o = 16; o; o >>= 1) {
-      sum += __shfl_xor_sync(0xffffffffu, sum, o);
-      partners += __shfl_xor_sync(0xffffffffu, partners, o);
-    }
-    if ((tid & 31) == 0) sSum[tid >> 5] = sum * 2 + partners;  // 2 * (vertex + edge pairs)
-  }
-  __syncthreads();
-  if (published == 0xdeadbeefu) result[3] = 1;  // result[3] is scratch: keeps `published` live
-  if (tid == 0) {
-    if (kFirst) {
-      unsigned long long bb = kNoConflict;
-      for (int w = 0; w < kHashThreads / 32; ++w) bb = min(bb, sBest[w]);
-      if (bb != kNoConflict) atomicMin(&result[0], bb);
-    }
-    if (kCount) {
-      unsigned long long tot = 0;
-      for (int w = 0; w < kHashThreads / 32; ++w) tot += sSum[w];
-      if (tot) atomicAdd(&result[1], tot / 2);
-    }
-  }
-}
-
 // ---- one table, one atomic per agent ----------------------------------------
-// conflict_hash_kernel above spends three atomics per agent and phase on a
-// 16-byte slot (key, count, smallest id) and builds a second table for the
-// moves.  This version keeps ONE table of 64-bit entries (cell << 32 | agent)
-// per timestep:
+// (A first generation spent three atomics per agent and phase on 16-byte slots
+// (key, count, smallest id) and built a second table for the moves: 0.45 ms on
+// the C5 table; removed in round 2.)  ONE table of 64-bit entries
+// (cell << 32 | agent) per timestep:
 //   * an agent is inserted with a single atomicCAS per probe; every entry of
 //     its own cell that it walks past on the way to its free slot is an agent
 //     that got there first, i.e. one vertex-conflict pair (i, j), seen exactly
@@ -845,8 +686,7 @@ int launchConflicts(const int32_t* d_cell, const int32_t* d_len, int N, int Tpad
   int32_t* posT = static_cast<int32_t*>(d_ws);
   // hand-over flags of the sieve kernel, cleared by the transposition
   unsigned char* todoAll = static_cast<unsigned char*>(d_ws) + (size_t)(Tpad + 1) * rowStride(N) * 4;
-  const bool hash1 = getenv("MRP_CONFLICTS_HASH1") != nullptr;
-  const bool sieve = !hash1 && !getenv("MRP_CONFLICTS_HASH2");
+  const bool sieve = !getenv("MRP_CONFLICTS_HASH2");
   auto transpose = [&](int tBase, int tEnd, int firstOnly) {
     dim3 tg((rowStride(N) + 31) / 32, (tEnd - tBase + 1 + 63) / 64);
     conflict_transpose_kernel<<<tg, dim3(32, 8), 0, st>>>(d_cell, d_len, N, Tpad, d_result, posT,
@@ -854,7 +694,7 @@ int launchConflicts(const int32_t* d_cell, const int32_t* d_len, int N, int Tpad
   };
   int H = 512;
   while (H < 2 * N) H <<= 1;
-  if (!hash1) {
+  {
     // default: sieve kernel, then the single-table kernel on the timesteps it
     // handed over (MRP_CONFLICTS_HASH2: single-table kernel on every timestep)
     unsigned char* todo = nullptr;
@@ -905,21 +745,6 @@ int launchConflicts(const int32_t* d_cell, const int32_t* d_len, int N, int Tpad
     MRP_CUDA(cudaGetLastError());
     return 0;
   }
-  transpose(0, Tpad, 0);
-  const size_t smem = (size_t)H * 16;
-  auto run = [&](auto kern) {
-    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    kern<<<Tpad, kHashThreads, smem, st>>>(posT, N, mode, H, d_result);
-  };
-  if (wantFirst && wantCount)
-    run(conflict_hash_kernel<true, true>);
-  else if (wantFirst)
-    run(conflict_hash_kernel<true, false>);
-  else
-    run(conflict_hash_kernel<false, true>);
-  countLaunch(2);
-  MRP_CUDA(cudaGetLastError());
-  return 0;
 }
 
 int launchConflictsBatch(const int32_t* d_cell, const int32_t* d_len, int B,

@@ -140,8 +140,8 @@ def test_hashed_path_equals_all_pairs(capi, orc, monkeypatch):
             monkeypatch.delenv("MRP_CONFLICTS_ALLPAIRS")
             assert (f_h, c_h) == (f_p, c_p), (N, mode)
             # the default is the sieve kernel (+ the single-table kernel for dense
-            # timesteps); the single-table and the three-atomics kernels on their own
-            for var in ("MRP_CONFLICTS_HASH2", "MRP_CONFLICTS_HASH1"):
+            # timesteps); the single-table kernel on its own
+            for var in ("MRP_CONFLICTS_HASH2",):
                 monkeypatch.setenv(var, "1")
                 assert (capi.first_conflict(cell, ln, 32, mode),
                         capi.count_conflicts(cell, ln, mode)) == (f_p, c_p), (N, mode, var)
@@ -229,3 +229,54 @@ def test_hashed_path_stress_high_load(capi, orc):
         for _ in range(3):
             assert capi.count_conflicts(cell, ln, 0) == want_c
         assert capi.first_conflict(cell, ln, 1000, 0) == want_f
+
+
+def test_c5_table_equals_the_oracle_golden(capi):
+    """The full config-C5 table (4096 agents walking down their goal fields on the synthetic
+    1024x1024 map, max_t = 1908): the table built on the GPU is byte-identical to the one the CPU
+    oracle built (CRC), and count / first-conflict key of every GPU sweep equal the oracle's
+    all-pairs answer (tests/golden/c5_conflicts.json, made by tests/golden/make_c5_conflict_golden.py;
+    reference loops: example/cbs.cpp:335-386, example/ecbs.cpp:315-350)."""
+    import json
+    import os
+    import sys
+    import zlib
+    import torch
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    with open(os.path.join(root, "tests", "golden", "c5_conflicts.json")) as f:
+        gold = json.load(f)
+    sys.path.insert(0, root)
+    import bench
+    import libmultirobotplanning_b200 as pkg
+    N, DIM = gold["N"], 1024
+    inst = pkg.instances.synthetic_c5(dim=DIM, n_agents=N)
+    gc = (inst.goals[:N, 0] + DIM * inst.goals[:N, 1]).astype(np.int32)
+    mp = capi.Map(DIM, DIM, inst.obstacles)
+    dev = torch.device("cuda", 0)
+    d_goals = torch.from_numpy(gc).to(dev)
+    d_out = torch.empty((N, DIM * DIM), dtype=torch.int32, device=dev)
+    ws = torch.empty(max(mp.workspace_bytes(N), 256), dtype=torch.uint8, device=dev)
+    mp.bfs_fields_dev(d_goals.data_ptr(), N, d_out.data_ptr(), ws.data_ptr(), 0)
+    torch.cuda.synchronize()
+    starts = (inst.starts[:, 0] + DIM * inst.starts[:, 1]).astype(np.int64)
+    table, length = bench.descend_paths(torch, d_out, inst, starts, N, 4096)
+    del d_out
+    tab = table.cpu().numpy()
+    ln = length.cpu().numpy()
+    assert tab.shape == (N, gold["T"])
+    assert zlib.crc32(tab.tobytes()) == gold["table_crc32"]
+    assert zlib.crc32(ln.tobytes()) == gold["length_crc32"]
+    lib = capi.lib()
+    for first, count in ((1, 1), (1, 0), (0, 1)):
+        res = torch.zeros(4, dtype=torch.int64, device=dev)
+        capi.check(lib.mrp_conflicts_dev(table.data_ptr(), length.data_ptr(), N, tab.shape[1], 0,
+                                         first, count, res.data_ptr(), 0))
+        torch.cuda.synchronize()
+        r = res.cpu().numpy()
+        if first:
+            assert int(np.uint64(r[0])) == gold["first_key"]
+        if count:
+            assert int(r[1]) == gold["count"]
+    # and through the host-pointer entry points
+    assert capi.count_conflicts(tab, ln, 0) == gold["count"]
+    assert list(capi.first_conflict(tab, ln, DIM, 0)) == gold["first_conflict"]

@@ -172,3 +172,48 @@ def test_host_assignment_matches_oracle(orc):
     c1, _ = solver.next_best_assignments(E, 60, 60, 3)
     c2, _ = orc.next_best_assignments(E, 60, 60, 3)
     assert list(c1) == list(c2)
+
+
+def test_validate_paths_agrees_with_the_oracle_conflict_count():
+    """validate.py (the vectorised solution checker bench.py runs over whole ECBS batches) against the
+    oracle's conflict loops (example/cbs.cpp:335-386, cbs_ta.cpp:369-420) on random walks."""
+    from libmultirobotplanning_b200 import validate
+    from oracle import orc
+
+    class I:
+        dimx, dimy = 9, 7
+        obstacles = np.zeros((0, 2), np.int32)
+    rng = np.random.default_rng(5)
+    seen = {True: 0, False: 0}
+    for trial in range(300):
+        n = int(rng.integers(2, 7))
+        paths, lens = [], []
+        for a in range(n):
+            L = int(rng.integers(1, 9))
+            x, y = int(rng.integers(0, 9)), int(rng.integers(0, 7))
+            p = [(x, y, 0)]
+            for t in range(1, L):
+                dx, dy = [(0, 0), (1, 0), (-1, 0), (0, 1), (0, -1)][int(rng.integers(0, 5))]
+                x, y = min(8, max(0, x + dx)), min(6, max(0, y + dy))
+                p.append((x, y, t))
+            paths.append(np.array(p))
+            lens.append(L)
+        I.starts = np.array([p[0][:2] for p in paths])
+        T = max(lens)
+        cell = np.zeros((n, T), np.int32)
+        for a, p in enumerate(paths):
+            c = p[:, 0] + 9 * p[:, 1]
+            cell[a, :len(c)] = c
+            cell[a, len(c):] = c[-1]
+        for mode in (0, 1):
+            want = orc.first_conflict(cell, np.array(lens, np.int32), 9, mode) is None
+            got = validate.validate_paths(I, paths, mode, goals=None) is None
+            assert got == want, (trial, mode, validate.validate_paths(I, paths, mode))
+            seen[want] += 1
+    assert seen[True] > 20 and seen[False] > 20
+    # moves and obstacles
+    I.starts = np.array([[0, 0]])
+    assert "more than one cell" in validate.validate_paths(I, [np.array([(0, 0, 0), (2, 0, 1)])])
+    I.obstacles = np.array([[1, 0]], np.int32)
+    assert "obstacle" in validate.validate_paths(I, [np.array([(0, 0, 0), (1, 0, 1)])])
+    assert "goal" in validate.validate_paths(I, [np.array([(0, 0, 0), (0, 1, 1)])], goals=[[3, 3]])
