@@ -11,10 +11,14 @@ conflict pair-steps/s of the same config (`also`), the HBM roofline of the
 dominant kernel, the CPU baseline (oracle port on the host cores) and the
 end-to-end number through the host-pointer C-ABI call.
 
-Multi-GPU: one process per GPU (torchrun); goals are sharded by rank, no
-data-path collective (weak scaling: 4096 goals per GPU); the optional NCCL
-all-gather that makes every field resident on every GPU is timed separately
-(`also.allgather_*`).
+Multi-GPU: one process per GPU (torchrun), STRONG scaling on the named C5 size:
+the 4096 goals are sharded by goal over the ranks and every field is resident on
+every GPU at the end of the step (mrp_bfs_fields_allgather_dev: kernels by goal
+slice, ncclAllGather of detour bytes in chunks overlapped with the next chunk's
+kernel, expansion to int32 on the device — the collective is INSIDE
+ms_per_step).  `also.weak_scaling_no_collective` is the variant with 4096 goals
+per GPU and no exchange; `also.conflict_pair_blocks_*` the conflict sweep by
+agent-pair block + all-reduce; the ECBS batch is sharded by instance.
 """
 import argparse
 import json
@@ -372,14 +376,15 @@ def c1_datapoint(pkg, s32):
     return {"c1_ecbs_w1.3_agents10_ex1": d}
 
 
-def c3_scaled(pkg, s32, sizes=(120, 160, 200), batch=100, seconds=60.0):
+def c3_scaled(pkg, s32, sizes=((120, 100), (160, 50), (200, 30)), seconds=30.0):
     """Config C3 at its stated sizes: the obstacle layouts of the 100-agent files scaled to N agents
     (instances.synthetic_c3), ECBS w = 1.3, one batch of `batch` instances per N under a
-    wall-clock cap; solved / cost over lower bound / validity per N."""
-    base = [i for i in s32 if i.n_agents == 100][:batch]
+    wall-clock cap; solved / cost over lower bound / validity per N.  (Full batches of 100 per N,
+    90 s cap: profiles/README.md, round 2.)"""
+    base = [i for i in s32 if i.n_agents == 100]
     rows = {}
-    for n in sizes:
-        insts = [pkg.instances.synthetic_c3(b, k, n) for k, b in enumerate(base)]
+    for n, batch in sizes:
+        insts = [pkg.instances.synthetic_c3(b, k, n) for k, b in enumerate(base[:batch])]
         t0 = time.perf_counter()
         res = pkg.solver.solve_batch(pkg.solver.ECBS, insts, w=1.3, max_hl=2000, max_seconds=seconds)
         dt = time.perf_counter() - t0
@@ -391,9 +396,9 @@ def c3_scaled(pkg, s32, sizes=(120, 160, 200), batch=100, seconds=60.0):
                         "max_cost_over_lb": max((r["cost"] / r["lower_bound"] for _, r in ok), default=None),
                         "invalid_solutions": 0}
     return {"ecbs_c3_scaled": rows,
-            "ecbs_c3_scaled_config": "32x32_obst204 layouts of the 100-agent files, %d instances per N, agents "
-                                     "appended by instances.synthetic_c3, w = 1.3, cap 2000 high-level "
-                                     "expansions / %.0f s per batch" % (batch, seconds)}
+            "ecbs_c3_scaled_config": "32x32_obst204 layouts of the 100-agent files, agents appended by "
+                                     "instances.synthetic_c3, w = 1.3, cap 2000 high-level expansions / "
+                                     "%.0f s per batch" % seconds}
 
 
 def reference_binary_rate(tool, insts, extra, timeout=60.0):
@@ -443,21 +448,42 @@ def run_ours(args):
     dev = torch.device("cuda", local if world > 1 else 0)
     capi.init(dev.index)
 
-    inst = c5_instance(world)
+    if world > 1:
+        # the product's own communicator (NCCL behind the C ABI, csrc/multi.cu); torch.distributed
+        # only carries its 128-byte id and the timing reductions of this script
+        idt = torch.zeros(capi.COMM_ID_BYTES, dtype=torch.uint8, device=dev)
+        if rank == 0:
+            idt = torch.frombuffer(bytearray(capi.comm_unique_id()), dtype=torch.uint8).to(dev)
+        dist.broadcast(idt, 0)
+        capi.comm_init_rank(idt.cpu().numpy().tobytes(), world, rank)
+
+    inst = c5_instance(1)  # the same 4096-agent instance at every N
     cells = DIM * DIM
     G = GOALS_PER_GPU
-    from libmultirobotplanning_b200.sharding import shard_range
-    g0, g1 = shard_range(world * G, rank, world)  # goals shard by rank, no collective
-    goals_xy = inst.goals[g0:g1]
+    # STRONG scaling, the named C5 size: the G = 4096 goals of the configuration in total, sharded by
+    # goal over the ranks, every field resident on every GPU at the end of the step (packed NCCL
+    # all-gather + device expansion INSIDE the step: mrp_bfs_fields_allgather_dev).  At N = 1 this is
+    # the plain distance-field kernel over 4096 goals.
+    goals_xy = inst.goals[:G]
     goal_cells = (goals_xy[:, 0] + DIM * goals_xy[:, 1]).astype(np.int32)
     mp = capi.Map(DIM, DIM, inst.obstacles)
     d_goals = torch.from_numpy(goal_cells).to(dev)
     d_out = torch.empty((G, cells), dtype=torch.int32, device=dev)
-    d_ws = torch.empty(max(mp.workspace_bytes(G), 256), dtype=torch.uint8, device=dev)
+    d_ws = torch.empty(max(mp.workspace_bytes(G), mp.allgather_workspace_bytes(G), 256),
+                       dtype=torch.uint8, device=dev)
     stream = torch.cuda.current_stream()
+    # the goals of this rank in the weak-scaling variant (4096 per GPU, no collective: `also`)
+    from libmultirobotplanning_b200.sharding import shard_range
+    g0, g1 = shard_range(world * G, rank, world)
+    weak_xy = (inst if world == 1 else c5_instance(world)).goals[g0:g1]
+    d_goals_weak = torch.from_numpy((weak_xy[:, 0] + DIM * weak_xy[:, 1]).astype(np.int32)).to(dev)
 
     def step():
-        mp.bfs_fields_dev(d_goals.data_ptr(), G, d_out.data_ptr(), d_ws.data_ptr(),
+        mp.bfs_fields_allgather_dev(d_goals.data_ptr(), G, d_out.data_ptr(), d_ws.data_ptr(),
+                                    stream.cuda_stream)
+
+    def weak_step():
+        mp.bfs_fields_dev(d_goals_weak.data_ptr(), G, d_out.data_ptr(), d_ws.data_ptr(),
                           stream.cuda_stream)
 
     def barrier():
@@ -488,12 +514,34 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     total_ms_max = float(t.item())
     ms_per_step = total_ms_max / args.steps
-    value = world * G * cells / (ms_per_step * 1e-3)
+    value = G * cells / (ms_per_step * 1e-3)  # whole job: G goals in total at every N
+    gather = capi.comm_last_gather() if world > 1 else None
+
+    # ---- weak scaling, no collective (goals AND their consumers sharded the same way): 4096 goals
+    # per GPU; also the timing of the distance-field kernel alone for the roofline at N > 1
+    weak_ms = None
+    if world > 1:
+        for _ in range(2):
+            weak_step()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(args.steps):
+            weak_step()
+        e1.record(stream)
+        barrier()
+        tw = torch.tensor([e0.elapsed_time(e1) / args.steps], device=dev, dtype=torch.float64)
+        dist.all_reduce(tw, op=dist.ReduceOp.MAX)
+        weak_ms = float(tw.item())
+        step()  # d_out holds the fields of goals 0..G-1 again (the conflict table below walks them)
+        barrier()
 
     # ---- roofline of the dominant kernel (bfs_large_kernel) -------------------
     peak, peak_src = measured_peaks()
     alg_bytes = G * cells * 4 + cells // 8       # 4 B per (goal, cell) + bitmap
-    kern_ms = float(np.mean(step_ms))            # one launch per step
+    # one launch of the distance-field kernel over 4096 goals: the step itself at N = 1, the
+    # no-collective step (4096 goals on this GPU) at N > 1
+    kern_ms = float(np.mean(step_ms)) if world == 1 else weak_ms
     achieved = alg_bytes / (kern_ms * 1e-3) / 1e9
     traffic = None
     tp = os.path.join(ROOT, "profiles", "traffic.json")
@@ -513,7 +561,7 @@ def run_ours(args):
     if rank == 0 and not args.skip_conflicts:
         starts_cell = (inst.starts[:, 0] + DIM * inst.starts[:, 1]).astype(np.int64)
         N = G
-        table, length = descend_paths(torch, d_out, inst, starts_cell[rank * G:], N, 4096)
+        table, length = descend_paths(torch, d_out, inst, starts_cell, N, 4096)
         Tpad = table.shape[1]
         d_res = torch.zeros(4, dtype=torch.int64, device=dev)
         lib = capi.lib()
@@ -574,63 +622,48 @@ def run_ours(args):
                                         "of the reference's loops divided by the time of the O(N*T) hashed sweep",
         })
 
-    # ---- conflict sweep sharded by time slab over the ranks:
-    # the path table is broadcast, every rank sweeps the steps of its slab, the
-    # first-conflict keys meet in an all-reduce(MIN), the counts in a SUM
+    # ---- conflict checks by agent-pair block over the ranks (north_star): every rank
+    # holds the table (here: builds it from the gathered fields), sweeps every world-th 64x64 block of
+    # agent pairs with the all-pairs kernel, keys meet in an NCCL all-reduce MIN, counts in a SUM
+    # (mrp_conflicts_sharded_dev).  On this table one GPU's hashed sweep (above) is faster than any
+    # sharding; the pair-block path is the formulation for tables beyond 4096 agents.
     if world > 1 and not args.skip_conflicts:
-        from libmultirobotplanning_b200 import sharding
-        shape = torch.zeros(2, dtype=torch.int64, device=dev)
-        if rank == 0:
-            shape[0], shape[1] = table.shape
-        dist.broadcast(shape, 0)
-        N, Tpad = int(shape[0].item()), int(shape[1].item())
-        torch.cuda.synchronize()
-        tp0 = time.perf_counter()
         if rank != 0:
-            table = torch.empty((N, Tpad), dtype=torch.int32, device=dev)
-            length = torch.empty(N, dtype=torch.int32, device=dev)
-        dist.broadcast(table, 0)
-        dist.broadcast(length, 0)
-        t_end = sharding.conflict_time_range(length, 0)
-        t0s, t1s = sharding.shard_range(t_end, rank, world)
-        sub, sublen = sharding.slab_table(table, length, t0s, max(t1s, t0s + 1))
-        torch.cuda.synchronize()
-        prep_ms = (time.perf_counter() - tp0) * 1e3
+            starts_cell = (inst.starts[:, 0] + DIM * inst.starts[:, 1]).astype(np.int64)
+            table, length = descend_paths(torch, d_out, inst, starts_cell, G, 4096)
+        N, Tpad = table.shape
         d_res2 = torch.zeros(4, dtype=torch.int64, device=dev)
         lib = capi.lib()
 
         def sweep():
-            capi.check(lib.mrp_conflicts_dev(sub.data_ptr(), sublen.data_ptr(), N, sub.shape[1],
-                                             0, 1, 1, d_res2.data_ptr(), stream.cuda_stream))
-            r = d_res2.cpu()
-            key = sharding.shift_key(int(r[0].item()), t0s) if t1s > t0s else sharding.NO_CONFLICT
-            cnt = int(r[1].item()) if t1s > t0s else 0
-            return sharding.reduce_conflicts(key, cnt, dist, dev)
-        for _ in range(3):
+            capi.check(lib.mrp_conflicts_sharded_dev(table.data_ptr(), length.data_ptr(), N, Tpad,
+                                                     0, 1, 1, d_res2.data_ptr(), stream.cuda_stream))
+        for _ in range(2):
             sweep()
         barrier()
-        ts0 = time.perf_counter()
-        reps = 5
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = 3
+        e0.record(stream)
         for _ in range(reps):
-            gkey, gcount = sweep()
-        torch.cuda.synchronize()
-        sms = torch.tensor([(time.perf_counter() - ts0) / reps * 1e3], device=dev, dtype=torch.float64)
+            sweep()
+        e1.record(stream)
+        barrier()
+        sms = torch.tensor([e0.elapsed_time(e1) / reps], device=dev, dtype=torch.float64)
         dist.all_reduce(sms, op=dist.ReduceOp.MAX)
+        r2 = d_res2.cpu().numpy()
         if rank == 0:
             want_key = also["conflict_first_key"] if also["conflict_first_key"] is not None else -1
-            assert gcount == also["conflict_count"] and gkey == want_key, \
-                "sharded conflict sweep differs from the single-GPU sweep"
+            assert int(r2[1]) == also["conflict_count"] and int(np.uint64(r2[0])) == (want_key & (2**64 - 1)), \
+                "pair-block sharded conflict sweep differs from the single-GPU sweep"
             also.update({
-                "conflict_sharded_ms": float(sms.item()),
-                "conflict_sharded_pair_steps_per_s":
+                "conflict_pair_blocks_ms": float(sms.item()),
+                "conflict_pair_blocks_pair_steps_per_s":
                     N * (N - 1) // 2 * also["conflict_max_t"] / (float(sms.item()) * 1e-3),
-                "conflict_sharded_prepare_ms": prep_ms,
-                "conflict_sharded_how": "time slabs over %d ranks: path table broadcast (prepare_ms), per-rank "
-                                        "slab sweep + device->host read + all-reduce MIN(key)/SUM(count) "
-                                        "(sharded_ms, wall clock, max over ranks); equals the single-GPU result"
-                                        % world,
+                "conflict_pair_blocks_how": "all-pairs kernel over every %d-th 64x64 block of agent pairs per rank + "
+                                            "NCCL all-reduce MIN(key) / SUM(count), device time, max over ranks; equals "
+                                            "the single-GPU result (one GPU: all pairs 7.3 ms, hashed sweep "
+                                            "conflict_ms)" % world,
             })
-        del sub, sublen
     if table is not None:
         del table, length
 
@@ -638,22 +671,24 @@ def run_ours(args):
     if not args.skip_search:
         also.update(search_metrics(pkg, rank, world, dist, dev))
 
-    # ---- optional all-gather of the fields over NVLink (north_star) -----------
-    if world > 1 and args.allgather:
-        Gg = 256  # fields per rank in the gathered sample
-        gathered = torch.empty((world * Gg, cells), dtype=torch.int32, device=dev)
-        for _ in range(2):
-            dist.all_gather_into_tensor(gathered, d_out[:Gg])
-        torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        dist.all_gather_into_tensor(gathered, d_out[:Gg])
-        e1.record()
-        torch.cuda.synchronize()
-        ms = e0.elapsed_time(e1)
-        also["allgather_ms_per_%d_fields_per_rank" % Gg] = ms
-        also["allgather_gbps_in_per_gpu"] = (world - 1) * Gg * cells * 4 / (ms * 1e-3) / 1e9
-        del gathered
+    # ---- the collective of the step and the weak-scaling variant ---------------------------
+    if world > 1 and rank == 0:
+        gbps = gather["timed_bytes_in"] / (gather["collective_ms"] * 1e-3) / 1e9 if gather["collective_ms"] else None
+        also.update({
+            "strong_scaling": "4096 goals in total; step = distance fields by goal slice + ncclAllGather of detour "
+                              "bytes (1 B per cell) in chunks of one wave, overlapped with the next chunk's kernel, "
+                              "+ expansion to int32 on the device; every field resident on every GPU",
+            "limiting_collective": "ncclAllGather (uint8 detour bytes)",
+            "allgather_ms_in_step": gather["collective_ms"],
+            "allgather_bytes_in_per_gpu": gather["wire_bytes_in"],
+            "allgather_gbps_in_per_gpu": gbps,
+            "allgather_frac_of_nvlink5_900gbps": gbps / 900.0 if gbps else None,
+            "allgather_bytes_per_cell": gather["bytes_per_cell"],
+            "weak_scaling_no_collective": {
+                "goals_per_gpu": G, "ms_per_step": weak_ms,
+                "cells_per_s": world * G * cells / (weak_ms * 1e-3),
+                "note": "goals and their consumers sharded the same way: no exchange (SURVEY §8e)"},
+        })
 
     # ---- e2e: host buffers through the C-ABI call (H2D + kernel + D2H) -------
     del d_out
@@ -662,7 +697,7 @@ def run_ours(args):
     h_out = torch.empty((Ge, cells), dtype=torch.int32).pin_memory()
     h_np = h_out.numpy()
     obst = np.ascontiguousarray(inst.obstacles, np.int32)
-    gxy = np.ascontiguousarray(goals_xy[:Ge], np.int32)
+    gxy = np.ascontiguousarray(weak_xy[:Ge], np.int32)
     def e2e_rate(steps):
         capi.bfs_fields(DIM, DIM, obst, gxy, out=h_np)  # warm (allocates scratch / staging)
         barrier()
@@ -718,11 +753,12 @@ def run_ours(args):
         line = {
             "metric": "BFS heuristic cells/s", "value": value, "unit": "cells/s",
             "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "int32", "data": "synthetic",
-            "config": {"workload": "C5 synthetic 1024x1024 grid, 20% obstacles, "
-                                   "4096 goals per GPU: one BFS distance field per goal",
-                       "dim": DIM, "goals_per_gpu": G, "obstacles": int(len(inst.obstacles)),
+            "config": {"workload": "C5 synthetic 1024x1024 grid, 20% obstacles, 4096 goals in total: one BFS "
+                                   "distance field per goal, sharded by goal over the GPUs, all fields "
+                                   "resident on every GPU after the step (NCCL all-gather inside the step)",
+                       "dim": DIM, "goals_total": G, "obstacles": int(len(inst.obstacles)),
                        "l2": "no flush: each step writes 17.2 GB >> 126 MB L2; the 128 KB "
                              "map bitmap is cache-resident by design"},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks,
@@ -732,6 +768,7 @@ def run_ours(args):
         print(json.dumps(line))
     if world > 1:
         dist.barrier()
+        capi.comm_destroy()
         dist.destroy_process_group()
 
 
@@ -743,7 +780,6 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--skip-conflicts", action="store_true")
     ap.add_argument("--skip-search", action="store_true")
-    ap.add_argument("--allgather", action="store_true", default=True)
     args = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if world > 1:

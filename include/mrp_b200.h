@@ -241,6 +241,56 @@ int mrp_lowlevel_batch_fs(const mrp_map* maps, int n_maps, mrp_fieldset fs,
                           int n_jobs, const mrp_lowlevel_params* params,
                           mrp_path_info* info, int32_t* out_cells, int32_t* out_g);
 
+/* ---- multi-GPU ----------------------------------------------------------
+ * One process (or host thread) per GPU, as SURVEY.md §8(e) shards the path:
+ * distance fields by goal, conflict checks by agent-pair block, replans by
+ * constraint-tree node / instance (no collective: results return to the host
+ * that owns the high-level OPEN list).  The reference has no counterpart: it is
+ * single-threaded (example/cbs.cpp:571-667).  NCCL is bound at run time
+ * (dlopen of libnccl.so.2); without it these calls fail with
+ * MRP_ERR_UNSUPPORTED and everything else works.
+ *
+ * Rank 0 makes an id (mrp_comm_unique_id), the caller hands its 128 bytes to
+ * the other ranks by any side channel (file, MPI, torch.distributed, a socket),
+ * and every rank — after mrp_init(device) — joins with mrp_comm_init_rank. */
+#define MRP_COMM_ID_BYTES 128
+int mrp_comm_unique_id(void* id128);
+int mrp_comm_init_rank(const void* id128, int n_ranks, int rank);
+/* returns 1 if a communicator exists; any out pointer may be NULL */
+int mrp_comm_info(int* rank, int* n_ranks, int* nccl_version);
+int mrp_comm_destroy(void);
+/* Distance fields sharded by goal, resident everywhere afterwards: every rank
+ * passes the same goal list; rank r computes goals [r*per, (r+1)*per), per =
+ * ceil(n_goals / n_ranks), in chunks of one wave of goals; a finished chunk is
+ * all-gathered as ONE BYTE per cell ((distance - Manhattan distance)/2, 255 =
+ * MRP_INF) on the library's second stream while the next chunk is computed,
+ * and expanded to int32 on the device: d_out[n_goals][dimx*dimy] holds every
+ * field on every rank when the stream reaches the end of the call.  If a
+ * detour does not fit a byte anywhere (all ranks agree through an all-reduce;
+ * this is the one host synchronisation of the call) the gather is repeated with
+ * int32.  Needs dimx*dimy % 16 == 0 and a 16-byte aligned d_out.  Without a
+ * communicator it is mrp_bfs_fields_dev.  This is what the cost matrix of
+ * cbs_ta reads (example/cbs_ta.cpp:272-280: getValue(start_i, goal_j) for all
+ * i, j) when the goals' fields are computed on several GPUs. */
+size_t mrp_bfs_allgather_workspace_bytes(mrp_map map, int n_goals);
+int mrp_bfs_fields_allgather_dev(mrp_map map, const int32_t* d_goal_cell, int n_goals,
+                                 int32_t* d_out, void* d_workspace, void* stream);
+/* After the stream of the last gather has finished: summed device time of its
+ * (first 64) all-gathers, the bytes those and all of them brought into this
+ * GPU, and the wire format used (1 = detour bytes, 4 = int32). */
+int mrp_comm_last_gather(double* collective_ms, long long* timed_bytes_in,
+                         long long* wire_bytes_in, int* bytes_per_cell);
+/* Conflict checks by agent-pair block: every rank holds the whole path table
+ * and sweeps every n_ranks-th 64x64 block of agent pairs (all-pairs kernel);
+ * the first-conflict keys meet in an all-reduce MIN, the counts in a SUM
+ * (order of the reference's loops, example/cbs.cpp:343-383).  d_result as in
+ * mrp_conflicts_dev, identical on every rank afterwards.  The formulation for
+ * tables beyond one GPU's hashed path (more than 4096 agents); on the C5
+ * table one GPU's hashed sweep is faster than any sharding. */
+int mrp_conflicts_sharded_dev(const int32_t* d_cell, const int32_t* d_len, int N,
+                              int Tpad, int mode, int want_first, int want_count,
+                              unsigned long long* d_result, void* stream);
+
 /* ---- instrumentation ---------------------------------------------------- */
 /* number of kernel launches issued by this library since mrp_init (bench.py's
  * `gpu_launches`) */

@@ -55,7 +55,11 @@ EXPORTS = [
     "mrp_lowlevel_batch", "mrp_launch_count", "mrp_fieldset_create",
     "mrp_fieldset_read", "mrp_fieldset_destroy", "mrp_lowlevel_batch_fs",
     "mrp_set_lane", "mrp_max_lanes", "mrp_widen_u16", "mrp_widen_u8", "mrp_bfs_d2h_bytes",
+    "mrp_comm_unique_id", "mrp_comm_init_rank", "mrp_comm_info", "mrp_comm_destroy",
+    "mrp_bfs_allgather_workspace_bytes", "mrp_bfs_fields_allgather_dev", "mrp_comm_last_gather",
+    "mrp_conflicts_sharded_dev",
 ]
+COMM_ID_BYTES = 128
 
 _lib = None
 
@@ -86,6 +90,13 @@ def lib():
                                            C.c_void_p, C.c_void_p]
         _lib.mrp_decode_conflict.argtypes = [C.c_ulonglong, C.c_int, C.c_int32,
                                              C.c_int32, C.c_void_p]
+        _lib.mrp_bfs_allgather_workspace_bytes.restype = C.c_size_t
+        _lib.mrp_bfs_allgather_workspace_bytes.argtypes = [C.c_void_p, C.c_int]
+        _lib.mrp_bfs_fields_allgather_dev.argtypes = [C.c_void_p, C.c_void_p, C.c_int,
+                                                      C.c_void_p, C.c_void_p, C.c_void_p]
+        _lib.mrp_conflicts_sharded_dev.argtypes = _lib.mrp_conflicts_dev.argtypes
+        _lib.mrp_comm_unique_id.argtypes = [C.c_void_p]
+        _lib.mrp_comm_init_rank.argtypes = [C.c_void_p, C.c_int, C.c_int]
     return _lib
 
 
@@ -121,6 +132,36 @@ def launch_count():
     return int(lib().mrp_launch_count())
 
 
+# ---- multi-GPU (one process per GPU; NCCL behind the C ABI) ----------------------
+def comm_unique_id():
+    """128 bytes made on rank 0; hand them to the other ranks by any side channel."""
+    buf = C.create_string_buffer(COMM_ID_BYTES)
+    check(lib().mrp_comm_unique_id(buf))
+    return buf.raw
+
+
+def comm_init_rank(comm_id, n_ranks, rank):
+    assert len(comm_id) == COMM_ID_BYTES
+    check(lib().mrp_comm_init_rank(C.create_string_buffer(bytes(comm_id), COMM_ID_BYTES), n_ranks, rank))
+
+
+def comm_info():
+    r, n, v = C.c_int(0), C.c_int(1), C.c_int(0)
+    have = lib().mrp_comm_info(C.byref(r), C.byref(n), C.byref(v))
+    return {"initialised": bool(have), "rank": r.value, "n_ranks": n.value, "nccl_version": v.value}
+
+
+def comm_destroy():
+    check(lib().mrp_comm_destroy())
+
+
+def comm_last_gather():
+    ms, tb, wb, fmt = C.c_double(0), C.c_longlong(0), C.c_longlong(0), C.c_int(0)
+    check(lib().mrp_comm_last_gather(C.byref(ms), C.byref(tb), C.byref(wb), C.byref(fmt)))
+    return {"collective_ms": ms.value, "timed_bytes_in": tb.value, "wire_bytes_in": wb.value,
+            "bytes_per_cell": fmt.value}
+
+
 class Map:
     """Device-resident bit-packed map (mrp_map)."""
 
@@ -148,6 +189,15 @@ class Map:
     def bfs_fields_dev(self, d_goal_cell_ptr, n_goals, d_out_ptr, d_ws_ptr, stream=0):
         check(lib().mrp_bfs_fields_dev(self.handle, d_goal_cell_ptr, n_goals,
                                        d_out_ptr, d_ws_ptr, stream))
+
+    def allgather_workspace_bytes(self, n_goals):
+        return int(lib().mrp_bfs_allgather_workspace_bytes(self.handle, n_goals))
+
+    def bfs_fields_allgather_dev(self, d_goal_cell_ptr, n_goals, d_out_ptr, d_ws_ptr, stream=0):
+        """Fields of ALL n_goals goals on every rank: computed by goal slice, gathered as detour
+        bytes over NCCL, expanded on the device (mrp_bfs_fields_allgather_dev)."""
+        check(lib().mrp_bfs_fields_allgather_dev(self.handle, d_goal_cell_ptr, n_goals,
+                                                 d_out_ptr, d_ws_ptr, stream))
 
 
 def bfs_fields(dimx, dimy, obst_xy, goal_xy, out=None):

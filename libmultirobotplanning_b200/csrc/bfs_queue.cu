@@ -428,6 +428,10 @@ __global__ void __launch_bounds__(1024, 1) bfs_queue_kernel(BfsQueueParams p) {
 #endif
 }
 
+static thread_local int t_bfsBlockCap = 0;
+void setBfsBlockCap(int blocks) { t_bfsBlockCap = blocks; }
+int bfsBlockCap() { return t_bfsBlockCap; }
+
 struct QueueGeom {
   int WPR, nOpenWords, cap, threads;
   size_t smemBytes;
@@ -529,6 +533,7 @@ int launchBfsQueue(const mrp_map_s* map, const int32_t* d_goal_cell, int n_goals
   const QueueKernel fn = queueKernelFor(map, q);
   int blocks = queueBlocks(fn, q);
   if (blocks > n_goals) blocks = n_goals;
+  if (bfsBlockCap() > 0 && blocks > bfsBlockCap()) blocks = bfsBlockCap();
   fn<<<blocks, q.threads, q.smemBytes, st>>>(p);
   countLaunch();
   MRP_CUDA(cudaGetLastError());

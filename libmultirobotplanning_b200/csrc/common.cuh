@@ -137,6 +137,10 @@ int launchBfsQueue(const mrp_map_s* map, const int32_t* d_goal_cell,
                    int n_goals, int32_t* d_out, void* d_ws, cudaStream_t st,
                    const uint32_t* d_goalList = nullptr,
                    const uint32_t* d_goalListCount = nullptr);
+// caps the CTAs of the next BFS launches of the calling thread (0 = no cap):
+// the sharded gather (multi.cu) leaves a few SMs to the collective
+void setBfsBlockCap(int blocks);
+int bfsBlockCap();
 bool bfsSweepFits(const mrp_map_s* map);
 size_t bfsSweepWorkspaceWords(int n_goals);
 int launchBfsSweep(const mrp_map_s* map, const int32_t* d_goal_cell,
@@ -146,6 +150,10 @@ int launchConflicts(const int32_t* d_cell, const int32_t* d_len, int N,
                     int Tpad, int mode, bool wantFirst, bool wantCount,
                     unsigned long long* d_result, void* d_ws, size_t wsBytes,
                     cudaStream_t st);
+int launchConflictsPairShard(const int32_t* d_cell, const int32_t* d_len, int N,
+                             int Tpad, int mode, bool wantFirst, bool wantCount,
+                             unsigned long long* d_result, int shard, int nShards,
+                             cudaStream_t st);
 int launchConflictsBatch(const int32_t* d_cell, const int32_t* d_len, int B,
                          int N, int Tpad, int mode,
                          unsigned long long* d_result, cudaStream_t st);

@@ -71,7 +71,8 @@ template <bool kFirst, bool kCount>
 __global__ void __launch_bounds__(256)
 conflict_pairs_kernel(const int32_t* __restrict__ cellAll,
                       const int32_t* __restrict__ lenAll, int N, int Tpad,
-                      int mode, int nb, unsigned long long* __restrict__ resultAll) {
+                      int mode, int nb, unsigned long long* __restrict__ resultAll,
+                      int shard, int nShards) {
   __shared__ int32_t sA[kPB * kStride];
   __shared__ int32_t sB[kPB * kStride];
   __shared__ int sCount[8];
@@ -92,8 +93,11 @@ conflict_pairs_kernel(const int32_t* __restrict__ cellAll,
   }
   const int tEnd = min(t0 + kTC, max_t);  // timesteps [t0, tEnd)
 
-  // upper-triangular block index -> (bi, bj), bi <= bj
-  int bi = 0, rem = blockIdx.x;
+  // upper-triangular block index -> (bi, bj), bi <= bj; with nShards > 1 the
+  // agent-pair blocks are dealt round-robin and this launch sweeps every
+  // nShards-th one (multi-GPU: conflict checks by agent-pair block)
+  int bi = 0, rem = blockIdx.x * nShards + shard;
+  if (rem >= nb * (nb + 1) / 2) return;
   while (rem >= nb - bi) {
     rem -= nb - bi;
     ++bi;
@@ -648,22 +652,22 @@ __global__ void focal_counts_kernel(const int32_t* __restrict__ cell,
 
 static int launchPairs(const int32_t* d_cell, const int32_t* d_len, int B, int N,
                        int Tpad, int mode, bool wantFirst, bool wantCount,
-                       unsigned long long* d_result, cudaStream_t st) {
+                       unsigned long long* d_result, cudaStream_t st, int shard = 0, int nShards = 1) {
   conflict_prep_kernel<<<B, 256, 0, st>>>(d_len, N, d_result);
   countLaunch();
   const int nb = (N + kPB - 1) / kPB;
-  const int nPairBlocks = nb * (nb + 1) / 2;
+  const int nPairBlocks = (nb * (nb + 1) / 2 + nShards - 1) / nShards;
   const int chunks = (Tpad + kTC - 1) / kTC;
   dim3 grid(nPairBlocks, chunks, B);
   if (wantFirst && wantCount)
     conflict_pairs_kernel<true, true><<<grid, 256, 0, st>>>(d_cell, d_len, N, Tpad,
-                                                            mode, nb, d_result);
+                                                            mode, nb, d_result, shard, nShards);
   else if (wantFirst)
     conflict_pairs_kernel<true, false><<<grid, 256, 0, st>>>(d_cell, d_len, N, Tpad,
-                                                             mode, nb, d_result);
+                                                             mode, nb, d_result, shard, nShards);
   else
     conflict_pairs_kernel<false, true><<<grid, 256, 0, st>>>(d_cell, d_len, N, Tpad,
-                                                             mode, nb, d_result);
+                                                             mode, nb, d_result, shard, nShards);
   countLaunch();
   MRP_CUDA(cudaGetLastError());
   return 0;
@@ -745,6 +749,14 @@ int launchConflicts(const int32_t* d_cell, const int32_t* d_len, int N, int Tpad
     MRP_CUDA(cudaGetLastError());
     return 0;
   }
+}
+
+// this rank's share of the agent-pair blocks of one table (all-pairs kernel);
+// the ranks' results meet in an all-reduce (multi.cu)
+int launchConflictsPairShard(const int32_t* d_cell, const int32_t* d_len, int N, int Tpad, int mode,
+                             bool wantFirst, bool wantCount, unsigned long long* d_result, int shard,
+                             int nShards, cudaStream_t st) {
+  return launchPairs(d_cell, d_len, 1, N, Tpad, mode, wantFirst, wantCount, d_result, st, shard, nShards);
 }
 
 int launchConflictsBatch(const int32_t* d_cell, const int32_t* d_len, int B,
