@@ -104,6 +104,23 @@ int mrp_widen_u16(const uint16_t* src, int32_t* dst, size_t n, int threads);
  * 2*src + |x - gx_k| + |y - gy_k|, goal_cell[k] = gx_k + dimx*gy_k. */
 int mrp_widen_u8(const uint8_t* src, int32_t* dst, int dimx, int dimy,
                  const int32_t* goal_cell, int n_fields, int threads);
+/* The packed RESULT mode: the same fields, handed to the caller as one byte per
+ * cell instead of int32 — out[g][x + dimx*y] = (distance - (|x-gx| + |y-gy|)) / 2,
+ * 255 = MRP_INF — copied straight into `out` (use page-locked memory), a quarter
+ * of the bytes over PCIe and no expansion on the host.  mrp_packed_value() below
+ * is ShortestPathHeuristic::getValue (example/shortest_path_heuristic.hpp:58-62)
+ * on such a field.  A field with a detour of 510 steps or more (mazes) does not
+ * fit: the call returns the number of such goals (0 = all fine) and marks them
+ * in overflowed[n_goals] (may be NULL); recompute those with mrp_bfs_fields. */
+int mrp_bfs_fields_packed(int dimx, int dimy, const int32_t* obst_xy, int n_obst,
+                          const int32_t* goal_xy, int n_goals, uint8_t* out,
+                          int32_t* overflowed);
+static inline int32_t mrp_packed_value(const uint8_t* field, int dimx, int x, int y,
+                                       int gx, int gy) {
+  const uint8_t b = field[x + dimx * y];
+  if (b == 255) return MRP_INF;
+  return 2 * (int32_t)b + (x > gx ? x - gx : gx - x) + (y > gy ? y - gy : gy - y);
+}
 /* Bytes the last mrp_bfs_fields call moved from the device to the host
  * (bench.py's `d2h_bytes_per_step`). */
 long long mrp_bfs_d2h_bytes(void);

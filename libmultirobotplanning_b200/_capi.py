@@ -57,7 +57,7 @@ EXPORTS = [
     "mrp_set_lane", "mrp_max_lanes", "mrp_widen_u16", "mrp_widen_u8", "mrp_bfs_d2h_bytes",
     "mrp_comm_unique_id", "mrp_comm_init_rank", "mrp_comm_info", "mrp_comm_destroy",
     "mrp_bfs_allgather_workspace_bytes", "mrp_bfs_fields_allgather_dev", "mrp_comm_last_gather",
-    "mrp_conflicts_sharded_dev",
+    "mrp_conflicts_sharded_dev", "mrp_bfs_fields_packed",
 ]
 COMM_ID_BYTES = 128
 
@@ -207,6 +207,31 @@ def bfs_fields(dimx, dimy, obst_xy, goal_xy, out=None):
         out = np.empty((len(goals), dimy * dimx), np.int32)
     check(lib().mrp_bfs_fields(dimx, dimy, _p(obst), len(obst), _p(goals),
                                len(goals), _p(out)))
+    return out
+
+
+def bfs_fields_packed(dimx, dimy, obst_xy, goal_xy, out=None):
+    """One detour byte per cell, (distance - Manhattan) / 2, 255 = INF (mrp_bfs_fields_packed).
+    Returns (bytes [n][cells], overflowed [n])."""
+    obst = _i32(obst_xy).reshape(-1, 2)
+    goals = _i32(goal_xy).reshape(-1, 2)
+    if out is None:
+        out = np.empty((len(goals), dimy * dimx), np.uint8)
+    ovf = np.zeros(len(goals), np.int32)
+    check(lib().mrp_bfs_fields_packed(dimx, dimy, _p(obst), len(obst), _p(goals), len(goals),
+                                      _p(out), _p(ovf)))
+    return out, ovf
+
+
+def unpack_field(packed, dimx, dimy, goal_xy):
+    """numpy mirror of mrp_packed_value over whole fields: int32 [n][cells]."""
+    goals = _i32(goal_xy).reshape(-1, 2)
+    yy, xx = np.mgrid[0:dimy, 0:dimx]
+    out = np.empty((len(goals), dimy * dimx), np.int32)
+    for k, (gx, gy) in enumerate(goals):
+        m = (np.abs(xx - gx) + np.abs(yy - gy)).reshape(-1)
+        b = packed[k].astype(np.int32)
+        out[k] = np.where(b == 255, INF, 2 * b + m)
     return out
 
 

@@ -87,7 +87,7 @@ struct Lane {
   Context c;
   std::mutex m;
   Scratch scratch[16];
-  PinnedScratch pinned[4];
+  PinnedScratch pinned[6];
   LaneLL ll;
 };
 static Lane g_lanes[kMaxLanes];
@@ -724,6 +724,105 @@ int mrp_bfs_fields(int dimx, int dimy, const int32_t* obst_xy, int n_obst,
   }
   mrp_map_destroy(map);
   return rc;
+}
+
+// The packed result mode: one detour byte per cell, copied straight into the
+// caller's buffer (no host expansion); see include/mrp_b200.h.
+int mrp_bfs_fields_packed(int dimx, int dimy, const int32_t* obst_xy, int n_obst,
+                          const int32_t* goal_xy, int n_goals, uint8_t* out, int32_t* overflowed) {
+  MRP_CHECK(n_goals >= 0, MRP_ERR_INVALID, "n_goals < 0");
+  MRP_CHECK(n_goals == 0 || (goal_xy && out), MRP_ERR_INVALID, "NULL pointer");
+  if (int rc = validateGoals(dimx, dimy, goal_xy, n_goals)) return rc;
+  if (overflowed) std::memset(overflowed, 0, sizeof(int32_t) * (size_t)n_goals);
+  if (n_goals == 0) return 0;
+  mrp_map map = nullptr;
+  if (int rc = mrp_map_create(dimx, dimy, obst_xy, n_obst, &map)) return rc;
+  int rc = 0, nOverflowed = 0;
+  {
+    std::lock_guard<std::mutex> lk(apiMutex());
+    Context& c = ctx();
+    const size_t cells = (size_t)dimx * dimy;
+    std::vector<int32_t> goalCell(n_goals);
+    for (int k = 0; k < n_goals; ++k) goalCell[k] = goal_xy[2 * k] + dimx * goal_xy[2 * k + 1];
+    size_t batch = std::max<size_t>((size_t)c.smCount, ((size_t)1 << 26) / cells);
+    if (envInt("MRP_BFS_BATCH", 0) > 0) batch = (size_t)envInt("MRP_BFS_BATCH", 0);  // tests
+    batch = std::min<size_t>(batch, (size_t)n_goals);
+    const size_t nBatches = ((size_t)n_goals + batch - 1) / batch;
+    const size_t wsBytes = (map->W == 1 && map->S == 1) ? 16 * batch + 256
+                                                        : bfsLargeWorkspaceBytes(map, (int)batch);
+    const size_t slotBytes = ((batch * cells + 255) & ~(size_t)255) + 256;
+    int32_t *d_goals = nullptr, *d_out = nullptr;
+    char *wsp = nullptr, *d_pack = nullptr;
+    void* h_flags = nullptr;
+    cudaEvent_t done[2] = {nullptr, nullptr}, copied[2] = {nullptr, nullptr};
+    g_bfsD2hBytes = 0;
+    do {
+      if ((rc = scratch(0, (size_t)n_goals, &d_goals))) break;
+      if ((rc = scratch(1, batch * cells, &d_out))) break;
+      if ((rc = scratch(3, wsBytes, &wsp))) break;
+      if ((rc = scratch(4, 2 * slotBytes, &d_pack))) break;
+      if ((rc = pinnedScratch(4, nBatches * sizeof(int), &h_flags))) break;
+      cudaError_t e = cudaMemcpyAsync(d_goals, goalCell.data(), (size_t)n_goals * 4,
+                                      cudaMemcpyHostToDevice, c.stream);
+      if (e != cudaSuccess) {
+        rc = fail(MRP_ERR_CUDA, "H2D copy failed: %s", cudaGetErrorString(e));
+        break;
+      }
+      for (int b = 0; b < 2; ++b) {
+        cudaEventCreateWithFlags(&done[b], cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&copied[b], cudaEventDisableTiming);
+      }
+      for (size_t j = 0; j < nBatches && rc == 0; ++j) {
+        const int sl = (int)(j & 1);
+        const size_t g0 = j * batch, n = std::min(batch, (size_t)n_goals - g0);
+        rc = bfsFieldsDevLocked(map, d_goals + g0, (int)n, d_out, wsp, c.stream);
+        if (rc) break;
+        char* dslot = d_pack + (size_t)sl * slotBytes;
+        int* dflag = reinterpret_cast<int*>(dslot + slotBytes - 256);
+        cudaStreamWaitEvent(c.stream, copied[sl], 0);  // the slot's previous batch has left
+        cudaMemsetAsync(dflag, 0, sizeof(int), c.stream);
+        const size_t total = n * cells;
+        const int grid = (int)std::min<size_t>((total / 8 + 255) / 256 + 1, (size_t)c.smCount * 16);
+        if (map->dimx % 16 == 0)
+          pack_fields_u8_kernel<true><<<grid, 256, 0, c.stream>>>(
+              d_out, reinterpret_cast<uint8_t*>(dslot), total, map->dimx, (int)cells, d_goals + g0, dflag);
+        else
+          pack_fields_u8_kernel<false><<<grid, 256, 0, c.stream>>>(
+              d_out, reinterpret_cast<uint8_t*>(dslot), total, map->dimx, (int)cells, d_goals + g0, dflag);
+        countLaunch();
+        cudaEventRecord(done[sl], c.stream);
+        cudaStreamWaitEvent(c.copyStream, done[sl], 0);
+        e = cudaMemcpyAsync(out + g0 * cells, dslot, total, cudaMemcpyDeviceToHost, c.copyStream);
+        if (e == cudaSuccess)
+          e = cudaMemcpyAsync(static_cast<int*>(h_flags) + j, dflag, sizeof(int), cudaMemcpyDeviceToHost,
+                              c.copyStream);
+        if (e != cudaSuccess) {
+          rc = fail(MRP_ERR_CUDA, "D2H copy failed: %s", cudaGetErrorString(e));
+          break;
+        }
+        g_bfsD2hBytes += (long long)total;
+        cudaEventRecord(copied[sl], c.copyStream);
+      }
+      cudaError_t e1 = cudaStreamSynchronize(c.stream);
+      cudaError_t e2 = cudaStreamSynchronize(c.copyStream);
+      if (rc == 0 && (e1 != cudaSuccess || e2 != cudaSuccess))
+        rc = fail(MRP_ERR_CUDA, "bfs fields failed: %s", cudaGetErrorString(e1 != cudaSuccess ? e1 : e2));
+      if (rc == 0)
+        for (size_t j = 0; j < nBatches; ++j)
+          if (static_cast<const int*>(h_flags)[j]) {
+            const size_t g0 = j * batch, n = std::min(batch, (size_t)n_goals - g0);
+            nOverflowed += (int)n;
+            if (overflowed)
+              for (size_t k = 0; k < n; ++k) overflowed[g0 + k] = 1;
+          }
+    } while (0);
+    for (int b = 0; b < 2; ++b) {
+      if (done[b]) cudaEventDestroy(done[b]);
+      if (copied[b]) cudaEventDestroy(copied[b]);
+    }
+  }
+  mrp_map_destroy(map);
+  return rc ? rc : nOverflowed;
 }
 
 long long mrp_bfs_d2h_bytes(void) { return g_bfsD2hBytes.load(); }

@@ -256,3 +256,28 @@ def test_device_entry_point(capi, orc):
     goals = np.stack([cells % dimx, cells // dimx], 1)
     assert np.array_equal(d_out.cpu().numpy(), orc.bfs_fields(dimx, dimy, obst, goals))
     m.close()
+
+
+def test_packed_result_mode(capi, orc):
+    """mrp_bfs_fields_packed: one detour byte per cell, decoded with the accessor formula of
+    mrp_packed_value (2*b + |x-gx| + |y-gy|, 255 = INF) == the oracle's int fields; a maze whose
+    detours do not fit a byte is reported per goal."""
+    rng = np.random.default_rng(11)
+    for dimx, dimy, density, batch in [(300, 200, 0.2, None), (1024, 96, 0.2, "3"), (33, 45, 0.3, "2")]:
+        obst = _rand_map(rng, dimx, dimy, density)
+        cells = rng.choice(dimx * dimy, 7, replace=False)
+        goals = np.stack([cells % dimx, cells // dimx], 1)
+        env = {"MRP_BFS_BATCH": batch} if batch else {}
+        packed, ovf = _with_env(env, lambda: capi.bfs_fields_packed(dimx, dimy, obst, goals))
+        assert ovf.sum() == 0
+        want = orc.bfs_fields(dimx, dimy, obst, goals)
+        assert np.array_equal(capi.unpack_field(packed, dimx, dimy, goals), want)
+    # serpentine corridor: detours far beyond 2 * 254
+    dimx, dimy = 96, 67
+    obst = []
+    for y in range(1, dimy, 2):
+        gap = dimx - 1 if (y // 2) % 2 == 0 else 0
+        obst += [[x, y] for x in range(dimx) if x != gap]
+    goals = [[0, 0], [dimx - 1, dimy - 1], [40, 20]]
+    packed, ovf = capi.bfs_fields_packed(dimx, dimy, obst, goals)
+    assert ovf.all()
