@@ -217,7 +217,7 @@ __device__ __forceinline__ void appendWinners(uint32_t oU, uint32_t oD, uint32_t
 // e = (y + 1) * 32 * WPR + (x + 1): word = e >> 5, bit = e & 31, the four
 // neighbours are e -+ 32*WPR and e -+ 1, and the field index follows from
 // e - (e / (32*WPR)) * (32*WPR - dimx).
-template <int kWPR, int kDimX>
+template <int kWPR, int kDimX, bool kList>
 __global__ void __launch_bounds__(1024, 1) bfs_queue_kernel(BfsQueueParams p) {
   extern __shared__ uint32_t smem[];
   __shared__ int sCount[3];
@@ -266,9 +266,10 @@ __global__ void __launch_bounds__(1024, 1) bfs_queue_kernel(BfsQueueParams p) {
     __syncthreads();
     if (tid == 0) sGoal = (int)atomicAdd(p.ws, 1u);
     __syncthreads();
-    const int nWork = p.goalList ? (int)*p.goalListCount : p.n_goals;
+    // kList: the goals another kernel handed over (indices into goals[] / out[])
+    const int nWork = kList ? (int)*p.goalListCount : p.n_goals;
     if (sGoal >= nWork) break;
-    const int gidx = p.goalList ? (int)p.goalList[sGoal] : sGoal;
+    const int gidx = kList ? (int)p.goalList[sGoal] : sGoal;
 #ifdef MRP_BFS_TIMING
     if (blockIdx.x == 0 && tid == 0) g_bfsqLevels[0][0] = (unsigned)clock64();
 #endif
@@ -477,14 +478,15 @@ typedef void (*QueueKernel)(BfsQueueParams);
 
 // the instance for this map: row strides as immediates for the power-of-two
 // widths of the synthetic configurations, run-time strides for everything else
-static QueueKernel queueKernelFor(const mrp_map_s* map, const QueueGeom& q) {
+static QueueKernel queueKernelFor(const mrp_map_s* map, const QueueGeom& q, bool list) {
+  if (list) return bfs_queue_kernel<0, 0, true>;  // hand-over path: run-time strides
   if (!getenv("MRP_BFS_GENERIC")) {
-    if (map->dimx == 1024 && q.WPR == 33) return bfs_queue_kernel<33, 1024>;
-    if (map->dimx == 512 && q.WPR == 17) return bfs_queue_kernel<17, 512>;
-    if (map->dimx == 256 && q.WPR == 9) return bfs_queue_kernel<9, 256>;
-    if (map->dimx == 2048 && q.WPR == 65) return bfs_queue_kernel<65, 2048>;
+    if (map->dimx == 1024 && q.WPR == 33) return bfs_queue_kernel<33, 1024, false>;
+    if (map->dimx == 512 && q.WPR == 17) return bfs_queue_kernel<17, 512, false>;
+    if (map->dimx == 256 && q.WPR == 9) return bfs_queue_kernel<9, 256, false>;
+    if (map->dimx == 2048 && q.WPR == 65) return bfs_queue_kernel<65, 2048, false>;
   }
-  return bfs_queue_kernel<0, 0>;
+  return bfs_queue_kernel<0, 0, false>;
 }
 
 static int queueBlocks(QueueKernel fn, const QueueGeom& q) {
@@ -530,7 +532,7 @@ int launchBfsQueue(const mrp_map_s* map, const int32_t* d_goal_cell, int n_goals
   p.tma = tma ? atoi(tma) : 1;
   if ((reinterpret_cast<uintptr_t>(map->d_rowbits) & 15) != 0) p.tma = 0;
   MRP_CUDA(cudaMemsetAsync(d_ws, 0, 64 * 4, st));
-  const QueueKernel fn = queueKernelFor(map, q);
+  const QueueKernel fn = queueKernelFor(map, q, d_goalList != nullptr);
   int blocks = queueBlocks(fn, q);
   if (blocks > n_goals) blocks = n_goals;
   if (bfsBlockCap() > 0 && blocks > bfsBlockCap()) blocks = bfsBlockCap();
