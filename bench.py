@@ -94,6 +94,35 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def bind_to_gpu_numa(index, local_rank, ranks_on_node):
+    """Binds this process (and the page-locked buffers it allocates from now on) to the host cores
+    next to its GPU: /sys/bus/pci/devices/<gpu>/local_cpulist, divided among the ranks that share
+    that list.  Eight ranks that leave this to chance put most of their staging memory on one
+    socket.  Returns a description for the JSON line."""
+    try:
+        import torch
+        pr = torch.cuda.get_device_properties(index)
+        bdf = "%04x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+        with open("/sys/bus/pci/devices/%s/local_cpulist" % bdf) as f:
+            txt = f.read().strip()
+        cpus = []
+        for part in txt.split(","):
+            a, _, b = part.partition("-")
+            cpus += list(range(int(a), int(b or a) + 1))
+        allowed = sorted(set(cpus) & set(os.sched_getaffinity(0)))
+        if not allowed:
+            return "no local cpulist"
+        # ranks whose GPUs share this list take consecutive slices of it
+        sharers = max(1, min(ranks_on_node, int(round(ranks_on_node * len(allowed) / max(1, os.cpu_count())))))
+        k = local_rank % sharers
+        per = max(1, len(allowed) // sharers)
+        mine = allowed[k * per:(k + 1) * per] or allowed
+        os.sched_setaffinity(0, mine)
+        return "gpu %s: cores %d-%d of %s" % (bdf, mine[0], mine[-1], txt)
+    except Exception as e:  # not fatal: the run is just not bound
+        return "not bound (%s)" % e
+
+
 def c5_instance(n_ranks):
     from libmultirobotplanning_b200 import instances
     return instances.synthetic_c5(dim=DIM, n_agents=GOALS_PER_GPU * n_ranks)
@@ -446,6 +475,7 @@ def run_ours(args):
     else:
         torch.cuda.set_device(0)
     dev = torch.device("cuda", local if world > 1 else 0)
+    numa = bind_to_gpu_numa(dev.index, local, world) if world > 1 else "single rank: not bound"
     capi.init(dev.index)
 
     if world > 1:
@@ -797,7 +827,7 @@ def run_ours(args):
                        "l2": "no flush: each step writes 17.2 GB >> 126 MB L2; the 128 KB "
                              "map bitmap is cache-resident by design"},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks,
-            "gpu_launches": int(launches), "also": also,
+            "gpu_launches": int(launches), "host_binding": numa, "also": also,
             "device": capi.device_info(),
         }
         print(json.dumps(line))

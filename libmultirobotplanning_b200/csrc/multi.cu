@@ -83,9 +83,11 @@ NcclApi& nccl() {
 struct Comm {
   ncclComm_t comm = nullptr;
   int rank = 0, nRanks = 1, device = -1;
-  cudaStream_t stream = nullptr;  // collectives + expansion of received chunks
+  cudaStream_t stream = nullptr;   // collectives
+  cudaStream_t xstream = nullptr;  // expansion of received chunks (overlaps the next collective)
   cudaEvent_t packed[2] = {nullptr, nullptr};    // chunk is packed (compute stream)
-  cudaEvent_t expanded[2] = {nullptr, nullptr};  // chunk is gathered and expanded (comm stream)
+  cudaEvent_t gathered[2] = {nullptr, nullptr};  // chunk has arrived (collective stream)
+  cudaEvent_t expanded[2] = {nullptr, nullptr};  // chunk is expanded (expansion stream)
   static constexpr int kTimed = 64;              // collectives of a call that are timed
   cudaEvent_t tc[2 * kTimed] = {};               // around each collective of the last call
   int nTimed = 0;
@@ -186,12 +188,12 @@ int gatherSpareSms() {
   return e ? std::max(0, atoi(e)) : 16;
 }
 
-// goals per chunk: two waves of the queue kernel on the SMs it is given (measured at
-// 2 GPUs, 2048 goals: one wave / 8 spare SMs 11.3 ms, two waves / 16 spare SMs 11.1 ms,
-// a single chunk without overlap 11.9 ms)
+// goals per chunk: one wave of the queue kernel on the SMs it is given (measured, 4096
+// goals over 8 GPUs: one wave / 16 spare SMs 13.4 ms, two waves 14.7 ms, a single chunk
+// without overlap 14.4 ms; 2048 goals over 2 GPUs: 11.3 / 11.1 / 11.9 ms)
 int chunkGoals() {
   const char* e = getenv("MRP_GATHER_CHUNK");
-  return e ? std::max(1, atoi(e)) : 2 * std::max(1, ctx().smCount - gatherSpareSms());
+  return e ? std::max(1, atoi(e)) : std::max(1, ctx().smCount - gatherSpareSms());
 }
 
 struct GatherPlan {
@@ -245,7 +247,9 @@ int mrp_comm_init_rank(const void* id128, int n_ranks, int rank) {
   g_comm.nRanks = n_ranks;
   g_comm.device = ctx().device;
   MRP_CUDA(cudaStreamCreateWithFlags(&g_comm.stream, cudaStreamNonBlocking));
+  MRP_CUDA(cudaStreamCreateWithFlags(&g_comm.xstream, cudaStreamNonBlocking));
   for (int i = 0; i < 2; ++i) {
+    MRP_CUDA(cudaEventCreateWithFlags(&g_comm.gathered[i], cudaEventDisableTiming));
     MRP_CUDA(cudaEventCreateWithFlags(&g_comm.packed[i], cudaEventDisableTiming));
     MRP_CUDA(cudaEventCreateWithFlags(&g_comm.expanded[i], cudaEventDisableTiming));
   }
@@ -268,9 +272,12 @@ int mrp_comm_destroy(void) {
   if (!g_comm.comm) return 0;
   cudaSetDevice(g_comm.device);
   cudaStreamSynchronize(g_comm.stream);
+  cudaStreamSynchronize(g_comm.xstream);
   nccl().commDestroy(g_comm.comm);
   cudaStreamDestroy(g_comm.stream);
+  cudaStreamDestroy(g_comm.xstream);
   for (int i = 0; i < 2; ++i) {
+    cudaEventDestroy(g_comm.gathered[i]);
     cudaEventDestroy(g_comm.packed[i]);
     cudaEventDestroy(g_comm.expanded[i]);
   }
@@ -329,6 +336,8 @@ static int gatherPass(const mrp_map_s* map, const int32_t* d_goal_cell, int nGoa
     }
     MRP_CUDA(cudaEventRecord(c.packed[b], st));
     MRP_CUDA(cudaStreamWaitEvent(c.stream, c.packed[b], 0));
+    // the receive buffer of chunk k - 2 must have been expanded
+    if (k >= 2) MRP_CUDA(cudaStreamWaitEvent(c.stream, c.expanded[b], 0));
     const bool timed = c.nTimed < Comm::kTimed;
     if (timed) MRP_CUDA(cudaEventRecord(c.tc[2 * c.nTimed], c.stream));
     MRP_NCCL(nccl().allGather(src, recv[b], chunkWire, ncclUint8, c.comm, c.stream));
@@ -338,15 +347,17 @@ static int gatherPass(const mrp_map_s* map, const int32_t* d_goal_cell, int nGoa
       c.timedBytesWire += (long long)chunkWire * (c.nRanks - 1);
       ++c.nTimed;
     }
+    MRP_CUDA(cudaEventRecord(c.gathered[b], c.stream));
+    MRP_CUDA(cudaStreamWaitEvent(c.xstream, c.gathered[b], 0));
     const dim3 eg(gx16, c.nRanks * g.chunk);
     if (fmt == 1)
-      expand_u8_kernel<<<eg, 256, 0, c.stream>>>(reinterpret_cast<const uint8_t*>(recv[b]), d_out, map->dimx, cells,
-                                                d_goal_cell, nGoals, g.perRank, first, g.chunk, c.rank);
+      expand_u8_kernel<<<eg, 256, 0, c.xstream>>>(reinterpret_cast<const uint8_t*>(recv[b]), d_out, map->dimx, cells,
+                                                 d_goal_cell, nGoals, g.perRank, first, g.chunk, c.rank);
     else
-      place_i32_kernel<<<eg, 256, 0, c.stream>>>(reinterpret_cast<const int32_t*>(recv[b]), d_out, cells, nGoals,
-                                                g.perRank, first, g.chunk, c.rank);
+      place_i32_kernel<<<eg, 256, 0, c.xstream>>>(reinterpret_cast<const int32_t*>(recv[b]), d_out, cells, nGoals,
+                                                 g.perRank, first, g.chunk, c.rank);
     countLaunch();
-    MRP_CUDA(cudaEventRecord(c.expanded[b], c.stream));
+    MRP_CUDA(cudaEventRecord(c.expanded[b], c.xstream));
   }
   // the caller's stream continues when everything is in place
   MRP_CUDA(cudaStreamWaitEvent(st, c.expanded[(g.nChunks - 1) & 1], 0));

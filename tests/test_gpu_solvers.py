@@ -353,3 +353,81 @@ def test_lanes_concurrent_calls(capi):
     for t in th:
         t.join()
     assert not errors, errors
+
+
+def test_sweep_binary_streams_yaml_files(capi, set8, tmp_path):
+    """bin/mapf_sweep: the benchmark sweep as one streaming run (reader thread + batched driver).
+    Same costs as the batch API on 60 files of the 8x8 set, output.yaml per solved file in the
+    reference's layout (example/cbs.cpp:637-661)."""
+    from libmultirobotplanning_b200 import instances as I
+    from libmultirobotplanning_b200 import solver
+    insts = [i for i in set8 if i.n_agents <= 6][:60]
+    files = []
+    for i in insts:
+        p = str(tmp_path / (i.name + ".yaml"))
+        I.save_yaml(i, p)
+        files.append(p)
+    lst = tmp_path / "files.txt"
+    lst.write_text("\n".join(files) + "\n")
+    outdir = tmp_path / "out"
+    outdir.mkdir()
+    csv = tmp_path / "res.csv"
+    r = subprocess.run([os.path.join(BIN, "mapf_sweep"), "--algo", "cbs", "--batch", "16", "--maxHighLevelExpansions",
+                        "2000", "--outputDir", str(outdir), "--csv", str(csv), "--list", str(lst)],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-500:]
+    rows = [l.split(",") for l in csv.read_text().strip().splitlines()[1:]]
+    assert [row[0] for row in rows] == files
+    want = solver.solve_batch(solver.CBS, insts, max_hl=2000)
+    for row, w, i in zip(rows, want, insts):
+        assert int(row[1]) == w["status"], i.name
+        if w["status"] == 0:
+            assert int(row[2]) == w["cost"] and int(row[3]) == w["makespan"], i.name
+            y = yaml.safe_load((outdir / (i.name + ".output.yaml")).read_text())
+            assert y["statistics"]["cost"] == w["cost"]
+            assert sorted(y["schedule"]) == sorted("agent%d" % a for a in range(i.n_agents))
+
+
+def test_output_yaml_replays_like_visualize_py(capi, set32, tmp_path):
+    """The schedule our `cbs` writes, consumed the way the reference's example/visualize.py consumes it
+    (matplotlib is not in this image, so its accesses are replayed): schedule["schedule"][agent name]
+    for every agent of the input (visualize.py:57-63), T = max last t (:63), getState's linear
+    interpolation between consecutive entries (:113-127) for the frames i/10 (:100-104), and its
+    agent-agent collision test ||p1 - p2|| < 0.7 (:111-123), which must never fire on a CBS solution."""
+    from libmultirobotplanning_b200 import instances as I
+    inst = next(i for i in set32 if i.name == "map_32by32_obst204_agents10_ex1")
+    inp, outp = str(tmp_path / "in.yaml"), str(tmp_path / "out.yaml")
+    I.save_yaml(inst, inp)
+    r = subprocess.run([os.path.join(BIN, "cbs"), "-i", inp, "-o", outp], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "Planning successful!" in r.stdout
+    with open(inp) as f:
+        mp = yaml.safe_load(f)
+    with open(outp) as f:
+        schedule = yaml.safe_load(f)
+    names = [d["name"] for d in mp["agents"]]
+    T = 0
+    for d in mp["agents"]:
+        s = schedule["schedule"][d["name"]]            # KeyError here = visualize.py would crash
+        assert (s[0]["x"], s[0]["y"], s[0]["t"]) == (d["start"][0], d["start"][1], 0)
+        assert (s[-1]["x"], s[-1]["y"]) == tuple(d["goal"])
+        assert all(b["t"] > a["t"] for a, b in zip(s, s[1:]))  # dt != 0 in getState
+        T = max(T, s[-1]["t"])
+    assert T == schedule["statistics"]["makespan"]
+
+    def get_state(t, d):
+        idx = 0
+        while idx < len(d) and d[idx]["t"] < t:
+            idx += 1
+        if idx == 0:
+            return np.array([float(d[0]["x"]), float(d[0]["y"])])
+        if idx < len(d):
+            last = np.array([float(d[idx - 1]["x"]), float(d[idx - 1]["y"])])
+            nxt = np.array([float(d[idx]["x"]), float(d[idx]["y"])])
+            dt = d[idx]["t"] - d[idx - 1]["t"]
+            return (nxt - last) * ((t - d[idx - 1]["t"]) / dt) + last
+        return np.array([float(d[-1]["x"]), float(d[-1]["y"])])
+    for i in range(int(T + 1) * 10):
+        pos = np.array([get_state(i / 10, schedule["schedule"][n]) for n in names])
+        assert (pos >= -0.5).all() and (pos[:, 0] <= inst.dimx - 0.5).all() and (pos[:, 1] <= inst.dimy - 0.5).all()
+        dist = np.linalg.norm(pos[:, None, :] - pos[None, :, :], axis=2) + 10 * np.eye(len(names))
+        assert dist.min() >= 0.7, "visualize.py would print COLLISION at frame %d" % i
