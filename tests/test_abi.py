@@ -13,7 +13,9 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 def _declared_symbols():
     text = open(os.path.join(ROOT, "include", "mrp_b200.h")).read()
     text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
-    return sorted(set(re.findall(r"\b(mrp_[a-z0-9_]+)\s*\(", text)))
+    # header-only helpers (static inline) are not exported symbols
+    inline = set(re.findall(r"static\s+inline\s+[^;{(]*?\b(mrp_[a-z0-9_]+)\s*\(", text))
+    return sorted(set(re.findall(r"\b(mrp_[a-z0-9_]+)\s*\(", text)) - inline)
 
 
 def test_header_symbols_exported():
