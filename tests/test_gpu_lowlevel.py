@@ -164,3 +164,85 @@ def test_lowlevel_edge_cases(capi):
                             max_expanded=50)
     assert r[0]["status"] == 2
     assert capi.lowlevel_batch([m], f, []) == []
+
+
+def _same_results(a, b):
+    assert len(a) == len(b)
+    for k, (x, y) in enumerate(zip(a, b)):
+        for key in ("status", "cost", "fmin", "expanded"):
+            assert x[key] == y[key], (k, key, x[key], y[key])
+        if x["status"] == 0:
+            assert np.array_equal(x["cells"], y["cells"]), k
+            assert np.array_equal(x["g"], y["g"]), k
+
+
+@pytest.mark.parametrize("dims", [(8, 8), (32, 32), (20, 13), (32, 9)])
+def test_tile_kernel_equals_general_kernel(capi, dims, monkeypatch):
+    """Single-tile maps with cbs/ecbs moves run in the shared-memory kernel
+    (lowlevel_tile.cu); MRP_LL_GENERIC=1 sends the same jobs through the general kernel.
+    Same selection rule, tie-breaking and node numbering: status, cost, fmin, the number
+    of expansions and every path must be identical, for A* and for A*-epsilon with the
+    occupancy planes, with the exact focal pass only (MRP_LL_TILE_NOOCC), and when the
+    visited bitmap is too short (MRP_LL_TILE_TB: those jobs are redone by the general
+    kernel)."""
+    dimx, dimy = dims
+    rng = np.random.default_rng(dimx * 1000 + dimy)
+    obst, free = _rand_map(rng, dimx, dimy, 0.15)
+    fc = np.flatnonzero(free.ravel())
+    m = capi.Map(dimx, dimy, obst)
+    N = min(24, len(fc) // 3)
+    pick = rng.choice(fc, 2 * N, replace=False)
+    starts, goals = pick[:N], pick[N:]
+    fields = capi.bfs_fields(dimx, dimy, obst, np.stack([goals % dimx, goals // dimx], 1))
+    ok = [i for i in range(N) if fields[i][starts[i]] != capi.INF]
+    base = capi.lowlevel_batch([m], fields, [{"start": int(starts[i]), "goal": int(goals[i]), "field": i}
+                                             for i in range(N)])
+    # two path tables: optimal paths, and the same with agents that have no path yet
+    # (ECBS root construction) and two agents on one cell (>= 2 per cell in the planes)
+    T = max([len(r["cells"]) for r in base if r["status"] == 0] + [2])
+    table = np.zeros((2, N, T), np.int32)
+    tlen = np.zeros((2, N), np.int32)
+    for i, r in enumerate(base):
+        if r["status"] != 0:
+            continue
+        for b in range(2):
+            table[b, i, :len(r["cells"])] = r["cells"]
+            tlen[b, i] = len(r["cells"])
+    tlen[1, ok[0]] = 0
+    if len(ok) > 3:
+        table[1, ok[1]] = table[1, ok[2]]
+        tlen[1, ok[1]] = tlen[1, ok[2]]
+    jobs = []
+    for k in range(160):
+        i = int(rng.choice(ok))
+        cells = base[i]["cells"]
+        reach = np.flatnonzero(fields[i] != capi.INF)
+        vc = [(int(rng.integers(1, len(cells) + 6)), int(rng.choice(reach))) for _ in range(int(rng.integers(0, 5)))]
+        # constraints on the agent's own optimal path so that they bite, sometimes on its goal
+        for _ in range(int(rng.integers(0, 4))):
+            t = int(rng.integers(1, len(cells) + 1))
+            vc.append((t, int(cells[min(t, len(cells) - 1)])))
+        if k % 4 == 0:
+            vc.append((len(cells) + int(rng.integers(0, 5)), int(goals[i])))
+        ec = []
+        for _ in range(int(rng.integers(0, 3))):
+            t = int(rng.integers(0, max(1, len(cells) - 1)))
+            ec.append((t, int(cells[min(t, len(cells) - 1)]), int(cells[min(t + 1, len(cells) - 1)])))
+        if k == 7:  # more constraints than the shared-memory cache holds
+            vc += [(int(rng.integers(40, 60)), int(rng.choice(reach))) for _ in range(120)]
+        jobs.append({"start": int(starts[i]), "goal": int(goals[i]), "field": i if k % 5 else -1,
+                     "table": k % 2, "self": i if k % 7 else -1, "vc": vc, "ec": ec})
+    for w, cap in ((0.0, 8000), (1.0, 8000), (1.3, 8000), (2.0, 8000), (1.3, 40)):
+        kw = dict(variant=0, w=w, max_expanded=cap, path_cap=256, tables=table, table_len=tlen)
+        monkeypatch.setenv("MRP_LL_GENERIC", "1")
+        ref = capi.lowlevel_batch([m], fields, jobs, **kw)
+        monkeypatch.delenv("MRP_LL_GENERIC")
+        _same_results(capi.lowlevel_batch([m], fields, jobs, **kw), ref)
+        monkeypatch.setenv("MRP_LL_TILE_NOOCC", "1")
+        _same_results(capi.lowlevel_batch([m], fields, jobs, **kw), ref)
+        monkeypatch.delenv("MRP_LL_TILE_NOOCC")
+        monkeypatch.setenv("MRP_LL_TILE_TB", "32")
+        _same_results(capi.lowlevel_batch([m], fields, jobs, **kw), ref)
+        monkeypatch.delenv("MRP_LL_TILE_TB")
+        assert sum(r["status"] == 0 for r in ref) >= (100 if cap > 40 else 1)
+    m.close()
