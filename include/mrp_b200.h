@@ -258,6 +258,44 @@ int mrp_lowlevel_batch_fs(const mrp_map* maps, int n_maps, mrp_fieldset fs,
                           int n_jobs, const mrp_lowlevel_params* params,
                           mrp_path_info* info, int32_t* out_cells, int32_t* out_g);
 
+/* ---- device-resident paths of the constraint-tree nodes -------------------
+ * The reference copies a high-level node with all its paths for every child
+ * (HighLevelNode newNode = P, include/libMultiRobotPlanning/cbs.hpp:144,
+ * ecbs.hpp:233) and passes them to getFirstConflict / focalHeuristic as host
+ * vectors (example/cbs.cpp:335-386, example/ecbs.cpp:315-350).  A child differs
+ * from its parent in one path, and the replan kernels produce that path on the
+ * device.  A path pool keeps every path in a row of device memory (cells only:
+ * with cbs / ecbs moves the g-score of a state is its time step, so this mode is
+ * limited to variant 0); a node is a list of row numbers owned by the caller,
+ * who also decides which rows are free.  Per call only row numbers and results
+ * cross PCIe; the rows of a node are gathered on the device into the dense
+ * tables the kernels sweep.  Row numbers: 0 <= row < capacity (mrp_pathpool_reserve),
+ * -1 in a table = that agent has no path (yet). */
+typedef struct mrp_pathpool_s* mrp_pathpool;
+int mrp_pathpool_create(int row_cap, mrp_pathpool* out);
+int mrp_pathpool_destroy(mrp_pathpool pool);
+/* makes rows 0 .. n_slots-1 valid (grows in chunks; existing rows keep their content) */
+int mrp_pathpool_reserve(mrp_pathpool pool, int n_slots);
+/* cells[n][row_cap] + len[n] <-> rows slots[n] (tests, output of the final solution) */
+int mrp_pathpool_write(mrp_pathpool pool, const int32_t* slots, int n, const int32_t* cells,
+                       const int32_t* len);
+int mrp_pathpool_read(mrp_pathpool pool, const int32_t* slots, int n, int32_t* cells,
+                      int32_t* len);
+/* mrp_conflicts_batch over tables given as pool rows: table_slots[B][N]; Tpad >= the
+ * longest path of the call */
+int mrp_conflicts_batch_pool(mrp_pathpool pool, const int32_t* table_slots, int B, int N,
+                             int Tpad, int dimx, int mode, int32_t* found,
+                             mrp_conflict* conflicts, int32_t* counts);
+/* mrp_lowlevel_batch_fs with the other agents' paths given as pool rows
+ * (table_slots[n_tables][N]) and the path of job j written to row out_slots[j]
+ * (rows of failed jobs keep their old content); info[j] as usual, no cells come back */
+int mrp_lowlevel_batch_pool(const mrp_map* maps, int n_maps, mrp_fieldset fs,
+                            const int32_t* vc, int n_vc, const int32_t* ec, int n_ec,
+                            mrp_pathpool pool, const int32_t* table_slots, int n_tables,
+                            int N, int Tpad, const mrp_job* jobs, int n_jobs,
+                            const mrp_lowlevel_params* params, const int32_t* out_slots,
+                            mrp_path_info* info);
+
 /* ---- multi-GPU ----------------------------------------------------------
  * One process (or host thread) per GPU, as SURVEY.md §8(e) shards the path:
  * distance fields by goal, conflict checks by agent-pair block, replans by

@@ -58,6 +58,8 @@ EXPORTS = [
     "mrp_comm_unique_id", "mrp_comm_init_rank", "mrp_comm_info", "mrp_comm_destroy",
     "mrp_bfs_allgather_workspace_bytes", "mrp_bfs_fields_allgather_dev", "mrp_comm_last_gather",
     "mrp_conflicts_sharded_dev", "mrp_bfs_fields_packed",
+    "mrp_pathpool_create", "mrp_pathpool_destroy", "mrp_pathpool_reserve", "mrp_pathpool_write",
+    "mrp_pathpool_read", "mrp_conflicts_batch_pool", "mrp_lowlevel_batch_pool",
 ]
 COMM_ID_BYTES = 128
 
@@ -312,6 +314,51 @@ def conflicts_batch(cell, length, dimx, mode):
     check(lib().mrp_conflicts_batch(_p(cell), _p(length), B, N, Tpad, dimx, mode,
                                     _p(found), confl, _p(counts)))
     return [confl[b].astuple() if found[b] else None for b in range(B)], counts
+
+
+class PathPool:
+    """Device rows of paths (mrp_pathpool_*): the caller owns the row numbers."""
+
+    def __init__(self, row_cap):
+        self.handle = C.c_void_p()
+        self.row_cap = row_cap
+        check(lib().mrp_pathpool_create(row_cap, C.byref(self.handle)))
+
+    def close(self):
+        if self.handle:
+            lib().mrp_pathpool_destroy(self.handle)
+            self.handle = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def reserve(self, n):
+        check(lib().mrp_pathpool_reserve(self.handle, n))
+
+    def write(self, slots, cells, length):
+        slots, cells, length = _i32(slots), _i32(cells), _i32(length)
+        assert cells.shape == (len(slots), self.row_cap)
+        check(lib().mrp_pathpool_write(self.handle, _p(slots), len(slots), _p(cells), _p(length)))
+
+    def read(self, slots):
+        slots = _i32(slots)
+        cells = np.zeros((len(slots), self.row_cap), np.int32)
+        length = np.zeros(len(slots), np.int32)
+        check(lib().mrp_pathpool_read(self.handle, _p(slots), len(slots), _p(cells), _p(length)))
+        return cells, length
+
+    def conflicts_batch(self, table_slots, Tpad, dimx, mode):
+        ts = _i32(table_slots)
+        B, N = ts.shape
+        found = np.zeros(B, np.int32)
+        counts = np.zeros(B, np.int32)
+        confl = (Conflict * max(B, 1))()
+        check(lib().mrp_conflicts_batch_pool(self.handle, _p(ts), B, N, Tpad, dimx, mode,
+                                             _p(found), confl, _p(counts)))
+        return [confl[b].astuple() if found[b] else None for b in range(B)], counts
 
 
 def focal_counts(cell, length, self_idx, cand_t, cand_from, cand_to):

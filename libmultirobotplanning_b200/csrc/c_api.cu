@@ -86,8 +86,8 @@ struct PinnedScratch {
 struct Lane {
   Context c;
   std::mutex m;
-  Scratch scratch[16];
-  PinnedScratch pinned[6];
+  Scratch scratch[24];
+  PinnedScratch pinned[10];
   LaneLL ll;
 };
 static Lane g_lanes[kMaxLanes];
@@ -99,6 +99,7 @@ Context& ctx() { return lane().c; }
 std::mutex& apiMutex() { return lane().m; }
 LaneLL& laneLL() { return lane().ll; }
 int pinnedScratch(int slot, size_t bytes, void** out) { return lane().pinned[slot].get(bytes, out); }
+int deviceScratch(int slot, size_t bytes, void** out) { return lane().scratch[slot].get(bytes, out); }
 cudaError_t waitStream(cudaStream_t st) {
   Context& c = ctx();
   if (!c.doneEvent) return cudaStreamSynchronize(st);

@@ -65,6 +65,8 @@ LaneLL& laneLL();
 // for the stream's kernel while it holds a context-wide lock, which serialises
 // the lanes (measured: 16 lanes took 3x longer than one before this).
 int pinnedScratch(int slot, size_t bytes, void** out);
+// grow-only device scratch of the calling thread's lane (slots 16.. belong to pathpool.cu)
+int deviceScratch(int slot, size_t bytes, void** out);
 // Waits for the lane's compute stream without spinning (the batched drivers
 // keep more host threads in flight than there are cores).
 cudaError_t waitStream(cudaStream_t st);

@@ -51,7 +51,52 @@ struct LLParams {
   const uint2* occ;
   const int32_t* occMany;
   int TB;  // rows of the visited bitmap (time steps a search may reach)
+  // path pool mode (pathpool.cu): the path of job j goes to pool row outSlots[j]
+  // (cells only: with unit move costs the g-score of a state is its time step),
+  // nothing is written to outCells / outG
+  const int32_t* outSlots;
+  int32_t* const* poolCells;  // per chunk: [kPoolChunk][rowCap]
+  int32_t* const* poolLen;    // per chunk: [kPoolChunk]
+  int rowCap;
 };
+
+constexpr int kPoolChunkBits = 15;
+constexpr int kPoolChunk = 1 << kPoolChunkBits;  // pool rows per device allocation
+
+// where job `job` writes its path: its rows of the call's output arrays, or its pool row
+__device__ __forceinline__ void pathOutput(const LLParams& p, int job, int32_t*& oc, int32_t*& og, int& cap) {
+  if (p.outSlots) {
+    const int slot = p.outSlots[job];
+    oc = p.poolCells[slot >> kPoolChunkBits] + (size_t)(slot & (kPoolChunk - 1)) * p.rowCap;
+    og = nullptr;
+    cap = p.rowCap;
+  } else {
+    oc = p.outCells + (size_t)job * p.pathCap;
+    og = p.outG + (size_t)job * p.pathCap;
+    cap = p.pathCap;
+  }
+}
+__device__ __forceinline__ void pathLength(const LLParams& p, int job, int len) {
+  if (p.outSlots) {
+    const int slot = p.outSlots[job];
+    p.poolLen[slot >> kPoolChunkBits][slot & (kPoolChunk - 1)] = len;
+  }
+}
+
+// pool mode of the host entry point (pathpool.cu); all pointers are device pointers
+struct LLPool {
+  const int32_t* d_tables = nullptr;  // [n_tables][N][Tpad], gathered from the pool
+  const int32_t* d_tlen = nullptr;
+  int32_t* const* d_poolCells = nullptr;
+  int32_t* const* d_poolLen = nullptr;
+  const int32_t* h_outSlots = nullptr;  // host: [n_jobs]
+  int rowCap = 0;
+};
+int lowlevelRun(const mrp_map* maps, int n_maps, const int32_t* fields, const int32_t* d_fields,
+                int n_fields, const int32_t* vc, int n_vc, const int32_t* ec, int n_ec,
+                const int32_t* tables, const int32_t* table_len, int n_tables, int N, int Tpad,
+                const mrp_job* jobs, int n_jobs, const mrp_lowlevel_params* params,
+                mrp_path_info* info, int32_t* out_cells, int32_t* out_g, const LLPool* pool);
 
 __device__ __forceinline__ bool cellFree(const uint32_t* bits, int W, int dimx, int dimy,
                                          int x, int y) {

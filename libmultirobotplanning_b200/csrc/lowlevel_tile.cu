@@ -38,6 +38,7 @@
 // redone by the general kernel.
 #include <algorithm>
 #include <cstdlib>
+#include <mutex>
 
 #include "lowlevel.cuh"
 
@@ -46,10 +47,11 @@ namespace mrp {
 constexpr int kOpenT = 768;   // OPEN entries in shared memory
 constexpr int kNodeT = 1024;  // nodes with (state, parent) in shared memory
 constexpr int kFMaxT = 512;   // f values tracked by the histogram
+constexpr int kOccSmemMax = 160 * 1024;  // shared memory of focal_occ_kernel (Tpad * 256 B)
 constexpr int kSelfT = 256;   // time steps of this agent's old path kept in shared memory
 
 struct TileLayout {
-  int openKey, vis, openState, nodeKey, field, nodePar, hist, rows, cons, selfRow, total;
+  int openKey, vis, openState, nodeKey, field, nodePar, hist, rows, cons, selfRow, stage, total;
 };
 __host__ __device__ inline TileLayout tileLayout(int TB) {
   TileLayout L;
@@ -64,6 +66,7 @@ __host__ __device__ inline TileLayout tileLayout(int TB) {
   L.rows = o;      o += 32 * 4;
   L.cons = o;      o += kConsCache * 3 * 4;
   L.selfRow = o;   o += kSelfT * 2;
+  L.stage = o;     o += 32 * 32;  // 3 x 8 B of occupancy words per lane, in 32-byte slots
   L.total = (o + 15) & ~15;
   return L;
 }
@@ -104,6 +107,54 @@ __global__ void __launch_bounds__(256) focal_occ_kernel(const int32_t* __restric
   if (threadIdx.x == 0) occMany[blockIdx.x] = sMany;
 }
 
+// ---- shared-memory accesses by 32-bit shared-window address ----
+// (the search loop is one dependent chain: explicit addresses keep every access a
+// single LDS / STS / ATOMS without generic-address arithmetic in front of it; the
+// statements are volatile, so they keep their order among themselves)
+__device__ __forceinline__ uint32_t sLd32(uint32_t a) {
+  uint32_t v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ uint32_t sLdU16(uint32_t a) {
+  uint32_t v;
+  asm volatile("{\n\t.reg .u16 h;\n\tld.shared.u16 h, [%1];\n\tcvt.u32.u16 %0, h;\n\t}" : "=r"(v) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ unsigned long long sLd64(uint32_t a) {
+  unsigned long long v;
+  asm volatile("ld.shared.u64 %0, [%1];" : "=l"(v) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ void sSt32(uint32_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v)); }
+__device__ __forceinline__ void sStU16(uint32_t a, uint32_t v) {
+  asm volatile("{\n\t.reg .u16 h;\n\tcvt.u16.u32 h, %1;\n\tst.shared.u16 [%0], h;\n\t}" ::"r"(a), "r"(v));
+}
+__device__ __forceinline__ void sSt64(uint32_t a, unsigned long long v) { asm volatile("st.shared.u64 [%0], %1;" ::"r"(a), "l"(v)); }
+__device__ __forceinline__ uint32_t sAtomOr(uint32_t a, uint32_t v) {
+  uint32_t old;
+  asm volatile("atom.shared.or.b32 %0, [%1], %2;" : "=r"(old) : "r"(a), "r"(v));
+  return old;
+}
+__device__ __forceinline__ void sAtomAdd(uint32_t a, uint32_t v) { asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(a), "r"(v)); }
+// 8-byte asynchronous copy global -> shared (completion tracked by the copy group, not by
+// a scoreboard: instructions in between never wait for it)
+__device__ __forceinline__ void cpAsync8(uint32_t dst, const void* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src));
+}
+__device__ __forceinline__ void cpAsyncCommit() { asm volatile("cp.async.commit_group;"); }
+__device__ __forceinline__ void cpAsyncWaitAll() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+// lane numbers of the set bits of a 5-bit mask, ascending, 3 bits each
+__constant__ unsigned short kNthSet[32] = {
+    0,     0,     1,     0 | 1 << 3, 2,     0 | 2 << 3, 1 | 2 << 3, 0 | 1 << 3 | 2 << 6,
+    3,     0 | 3 << 3, 1 | 3 << 3, 0 | 1 << 3 | 3 << 6, 2 | 3 << 3, 0 | 2 << 3 | 3 << 6, 1 | 2 << 3 | 3 << 6,
+    0 | 1 << 3 | 2 << 6 | 3 << 9,
+    4,     0 | 4 << 3, 1 | 4 << 3, 0 | 1 << 3 | 4 << 6, 2 | 4 << 3, 0 | 2 << 3 | 4 << 6, 1 | 2 << 3 | 4 << 6,
+    0 | 1 << 3 | 2 << 6 | 4 << 9,
+    3 | 4 << 3, 0 | 3 << 3 | 4 << 6, 1 | 3 << 3 | 4 << 6, 0 | 1 << 3 | 3 << 6 | 4 << 9, 2 | 3 << 3 | 4 << 6,
+    0 | 2 << 3 | 3 << 6 | 4 << 9, 1 | 2 << 3 | 3 << 6 | 4 << 9, 0 | 1 << 3 | 2 << 6 | 3 << 9 | 4 << 12};
+
 __device__ __forceinline__ uint32_t edgeHash(int t, int from, int to) {
   return hashState((uint32_t)t * 0x9E3779B1u ^ ((uint32_t)from << 11) ^ (uint32_t)to);
 }
@@ -111,17 +162,18 @@ __device__ __forceinline__ uint32_t edgeHash(int t, int from, int to) {
 __global__ void __launch_bounds__(32) lowlevel_tile_kernel(LLParams p) {
   extern __shared__ __align__(16) unsigned char smemRaw[];
   const TileLayout lay = tileLayout(p.TB);
-  unsigned long long* openS = reinterpret_cast<unsigned long long*>(smemRaw + lay.openKey);
   uint32_t* vis = reinterpret_cast<uint32_t*>(smemRaw + lay.vis);
-  uint32_t* openStateS = reinterpret_cast<uint32_t*>(smemRaw + lay.openState);
-  uint32_t* nodeKeyS = reinterpret_cast<uint32_t*>(smemRaw + lay.nodeKey);
   uint32_t* hist32 = reinterpret_cast<uint32_t*>(smemRaw + lay.hist);
-  unsigned short* hist = reinterpret_cast<unsigned short*>(smemRaw + lay.hist);
   unsigned short* fieldS = reinterpret_cast<unsigned short*>(smemRaw + lay.field);
-  unsigned short* nodeParS = reinterpret_cast<unsigned short*>(smemRaw + lay.nodePar);
   uint32_t* rowsS = reinterpret_cast<uint32_t*>(smemRaw + lay.rows);
   int32_t* cons = reinterpret_cast<int32_t*>(smemRaw + lay.cons);
   unsigned short* selfRow = reinterpret_cast<unsigned short*>(smemRaw + lay.selfRow);
+  // the same regions as 32-bit shared-window addresses (search loop)
+  const uint32_t sBase = (uint32_t)__cvta_generic_to_shared(smemRaw);
+  const uint32_t aOpen = sBase + lay.openKey, aVis = sBase + lay.vis, aOpenState = sBase + lay.openState,
+                 aNodeKey = sBase + lay.nodeKey, aHist = sBase + lay.hist, aField = sBase + lay.field,
+                 aNodePar = sBase + lay.nodePar, aRows = sBase + lay.rows, aCons = sBase + lay.cons,
+                 aSelf = sBase + lay.selfRow, aStage = sBase + lay.stage;
 
   const int lane = threadIdx.x;
   const int slot = blockIdx.x;
@@ -135,12 +187,6 @@ __global__ void __launch_bounds__(32) lowlevel_tile_kernel(LLParams p) {
   // a cell of the map (x + dimx*y) as tile position (y*32 + x) and back
   auto toTile = [&](int c) -> int { return dimx == 32 ? c : ((c / dimx) << 5) | (c % dimx); };
   auto toCell = [&](int tile) -> int { return dimx == 32 ? tile : (tile & 31) + dimx * (tile >> 5); };
-  auto openGet = [&](int i) -> unsigned long long { return i < kOpenT ? openS[i] : openG[i]; };
-  auto openSet = [&](int i, unsigned long long v) {
-    if (i < kOpenT) openS[i] = v; else openG[i] = v;
-  };
-  auto nodeKeyOf = [&](int n) -> uint32_t { return n < kNodeT ? nodeKeyS[n] : nodeKeyG[n]; };
-
   int visTop = TB;  // rows of vis[] that may hold bits of the previous job
 
   while (true) {
@@ -224,16 +270,16 @@ __global__ void __launch_bounds__(32) lowlevel_tile_kernel(LLParams p) {
       }
     }
     __syncwarp();
-    const int32_t* ecp = cons + 2 * nVc;
     const int goalTile = goal >= 0 ? toTile(goal) : -1;
     const int goalX = goalTile & 31, goalY = goalTile >> 5;
+    const uint32_t aEc = aCons + 8u * (uint32_t)nVc;  // edge constraints: (t, from, to)
 
     // admissible heuristic: the reference's value (Manhattan, example/cbs.cpp:278-284,
     // or the distance field) raised to the time bound of the goal test (see lowlevel.cu)
     auto heur = [&](int tile, int t) -> int {
       int h;
       if (field) {
-        const int v = fieldS[tile];
+        const int v = (int)sLdU16(aField + 2u * (uint32_t)tile);
         h = v == 0xFFFF ? MRP_INF : v;
       } else {
         h = abs((tile & 31) - goalX) + abs((tile >> 5) - goalY);
@@ -242,12 +288,26 @@ __global__ void __launch_bounds__(32) lowlevel_tile_kernel(LLParams p) {
       return h;
     };
     const bool exactTail = !p.focalMode && field != nullptr;
-    auto selfAt = [&](int t) -> int { return selfLen > 0 ? (int)selfRow[min(t, selfLen - 1)] : -1; };
+    auto selfAt = [&](int t) -> int {
+      return selfLen > 0 ? (int)sLdU16(aSelf + 2u * (uint32_t)min(t, selfLen - 1)) : -1;
+    };
+    auto openGet = [&](int i) -> unsigned long long {
+      if (i < kOpenT) return sLd64(aOpen + 8u * (uint32_t)i);
+      return openG[i];
+    };
+    auto openSet = [&](int i, unsigned long long v) {
+      if (i < kOpenT) sSt64(aOpen + 8u * (uint32_t)i, v); else openG[i] = v;
+    };
+    auto nodeKeyOf = [&](int n) -> uint32_t {
+      if (n < kNodeT) return sLd32(aNodeKey + 4u * (uint32_t)n);
+      return nodeKeyG[n];
+    };
 
     // ---- root ----
     int nNodes = 0, nOpen = 0, expanded = 0, tTop = tMark;
     int goalNode = -1, tailFrom = -1, goalF = 0;
     const int startTile = toTile(jb.start_cell);
+    int bestF = 0;
     if (status == -1) {
       const int h0 = heur(startTile, 0);
       if (h0 == MRP_INF) {
@@ -256,19 +316,19 @@ __global__ void __launch_bounds__(32) lowlevel_tile_kernel(LLParams p) {
         status = kTileStatusRedo;
       } else {
         if (lane == 0) {
-          nodeKeyS[0] = (uint32_t)startTile;
-          nodeParS[0] = 0xFFFF;
-          openS[0] = packOpenKey(0, h0, 0, 0);
-          openStateS[0] = (uint32_t)startTile;
-          vis[startTile >> 5] |= 1u << (startTile & 31);
-          hist[h0] = 1;
+          sSt32(aNodeKey, (uint32_t)startTile);
+          sStU16(aNodePar, 0xFFFFu);
+          sSt64(aOpen, packOpenKey(0, h0, 0, 0));
+          sSt32(aOpenState, (uint32_t)startTile);
+          sAtomOr(aVis + 4u * (uint32_t)(startTile >> 5), 1u << (startTile & 31));
+          sStU16(aHist + 2u * (uint32_t)h0, 1u);
         }
         nNodes = 1;
         nOpen = 1;
+        bestF = h0;
       }
     }
     __syncwarp();
-    int bestF = (status == -1) ? (int)(openS[0] >> 38) & 0xfff : 0;
     // per-lane minimum of the eligible OPEN entries this lane owns (positions == lane mod 32)
     unsigned long long cbest = ~0ull;
     int cpos = 0;
@@ -305,7 +365,7 @@ __global__ void __launch_bounds__(32) lowlevel_tile_kernel(LLParams p) {
         status = 1;
         break;
       }
-      while (bestF < kFMaxT && hist[bestF] == 0) ++bestF;
+      while (bestF < kFMaxT && sLdU16(aHist + 2u * (uint32_t)bestF) == 0) ++bestF;
       if (bestF >= kFMaxT) {
         status = kTileStatusRedo;
         break;
@@ -317,7 +377,7 @@ __global__ void __launch_bounds__(32) lowlevel_tile_kernel(LLParams p) {
         int bestPos = 0;
         const int nS = min(nOpen, kOpenT);
         for (int i = lane; i < nS; i += 32) {
-          const unsigned long long e = openS[i];
+          const unsigned long long e = sLd64(aOpen + 8u * (uint32_t)i);
           const int f = (int)((e >> 38) & 0xfffull);
           if (f <= fBound && e < best) {
             best = e;
@@ -350,7 +410,7 @@ __global__ void __launch_bounds__(32) lowlevel_tile_kernel(LLParams p) {
       const int owner = __ffs(who) - 1;
       const int pos = __shfl_sync(0xffffffffu, cpos, owner);
       const int cur = (int)(bestAll & 0x3ffffffull);
-      const uint32_t ckey = pos < kOpenT ? openStateS[pos] : nodeKeyOf(cur);
+      const uint32_t ckey = pos < kOpenT ? sLd32(aOpenState + 4u * (uint32_t)pos) : nodeKeyOf(cur);
       const int ct = (int)(ckey >> 10), ctile = (int)(ckey & 1023u);
       const int cg = 4095 - (int)((bestAll >> 26) & 0xfffull);
       const int cfo = (int)(bestAll >> 50);
@@ -390,29 +450,36 @@ __global__ void __launch_bounds__(32) lowlevel_tile_kernel(LLParams p) {
       if (lane == 4) ny = cy - 1;
       const bool inMap = lane < 5 && nx >= 0 && ny >= 0 && nx < dimx && ny < dimy;
       const int ntile = inMap ? (ny << 5) | nx : ctile;
-      // occupancy of the successor's cell at both times and of this cell at the next
-      // step (consumed by the focal values below; issued here to overlap the rest)
-      uint2 oA = make_uint2(0, 0), oB = oA, oC = oA;
-      if (occOK && inMap) {
-        const int r1 = min(nt, p.Tpad - 1) * 32, r0 = min(ct, p.Tpad - 1) * 32;
-        oA = occ[r1 + (ntile >> 5)];
-        oB = occ[r0 + (ntile >> 5)];
-        oC = occ[r1 + cy];
+      // occupancy of the successor's cell at both times and of this cell at the next step
+      // (consumed by the focal values below): asynchronous copies into the lane's staging
+      // words, so that nothing in between waits for them
+      const bool useOcc = wantFocal && occOK;
+      if (useOcc) {
+        if (inMap) {
+          const int r1 = min(nt, p.Tpad - 1) * 32, r0 = min(ct, p.Tpad - 1) * 32;
+          const uint32_t st = aStage + 32u * (uint32_t)lane;
+          cpAsync8(st, occ + r1 + (ntile >> 5));
+          cpAsync8(st + 8u, occ + r0 + (ntile >> 5));
+          cpAsync8(st + 16u, occ + r1 + cy);
+        }
+        cpAsyncCommit();
       }
       // remove from OPEN (swap with last) and the histogram
       __syncwarp();
       if (lane == 0) {
-        openSet(pos, openGet(nOpen - 1));
+        const unsigned long long last = openGet(nOpen - 1);
+        openSet(pos, last);
         if (pos < kOpenT)
-          openStateS[pos] = nOpen - 1 < kOpenT ? openStateS[nOpen - 1]
-                                               : nodeKeyOf((int)(openGet(nOpen - 1) & 0x3ffffffull));
-        hist[cf] -= 1;
+          sSt32(aOpenState + 4u * (uint32_t)pos,
+                nOpen - 1 < kOpenT ? sLd32(aOpenState + 4u * (uint32_t)(nOpen - 1))
+                                   : nodeKeyOf((int)(last & 0x3ffffffull)));
+        sStU16(aHist + 2u * (uint32_t)cf, sLdU16(aHist + 2u * (uint32_t)cf) - 1u);
       }
       --nOpen;
       __syncwarp();
       afterRemoval(pos, nOpen, fBound);
 
-      bool ok = inMap && ((rowsS[ny & 31] >> (nx & 31)) & 1u);
+      bool ok = inMap && ((sLd32(aRows + 4u * (uint32_t)(ny & 31)) >> (nx & 31)) & 1u);
       const int cc = toCell(ctile), nc = toCell(ntile);
       // transitionValid (example/cbs.cpp:438-444): Bloom filter first
       if (nEc) {
@@ -420,13 +487,15 @@ __global__ void __launch_bounds__(32) lowlevel_tile_kernel(LLParams p) {
         const uint32_t word = __shfl_sync(0xffffffffu, bloom, (int)(h >> 5));
         if (ok && ((word >> (h & 31u)) & 1u))
           for (int i = 0; i < nEc; ++i)
-            if (ecp[3 * i] == ct && ecp[3 * i + 1] == cc && ecp[3 * i + 2] == nc) ok = false;
+            if ((int)sLd32(aEc + 12u * (uint32_t)i) == ct && (int)sLd32(aEc + 12u * (uint32_t)i + 4u) == cc &&
+                (int)sLd32(aEc + 12u * (uint32_t)i + 8u) == nc)
+              ok = false;
       }
       // closed/open membership; a vertex-constrained state reads as seen
       bool isNew = false;
       if (ok) {
         const uint32_t bit = 1u << nx;
-        isNew = (atomicOr(&vis[nt * 32 + ny], bit) & bit) == 0;
+        isNew = (sAtomOr(aVis + 4u * (uint32_t)(nt * 32 + ny), bit) & bit) == 0;
       }
       int nh = 0;
       if (ok) nh = heur(ntile, nt);
@@ -446,13 +515,21 @@ __global__ void __launch_bounds__(32) lowlevel_tile_kernel(LLParams p) {
       const int myNode = nNodes + __popc(newMask & ((1u << lane) - 1u));
       // ---- focal values of the new nodes (ecbs.cpp:282-312) ----
       int focalAdd = 0;
+      if (useOcc) {
+        cpAsyncWaitAll();
+        __syncwarp();
+      }
       if (wantFocal && newMask) {
         bool needExact = !occOK;
         if (occOK) {
+          const uint32_t st = aStage + 32u * (uint32_t)lane;
+          const unsigned long long oA = inMap ? sLd64(st) : 0ull, oB = inMap ? sLd64(st + 8u) : 0ull,
+                                   oC = inMap ? sLd64(st + 16u) : 0ull;
           const int sN = selfAt(nt), sC = selfAt(ct);
-          const int vN = (int)((oA.x >> nx) & 1u) + (int)((oA.y >> nx) & 1u) - (sN == ntile ? 1 : 0);
-          const int othersHere = (int)((oC.x >> cx) & 1u) + (int)((oC.y >> cx) & 1u) - (sN == ctile ? 1 : 0);
-          const int othersFrom = (int)((oB.x >> nx) & 1u) + (int)((oB.y >> nx) & 1u) - (sC == ntile ? 1 : 0);
+          // (low word: cells with >= 1 agent, high word: cells with >= 2)
+          const int vN = (int)((oA >> nx) & 1ull) + (int)((oA >> (32 + nx)) & 1ull) - (sN == ntile ? 1 : 0);
+          const int othersHere = (int)((oC >> cx) & 1ull) + (int)((oC >> (32 + cx)) & 1ull) - (sN == ctile ? 1 : 0);
+          const int othersFrom = (int)((oB >> nx) & 1ull) + (int)((oB >> (32 + nx)) & 1ull) - (sC == ntile ? 1 : 0);
           focalAdd = vN;
           // a swap needs another agent on this cell at nt that stood on the successor's cell at ct
           needExact = __any_sync(0xffffffffu, isNew && othersHere > 0 && othersFrom > 0);
@@ -503,8 +580,8 @@ __global__ void __launch_bounds__(32) lowlevel_tile_kernel(LLParams p) {
       if (isNew) {
         const uint32_t nkey = ((uint32_t)nt << 10) | (uint32_t)ntile;
         if (myNode < kNodeT) {
-          nodeKeyS[myNode] = nkey;
-          nodeParS[myNode] = (unsigned short)cur;
+          sSt32(aNodeKey + 4u * (uint32_t)myNode, nkey);
+          sStU16(aNodePar + 2u * (uint32_t)myNode, (uint32_t)cur);
         } else {
           nodeKeyG[myNode] = nkey;
           nodeParG[myNode] = cur;
@@ -512,27 +589,30 @@ __global__ void __launch_bounds__(32) lowlevel_tile_kernel(LLParams p) {
         newKey = packOpenKey(cfo + focalAdd, nf, ng, myNode);
         const int at = nOpen + myNode - nNodes;
         openSet(at, newKey);
-        if (at < kOpenT) openStateS[at] = nkey;
+        if (at < kOpenT) sSt32(aOpenState + 4u * (uint32_t)at, nkey);
         // two 16-bit counters per word: same-bin successors add up in the atomic
-        atomicAdd(&hist32[nf >> 1], (nf & 1) ? 0x10000u : 1u);
+        sAtomAdd(aHist + 4u * (uint32_t)(nf >> 1), (nf & 1) ? 0x10000u : 1u);
       }
       bestF = min(bestF, (int)__reduce_min_sync(0xffffffffu, isNew ? (uint32_t)nf : 0x7fffffffu));
-      __syncwarp();
-      // the new OPEN entries join the caches of their lanes
-      for (int k = 0; k < 5; ++k) {
-        if (!((newMask >> k) & 1u)) continue;
-        const int kf = __shfl_sync(0xffffffffu, nf, k);
-        const int kpos = nOpen + __popc(newMask & ((1u << k) - 1u));
-        const unsigned long long kkey = __shfl_sync(0xffffffffu, newKey, k);
-        if (lane == (kpos & 31) && kf <= fBound && kkey < cbest) {
-          cbest = kkey;
-          cpos = kpos;
+      // the new OPEN entries (positions nOpen .. nOpen + nNew - 1) join the caches of their
+      // lanes: lane (nOpen + r) & 31 takes the r-th new successor
+      {
+        const int r = (lane - nOpen) & 31;
+        const int src = (int)((kNthSet[newMask & 31u] >> (3 * min(r, 4))) & 7u);
+        const unsigned long long kkey = __shfl_sync(0xffffffffu, newKey, src);
+        if (r < nNew) {
+          const int kf = (int)((kkey >> 38) & 0xfffull);
+          if (kf <= fBound && kkey < cbest) {
+            cbest = kkey;
+            cpos = nOpen + r;
+          }
         }
       }
       nNodes += nNew;
       nOpen += nNew;
       __syncwarp();
     }
+    __syncwarp();
 
     // ---- result ----
     mrp_path_info pi;
@@ -542,15 +622,16 @@ __global__ void __launch_bounds__(32) lowlevel_tile_kernel(LLParams p) {
     pi.length = 0;
     pi.expanded = expanded;
     if (status == 0) {
-      int32_t* oc = p.outCells + (size_t)job * p.pathCap;
-      int32_t* og = p.outG + (size_t)job * p.pathCap;
+      int32_t *oc, *og;
+      int outCap;
+      pathOutput(p, job, oc, og, outCap);
       const uint32_t gk = nodeKeyOf(goalNode);
       const int gt = (int)(gk >> 10);  // depth of the goal node = its time = its g
       int len = gt + 1;
       int cost = gt;
       const int tailTile = (int)(gk & 1023u);
       if (tailFrom >= 0) {
-        const int rest = fieldS[tailTile];
+        const int rest = (int)sLdU16(aField + 2u * (uint32_t)tailTile);
         len += rest;
         cost += rest;
       }
@@ -559,29 +640,32 @@ __global__ void __launch_bounds__(32) lowlevel_tile_kernel(LLParams p) {
       // minimum f in OPEN at termination (a_star_epsilon.hpp:210)
       pi.fmin = p.focalMode ? bestF : goalF;
       pi.length = len;
-      if (len > p.pathCap) {
+      if (len > outCap) {
         pi.status = 2;
       } else if (lane == 0) {
+        pathLength(p, job, len);
         int n = goalNode;
         for (int t = gt; t >= 0; --t) {
           oc[t] = toCell((int)(nodeKeyOf(n) & 1023u));
-          og[t] = t;
-          n = n < kNodeT ? (int)nodeParS[n] : nodeParG[n];
+          if (og) og[t] = t;
+          n = n < kNodeT ? (int)sLdU16(aNodePar + 2u * (uint32_t)n) : nodeParG[n];
         }
         if (tailFrom >= 0) {
           // follow the field's gradient: Left, Right, Up, Down (any optimum)
           int c = tailTile, t = gt;
-          while (fieldS[c] > 0) {
-            const int x = c & 31, y = c >> 5, d = fieldS[c];
+          auto fieldAt = [&](int tile) -> int { return (int)sLdU16(aField + 2u * (uint32_t)tile); };
+          auto rowAt = [&](int y) -> uint32_t { return sLd32(aRows + 4u * (uint32_t)y); };
+          while (fieldAt(c) > 0) {
+            const int x = c & 31, y = c >> 5, d = fieldAt(c);
             int nxt;
-            if (x > 0 && ((rowsS[y] >> (x - 1)) & 1u) && fieldS[c - 1] == d - 1) nxt = c - 1;
-            else if (x + 1 < dimx && ((rowsS[y] >> (x + 1)) & 1u) && fieldS[c + 1] == d - 1) nxt = c + 1;
-            else if (y + 1 < dimy && ((rowsS[y + 1] >> x) & 1u) && fieldS[c + 32] == d - 1) nxt = c + 32;
+            if (x > 0 && ((rowAt(y) >> (x - 1)) & 1u) && fieldAt(c - 1) == d - 1) nxt = c - 1;
+            else if (x + 1 < dimx && ((rowAt(y) >> (x + 1)) & 1u) && fieldAt(c + 1) == d - 1) nxt = c + 1;
+            else if (y + 1 < dimy && ((rowAt(y + 1) >> x) & 1u) && fieldAt(c + 32) == d - 1) nxt = c + 32;
             else nxt = c - 32;
             c = nxt;
             ++t;
             oc[t] = toCell(c);
-            og[t] = t;
+            if (og) og[t] = t;
           }
         }
       }
@@ -602,7 +686,7 @@ static int tileRows(const LLParams& p) {
 bool lowlevelTileEligible(const LLParams& p, int n_tables) {
   if (getenv("MRP_LL_GENERIC")) return false;  // A/B switch, read per call (tests flip it)
   if (p.variant != 0 || p.W != 1 || p.dimy > 32 || p.dimx > 32) return false;
-  if (n_tables > 0 && p.tables && (size_t)p.Tpad * 256 > 160 * 1024) return false;
+  if (n_tables > 0 && p.tables && (size_t)p.Tpad * 256 > (size_t)kOccSmemMax) return false;
   return true;
 }
 
@@ -610,11 +694,22 @@ size_t lowlevelTileOccBytes(int n_tables, int Tpad) {
   return (size_t)std::max(n_tables, 0) * Tpad * 32 * sizeof(uint2) + (size_t)std::max(n_tables, 1) * 4;
 }
 
+// The shared-memory limits of the two kernels are set once, to the largest size
+// any launch asks for: the attribute belongs to the function, and lanes launch
+// concurrently with different sizes.
+static void setSmemLimits() {
+  static std::once_flag once;
+  std::call_once(once, [] {
+    cudaFuncSetAttribute(focal_occ_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kOccSmemMax);
+    cudaFuncSetAttribute(lowlevel_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tileLayout(512).total);
+  });
+}
+
 int lowlevelTileSlots(const LLParams& pIn) {
   LLParams p = pIn;
   p.TB = tileRows(p);
   const TileLayout lay = tileLayout(p.TB);
-  cudaFuncSetAttribute(lowlevel_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, lay.total);
+  setSmemLimits();
   int perSm = 1;
   if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, lowlevel_tile_kernel, 32, lay.total) != cudaSuccess ||
       perSm < 1)
@@ -631,7 +726,7 @@ int launchLowlevelTile(const LLParams& pIn, int n_tables, uint2* d_occ, int32_t*
   const bool noOcc = getenv("MRP_LL_TILE_NOOCC") != nullptr;
   if (p.focalMode && p.tables && n_tables > 0 && d_occ && !noOcc) {
     const size_t smem = (size_t)p.Tpad * 32 * 8;
-    cudaFuncSetAttribute(focal_occ_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    setSmemLimits();
     focal_occ_kernel<<<n_tables, 256, smem, st>>>(p.tables, p.tableLen, p.N, p.Tpad, p.dimx, d_occ, d_occMany);
     countLaunch();
     MRP_CUDA(cudaGetLastError());
@@ -639,7 +734,6 @@ int launchLowlevelTile(const LLParams& pIn, int n_tables, uint2* d_occ, int32_t*
     p.occMany = d_occMany;
   }
   const TileLayout lay = tileLayout(p.TB);
-  cudaFuncSetAttribute(lowlevel_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, lay.total);
   lowlevel_tile_kernel<<<slots, 32, lay.total, st>>>(p);
   countLaunch();
   MRP_CUDA(cudaGetLastError());

@@ -60,6 +60,10 @@ struct AgentPath {
   std::vector<int> g;  // g-score per state: the "t" of output.yaml (cbs.cpp:659)
   int cost = 0;
   int fmin = 0;
+  // pool mode (cbs / ecbs batches): the cells live in row `slot` of the device path
+  // pool, `length` states; cells / g are filled from the pool for the final solution only
+  int slot = -1;
+  int length = 0;
 };
 
 enum SolveStatus { kSolved = 0, kNoSolution = 1, kCapped = 2 };
@@ -131,8 +135,11 @@ class BatchSolver {
       m_slowThread.join();
     }
     for (Node* n : m_slowOut) delete n;
-    for (Inst& I : m_inst)
+    for (Inst& I : m_inst) {
       for (Node* n : I.open) delete n;
+      I.solution.clear();
+    }
+    if (m_pool) mrp_pathpool_destroy(m_pool);
     if (m_fields) mrp_fieldset_destroy(m_fields);
     for (mrp_map m : m_maps) mrp_map_destroy(m);
   }
@@ -152,8 +159,9 @@ class BatchSolver {
     std::vector<Node*> fresh;
     const double tRun = nowSeconds();
     buildRoots(fresh);
+    // (the path pool belongs to one lane: pool mode keeps to the lock-step launches)
     const bool twoSpeed = m_opt.fastLlExpanded > 0 && m_opt.fastLlExpanded < m_opt.maxLlExpanded &&
-                          m_opt.slowLane >= 0 && (m_algo == Algo::CBS || m_algo == Algo::ECBS);
+                          m_opt.slowLane >= 0 && (m_algo == Algo::CBS || m_algo == Algo::ECBS) && !m_pool;
     if (twoSpeed) m_slowThread = std::thread([this] { slowWorker(); });
     size_t nSuspended = 0;
     while (true) {
@@ -200,6 +208,7 @@ class BatchSolver {
         pd.parent = std::move(popped[k]);
         pending.push_back(std::move(pd));
       }
+      fetchSolutions();
       m_prof.pop += nowSeconds() - tPop;
       if (!anyRunning) {
         if (nSuspended == 0) break;
@@ -231,6 +240,7 @@ class BatchSolver {
       m_slowThread.join();
       if (!m_slowError.empty()) throw std::runtime_error(m_slowError);
     }
+    fetchSolutions();
     for (size_t k = 0; k < m_inst.size(); ++k) out[k] = std::move(m_inst[k].res);
     m_prof.total = nowSeconds() - tRun;
     if (getenv("MRP_HOST_PROFILE"))
@@ -296,6 +306,7 @@ class BatchSolver {
     std::unique_ptr<NextBestAssignment<int, int> > assignment;
     long nextRootNodeCost = 0;  // ecbs_ta (STYLE_MINROOT, ecbs_ta.hpp:142,345)
     SolveResult res;
+    std::vector<PathPtr> solution;  // pool mode: the rows of the solution until they are fetched
   };
   struct Pending {
     int inst = 0;
@@ -309,8 +320,70 @@ class BatchSolver {
   struct JobOut {
     int status;
     long expanded;
-    AgentPath path;
+    PathPtr path;  // set iff status == 0
   };
+
+  // ---- device path pool (cbs / ecbs): rows are handed out and taken back here ----
+  bool poolWanted() const {
+    if (!(m_algo == Algo::CBS || m_algo == Algo::ECBS)) return false;
+    const char* e = getenv("MRP_HOST_POOL");
+    return !(e && atoi(e) == 0);
+  }
+  void takeRows(size_t n, std::vector<int32_t>& rows) {
+    rows.resize(n);
+    std::lock_guard<std::mutex> lk(m_rowMutex);
+    for (size_t i = 0; i < n; ++i) {
+      if (!m_freeRows.empty()) {
+        rows[i] = m_freeRows.back();
+        m_freeRows.pop_back();
+      } else {
+        rows[i] = m_nextRow++;
+      }
+    }
+  }
+  void giveRow(int row) {
+    std::lock_guard<std::mutex> lk(m_rowMutex);
+    m_freeRows.push_back(row);
+  }
+  // a path that owns a pool row gives it back when the last node drops it
+  PathPtr adopt(AgentPath&& p) {
+    if (p.slot < 0) return std::make_shared<const AgentPath>(std::move(p));
+    return PathPtr(new AgentPath(std::move(p)), [this](const AgentPath* q) {
+      giveRow(q->slot);
+      delete q;
+    });
+  }
+  // pool mode: the paths of the instances that finished since the last call come to
+  // the host (one read for all of them; main thread only)
+  void fetchSolutions() {
+    if (!m_pool) return;
+    std::vector<int32_t> rows;
+    std::vector<size_t> owner;
+    for (size_t k = 0; k < m_inst.size(); ++k)
+      for (const PathPtr& p : m_inst[k].solution) {
+        rows.push_back(p->slot);
+        owner.push_back(k);
+      }
+    if (rows.empty()) return;
+    std::vector<int32_t> cells(rows.size() * (size_t)m_pathCap), len(rows.size());
+    gpuCheck(mrp_pathpool_read(m_pool, rows.data(), (int)rows.size(), cells.data(), len.data()));
+    size_t r = 0;
+    for (size_t k = 0; k < m_inst.size(); ++k) {
+      Inst& I = m_inst[k];
+      for (const PathPtr& p : I.solution) {
+        AgentPath out;
+        out.cost = p->cost;
+        out.fmin = p->fmin;
+        out.length = len[r];
+        out.cells.assign(cells.begin() + r * m_pathCap, cells.begin() + r * m_pathCap + len[r]);
+        out.g.resize(len[r]);
+        for (int t = 0; t < len[r]; ++t) out.g[t] = t;  // cbs / ecbs moves: g-score = time step
+        I.res.paths.push_back(std::move(out));
+        ++r;
+      }
+      I.solution.clear();
+    }
+  }
 
   // ---------------------------------------------------------------------
   void setup() {
@@ -338,6 +411,7 @@ class BatchSolver {
         }
       }
     }
+    if (poolWanted()) gpuCheck(mrp_pathpool_create(m_pathCap, &m_pool));
     // the heuristic precompute sits outside the reference's timer as well
     // (Environment ctor, example/cbs_ta.cpp:254-281,570-578)
     gpuCheck(mrp_fieldset_create(m_maps.data(), (int)m_maps.size(), goalMap.data(),
@@ -384,7 +458,10 @@ class BatchSolver {
     I.res.runtime = t;
     if (n) {
       for (const auto& p : n->paths) {  // example/cbs.cpp:630-635
-        I.res.paths.push_back(*p);
+        if (p->slot >= 0)
+          I.solution.push_back(p);  // cells follow in fetchSolutions()
+        else
+          I.res.paths.push_back(*p);
         I.res.cost += p->cost;
         I.res.makespan = std::max<long>(I.res.makespan, p->cost);
         I.res.lowerBound += p->fmin;
@@ -486,18 +563,54 @@ class BatchSolver {
       j.table = s.table;
       j.self = s.self;
     }
-    // path tables of the other agents (ECBS focal heuristics)
-    std::vector<int32_t>& tables = buf.tables;
-    std::vector<int32_t>& tlen = buf.tlen;
-    const bool haveTables = !tableNodes.empty();
-    int N = 0, Tpad = 0;
-    if (haveTables) packTables(tableNodes, tables, tlen, N, Tpad);
     mrp_lowlevel_params prm;
     prm.variant = isTA() ? 1 : 0;
     prm.w = isFocal() ? m_opt.w : 0.0f;
     prm.max_expanded = maxExpanded;
     prm.path_cap = m_pathCap;
     std::vector<mrp_path_info> info(specs.size());
+    if (m_pool) {
+      // the other agents' paths as pool rows, the new paths into fresh rows
+      int N = 0, Tpad = 0;
+      std::vector<int32_t>& rowsOf = buf.tables;
+      slotTables(tableNodes, rowsOf, N, Tpad);
+      std::vector<int32_t> outRows;
+      takeRows(specs.size(), outRows);
+      gpuCheck(mrp_pathpool_reserve(m_pool, m_nextRow));
+      const double tg = nowSeconds();
+      prof.llPack += tg - tPack;
+      prof.jobs += (long)specs.size();
+      gpuCheck(mrp_lowlevel_batch_pool(m_maps.data(), (int)m_maps.size(), m_fields, vc.data(),
+                                       (int)vc.size() / 2, ec.data(), (int)ec.size() / 3, m_pool,
+                                       rowsOf.data(), (int)tableNodes.size(), N, Tpad, jobs.data(),
+                                       (int)jobs.size(), &prm, outRows.data(), info.data()));
+      const double tUn = nowSeconds();
+      prof.gpuLowLevel += tUn - tg;
+      for (size_t k = 0; k < specs.size(); ++k) {
+        JobOut& o = out[k];
+        o.status = info[k].status;
+        o.expanded = info[k].expanded;
+        m_inst[specs[k].inst].res.llExpanded += info[k].expanded;
+        if (o.status == 0) {
+          AgentPath ap;
+          ap.cost = info[k].cost;
+          ap.fmin = info[k].fmin;
+          ap.slot = outRows[k];
+          ap.length = info[k].length;
+          o.path = adopt(std::move(ap));
+        } else {
+          giveRow(outRows[k]);
+        }
+      }
+      prof.llUnpack += nowSeconds() - tUn;
+      return;
+    }
+    // path tables of the other agents (ECBS focal heuristics)
+    std::vector<int32_t>& tables = buf.tables;
+    std::vector<int32_t>& tlen = buf.tlen;
+    const bool haveTables = !tableNodes.empty();
+    int N = 0, Tpad = 0;
+    if (haveTables) packTables(tableNodes, tables, tlen, N, Tpad);
     // output staging is kept across calls (no zero fill of tens of MB per launch)
     if (buf.cells.size() < specs.size() * (size_t)m_pathCap) {
       buf.cells.resize(specs.size() * (size_t)m_pathCap);
@@ -523,10 +636,13 @@ class BatchSolver {
       m_inst[specs[k].inst].res.llExpanded += info[k].expanded;
       if (o.status == 0) {
         const int L = info[k].length;
-        o.path.cells.assign(cells.begin() + k * m_pathCap, cells.begin() + k * m_pathCap + L);
-        o.path.g.assign(gs.begin() + k * m_pathCap, gs.begin() + k * m_pathCap + L);
-        o.path.cost = info[k].cost;
-        o.path.fmin = info[k].fmin;
+        AgentPath ap;
+        ap.cells.assign(cells.begin() + k * m_pathCap, cells.begin() + k * m_pathCap + L);
+        ap.g.assign(gs.begin() + k * m_pathCap, gs.begin() + k * m_pathCap + L);
+        ap.cost = info[k].cost;
+        ap.fmin = info[k].fmin;
+        ap.length = L;
+        o.path = adopt(std::move(ap));
       }
     }
     prof.llUnpack += nowSeconds() - tUn;
@@ -576,6 +692,26 @@ class BatchSolver {
     return n;
   }
 
+  // pool mode: the tables of `nodes` as pool rows [B][N] (-1: no path yet) and the
+  // length of the longest path among them
+  void slotTables(const std::vector<const Node*>& nodes, std::vector<int32_t>& rows, int& N,
+                  int& Tpad) const {
+    N = 0;
+    Tpad = 1;
+    for (const Node* n : nodes) N = std::max(N, (int)n->paths.size());
+    rows.assign(nodes.size() * (size_t)N, -1);
+    std::vector<int> tmax(nodes.size(), 1);
+#pragma omp parallel for schedule(static) if (nodes.size() >= kParallelMin)
+    for (long b = 0; b < (long)nodes.size(); ++b)
+      for (size_t a = 0; a < nodes[b]->paths.size(); ++a) {
+        const PathPtr& p = nodes[b]->paths[a];
+        if (!p) continue;
+        rows[b * N + a] = p->slot;
+        tmax[b] = std::max(tmax[b], p->length);
+      }
+    for (int t : tmax) Tpad = std::max(Tpad, t);
+  }
+
   void packTables(const std::vector<const Node*>& nodes, std::vector<int32_t>& tables,
                   std::vector<int32_t>& tlen, int& N, int& Tpad) const {
     N = 0;
@@ -607,11 +743,26 @@ class BatchSolver {
     std::vector<int32_t>& tables = m_evTables;
     std::vector<int32_t>& tlen = m_evTlen;
     int N = 0, Tpad = 0;
-    packTables(nodes, tables, tlen, N, Tpad);
-    m_prof.evalPack += nowSeconds() - tEp;
     const int B = (int)fresh.size();
     std::vector<int32_t> found(B), counts(B);
     std::vector<mrp_conflict> confl(B);
+    if (m_pool) {
+      slotTables(nodes, tables, N, Tpad);
+      const double tg = nowSeconds();
+      m_prof.evalPack += tg - tEp;
+      m_prof.nodes += B;
+      gpuCheck(mrp_conflicts_batch_pool(m_pool, tables.data(), B, N, Tpad, m_dimx, 0, found.data(),
+                                        confl.data(), counts.data()));
+      m_prof.gpuConflicts += nowSeconds() - tg;
+      for (int b = 0; b < B; ++b) {
+        fresh[b]->found = found[b];
+        fresh[b]->conflict = confl[b];
+        fresh[b]->focal = counts[b];
+      }
+      return;
+    }
+    packTables(nodes, tables, tlen, N, Tpad);
+    m_prof.evalPack += nowSeconds() - tEp;
     // getFirstConflict bound: size-1 for cbs/ecbs (cbs.cpp:338-341), size for
     // cbs_ta (cbs_ta.cpp:372-375); focalHeuristic counts with the same table
     const int mode = isTA() ? 1 : 0;
@@ -715,9 +866,9 @@ class BatchSolver {
       return;
     }
     Node& n = *roots[s.inst];
-    n.cost += o.path.cost;
-    n.LB += o.path.fmin;
-    n.paths[s.agent] = std::make_shared<const AgentPath>(std::move(o.path));
+    n.cost += o.path->cost;
+    n.LB += o.path->fmin;
+    n.paths[s.agent] = std::move(o.path);
   }
 
   // ecbs_ta, STYLE_MINROOT (ecbs_ta.hpp:299-348): once the cheapest open node
@@ -889,9 +1040,9 @@ class BatchSolver {
         if (!ok) continue;  // no path under these constraints: the child is dropped
         for (size_t j = cp.firstJob; j < cp.firstJob + cp.nJobs; ++j) {
           const int a = specs[j].agent;
-          n.cost += outs[j].path.cost;
-          n.LB += outs[j].path.fmin;
-          n.paths[a] = std::make_shared<const AgentPath>(std::move(outs[j].path));
+          n.cost += outs[j].path->cost;
+          n.LB += outs[j].path->fmin;
+          n.paths[a] = std::move(outs[j].path);
         }
         n.id = I.nextId++;
         made[q] = cp.node.release();
@@ -920,6 +1071,10 @@ class BatchSolver {
   std::vector<Inst> m_inst;
   std::vector<mrp_map> m_maps;
   mrp_fieldset m_fields = nullptr;
+  mrp_pathpool m_pool = nullptr;  // device rows of the paths (cbs / ecbs)
+  std::vector<int32_t> m_freeRows;
+  int m_nextRow = 0;
+  std::mutex m_rowMutex;
   const ConsPtr m_noCons = std::make_shared<const ConsList>();
   HostProfile m_prof;
   // staging buffers reused across lock-step iterations

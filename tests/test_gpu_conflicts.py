@@ -280,3 +280,55 @@ def test_c5_table_equals_the_oracle_golden(capi):
     # and through the host-pointer entry points
     assert capi.count_conflicts(tab, ln, 0) == gold["count"]
     assert list(capi.first_conflict(tab, ln, DIM, 0)) == gold["first_conflict"]
+
+
+def test_path_pool_rows_and_conflicts(capi, orc):
+    """mrp_pathpool_write / _read round trip over two chunks of rows, and
+    mrp_conflicts_batch_pool (tables gathered on the device from row numbers, -1 = agent
+    without a path) against mrp_conflicts_batch on the same tables."""
+    rng = np.random.default_rng(77)
+    cap, dimx = 48, 16
+    pool = capi.PathPool(cap)
+    n = 400
+    slots = rng.choice(40000, n, replace=False).astype(np.int32)  # beyond the first 32768-row chunk
+    pool.reserve(int(slots.max()) + 1)
+    length = rng.integers(1, cap + 1, n).astype(np.int32)
+    cells = rng.integers(0, dimx * dimx, (n, cap)).astype(np.int32)
+    # random walks so that conflicts are real ones
+    for i in range(n):
+        c = int(cells[i, 0])
+        for t in range(1, cap):
+            x, y = c % dimx, c // dimx
+            dx, dy = [(0, 0), (1, 0), (-1, 0), (0, 1), (0, -1)][int(rng.integers(0, 5))]
+            x, y = min(max(x + dx, 0), dimx - 1), min(max(y + dy, 0), dimx - 1)
+            c = x + dimx * y
+            cells[i, t] = c
+    pool.write(slots, cells, length)
+    back, blen = pool.read(slots[::-1].copy())
+    assert np.array_equal(blen, length[::-1])
+    for k in range(n):
+        L = length[n - 1 - k]
+        assert np.array_equal(back[k, :L], cells[n - 1 - k, :L])
+    B, N = 30, 12
+    pick = rng.integers(0, n, (B, N))
+    pick[3, 5] = -1
+    pick[7, 0] = -1
+    table_slots = np.where(pick >= 0, slots[np.maximum(pick, 0)], -1).astype(np.int32)
+    Tpad = int(length.max())
+    dense = np.zeros((B, N, Tpad), np.int32)
+    dlen = np.zeros((B, N), np.int32)
+    for b in range(B):
+        for a in range(N):
+            if pick[b, a] >= 0:
+                L = length[pick[b, a]]
+                dense[b, a, :L] = cells[pick[b, a], :L]
+                dlen[b, a] = L
+    for mode in (0, 1):
+        ref_c, ref_n = capi.conflicts_batch(dense, dlen, dimx, mode)
+        got_c, got_n = pool.conflicts_batch(table_slots, Tpad, dimx, mode)
+        assert got_c == ref_c
+        assert np.array_equal(got_n, ref_n)
+        assert sum(c is not None for c in ref_c) >= B // 2
+    with pytest.raises(capi.MrpError):
+        pool.read(np.array([10 ** 6], np.int32))
+    pool.close()

@@ -431,3 +431,28 @@ def test_output_yaml_replays_like_visualize_py(capi, set32, tmp_path):
         assert (pos >= -0.5).all() and (pos[:, 0] <= inst.dimx - 0.5).all() and (pos[:, 1] <= inst.dimy - 0.5).all()
         dist = np.linalg.norm(pos[:, None, :] - pos[None, :, :], axis=2) + 10 * np.eye(len(names))
         assert dist.min() >= 0.7, "visualize.py would print COLLISION at frame %d" % i
+
+
+def test_path_pool_gives_the_same_answers(capi, set8, set32, monkeypatch):
+    """cbs / ecbs batches keep their paths in a device pool (mrp_pathpool_*: nodes are
+    lists of row numbers, conflict tables are gathered on the device, replans write
+    their path into a fresh row); MRP_HOST_POOL=0 is the driver that ships whole
+    tables.  Same searches: status, cost, makespan, expansion counts and every
+    path must be identical."""
+    from libmultirobotplanning_b200 import solver
+    cases = [(solver.CBS, set8[:96], dict(max_hl=300)),
+             (solver.CBS, [i for i in set32 if i.n_agents <= 20][:40], dict(max_hl=300)),
+             (solver.ECBS, [i for i in set32 if i.n_agents in (30, 50)][:24], dict(w=1.3, max_hl=500)),
+             (solver.ECBS, set8[:64], dict(w=1.5, max_hl=300))]
+    for algo, insts, kw in cases:
+        monkeypatch.setenv("MRP_HOST_POOL", "0")
+        ref = solver.solve_batch(algo, insts, **kw)
+        monkeypatch.delenv("MRP_HOST_POOL")
+        got = solver.solve_batch(algo, insts, **kw)
+        assert sum(r["status"] == 0 for r in ref) >= len(insts) // 3
+        for a, b in zip(got, ref):
+            for key in ("status", "cost", "makespan", "lower_bound", "hl_expanded", "ll_expanded"):
+                assert a[key] == b[key], key
+            assert len(a["paths"]) == len(b["paths"])
+            for pa, pb in zip(a["paths"], b["paths"]):
+                assert np.array_equal(np.asarray(pa), np.asarray(pb))

@@ -16,9 +16,13 @@ insts, _ = bench.c3_shard(pkg, s32, 0)
 insts = insts[:n]
 pkg.solver.solve_batch(pkg.solver.ECBS, insts[:2], w=1.3, max_hl=50)
 sys.stderr.write("==== timed batch ====\n")
-t0 = time.perf_counter()
-res = pkg.solver.solve_batch(pkg.solver.ECBS, insts, w=1.3, max_hl=2000, max_seconds=120)
-dt = time.perf_counter() - t0
+runs = int(os.environ.get("PROF_RUNS", "1"))  # later runs find the lanes' device arenas grown
+for _ in range(runs):
+    t0 = time.perf_counter()
+    res = pkg.solver.solve_batch(pkg.solver.ECBS, insts, w=1.3, max_hl=2000, max_seconds=120)
+    dt = time.perf_counter() - t0
+    if runs > 1:
+        print("run: %.2f s" % dt, end="; ")
 ok = sum(r["status"] == 0 for r in res)
 print("%d/%d solved in %.2f s = %.1f instances/s" % (ok, len(insts), dt, ok / dt))
 import collections
