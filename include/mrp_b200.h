@@ -296,6 +296,29 @@ int mrp_lowlevel_batch_pool(const mrp_map* maps, int n_maps, mrp_fieldset fs,
                             const mrp_lowlevel_params* params, const int32_t* out_slots,
                             mrp_path_info* info);
 
+/* Sliced searches (single-tile maps): a lock-step batch lasts as long as its longest
+ * search, and on 100-agent instances the longest of a few hundred replans is
+ * thousands of expansions while the typical one is a few dozen.  With a slice, job j
+ * stops after slice_expanded expansions of this call (info[j].status ==
+ * MRP_SUSPENDED) and leaves its search state (OPEN, visited set, node pool) in blob
+ * state_ids[j] of the pool; a later call with resume[j] != 0 and the same job
+ * continues it — the same search, expansion for expansion, cut into launches, while
+ * the instances whose replans are done move on.  state_ids[j] == -1: that job runs to
+ * its end.  Maps the shared-memory kernel does not take (more than one 32x32 tile)
+ * ignore the slice.  Blobs are reserved with mrp_pathpool_reserve_states (one layout
+ * per pool: map size and expansion cap of the first call). */
+#define MRP_SUSPENDED 4
+int mrp_pathpool_reserve_states(mrp_pathpool pool, int n_states, int dimx, int dimy,
+                                int max_expanded);
+int mrp_lowlevel_batch_pool_sliced(const mrp_map* maps, int n_maps, mrp_fieldset fs,
+                                   const int32_t* vc, int n_vc, const int32_t* ec, int n_ec,
+                                   mrp_pathpool pool, const int32_t* table_slots,
+                                   int n_tables, int N, int Tpad, const mrp_job* jobs,
+                                   int n_jobs, const mrp_lowlevel_params* params,
+                                   const int32_t* out_slots, const int32_t* state_ids,
+                                   const int32_t* resume, int slice_expanded,
+                                   mrp_path_info* info);
+
 /* ---- multi-GPU ----------------------------------------------------------
  * One process (or host thread) per GPU, as SURVEY.md §8(e) shards the path:
  * distance fields by goal, conflict checks by agent-pair block, replans by

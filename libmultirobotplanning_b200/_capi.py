@@ -60,6 +60,7 @@ EXPORTS = [
     "mrp_conflicts_sharded_dev", "mrp_bfs_fields_packed",
     "mrp_pathpool_create", "mrp_pathpool_destroy", "mrp_pathpool_reserve", "mrp_pathpool_write",
     "mrp_pathpool_read", "mrp_conflicts_batch_pool", "mrp_lowlevel_batch_pool",
+    "mrp_pathpool_reserve_states", "mrp_lowlevel_batch_pool_sliced",
 ]
 COMM_ID_BYTES = 128
 

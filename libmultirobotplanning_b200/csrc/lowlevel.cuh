@@ -58,6 +58,14 @@ struct LLParams {
   int32_t* const* poolCells;  // per chunk: [kPoolChunk][rowCap]
   int32_t* const* poolLen;    // per chunk: [kPoolChunk]
   int rowCap;
+  // sliced searches (tile kernel): a job with jobState[j] >= 0 stops after sliceCap
+  // expansions of this launch (status kTileStatusSuspended) and leaves its search state
+  // in blob jobState[j]; jobResume[j] != 0 continues from that blob
+  const int32_t* jobState;
+  const int32_t* jobResume;
+  unsigned char* const* stateChunks;  // per chunk: [kStateChunk][blobBytes]
+  size_t blobBytes;
+  int sliceCap;
 };
 
 constexpr int kPoolChunkBits = 15;
@@ -91,6 +99,13 @@ struct LLPool {
   int32_t* const* d_poolLen = nullptr;
   const int32_t* h_outSlots = nullptr;  // host: [n_jobs]
   int rowCap = 0;
+  // sliced searches: host arrays [n_jobs] (NULL: every job runs to its end)
+  const int32_t* h_jobState = nullptr;
+  const int32_t* h_jobResume = nullptr;
+  unsigned char* const* d_stateChunks = nullptr;
+  size_t blobBytes = 0;
+  int sliceCap = 0;
+  int tileTB = 0;  // rows of the visited bitmap the blobs were laid out for
 };
 int lowlevelRun(const mrp_map* maps, int n_maps, const int32_t* fields, const int32_t* d_fields,
                 int n_fields, const int32_t* vc, int n_vc, const int32_t* ec, int n_ec,
@@ -130,6 +145,10 @@ __device__ __forceinline__ unsigned long long packOpenKey(int focal, int f, int 
 
 // ---- tile kernel (lowlevel_tile.cu) ----
 constexpr int kTileStatusRedo = 3;  // job left to the general kernel
+constexpr int kTileStatusSuspended = 4;  // slice used up: continue from the state blob (MRP_SUSPENDED)
+constexpr int kStateChunkBits = 6;
+constexpr int kStateChunk = 1 << kStateChunkBits;  // state blobs per device allocation
+size_t lowlevelTileBlobBytes(int TB, int maxNodes);
 bool lowlevelTileEligible(const LLParams& p, int n_tables);
 size_t lowlevelTileOccBytes(int n_tables, int Tpad);
 int lowlevelTileSlots(const LLParams& p);

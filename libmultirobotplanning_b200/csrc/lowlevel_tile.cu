@@ -180,9 +180,11 @@ __global__ void __launch_bounds__(32) lowlevel_tile_kernel(LLParams p) {
   const int TB = p.TB;
   const int dimx = p.dimx, dimy = p.dimy;
   const int cells = dimx * dimy;
-  uint32_t* nodeKeyG = p.nodeKey + (size_t)slot * p.maxNodes;
-  int32_t* nodeParG = p.nodeParent + (size_t)slot * p.maxNodes;
-  unsigned long long* openG = p.openKey + (size_t)slot * p.maxNodes;
+  // what does not fit shared memory: per warp slot, or in the job's state blob
+  uint32_t* const nodeKeySlot = p.nodeKey + (size_t)slot * p.maxNodes;
+  int32_t* const nodeParSlot = p.nodeParent + (size_t)slot * p.maxNodes;
+  unsigned long long* const openSlot = p.openKey + (size_t)slot * p.maxNodes;
+  const int imageBytes = lay.total;
 
   // a cell of the map (x + dimx*y) as tile position (y*32 + x) and back
   auto toTile = [&](int c) -> int { return dimx == 32 ? c : ((c / dimx) << 5) | (c % dimx); };
@@ -208,6 +210,21 @@ __global__ void __launch_bounds__(32) lowlevel_tile_kernel(LLParams p) {
 
     int status = -1;  // running
     if (goal < 0 || nVc + nEc > kConsCache) status = kTileStatusRedo;
+    // sliced search: blob = [64-byte header][image of the shared-memory regions][spill arrays]
+    const int stateId = p.jobState ? p.jobState[job] : -1;
+    unsigned char* blob = stateId >= 0 ? p.stateChunks[stateId >> kStateChunkBits] +
+                                             (size_t)(stateId & (kStateChunk - 1)) * p.blobBytes
+                                       : nullptr;
+    const bool resume = blob && p.jobResume[job] != 0;
+    uint32_t* nodeKeyG = nodeKeySlot;
+    int32_t* nodeParG = nodeParSlot;
+    unsigned long long* openG = openSlot;
+    if (blob) {
+      unsigned char* sp = blob + 64 + imageBytes;
+      openG = reinterpret_cast<unsigned long long*>(sp);
+      nodeKeyG = reinterpret_cast<uint32_t*>(sp + (size_t)p.maxNodes * 8);
+      nodeParG = reinterpret_cast<int32_t*>(sp + (size_t)p.maxNodes * 12);
+    }
 
     // ---- per-job setup ----
     __syncwarp();
@@ -308,7 +325,38 @@ __global__ void __launch_bounds__(32) lowlevel_tile_kernel(LLParams p) {
     int goalNode = -1, tailFrom = -1, goalF = 0;
     const int startTile = toTile(jb.start_cell);
     int bestF = 0;
-    if (status == -1) {
+    // warp copy between the shared-memory regions and their image in the blob
+    auto copyRegion = [&](int off, int bytes, bool toShared) {
+      uint4* sm = reinterpret_cast<uint4*>(smemRaw + off);
+      uint4* gl = reinterpret_cast<uint4*>(blob + 64 + off);
+      const int n = (bytes + 15) >> 4;
+      if (toShared)
+        for (int i = lane; i < n; i += 32) sm[i] = gl[i];
+      else
+        for (int i = lane; i < n; i += 32) gl[i] = sm[i];
+    };
+    auto copyState = [&](bool toShared) {
+      copyRegion(lay.openKey, min(nOpen, kOpenT) * 8, toShared);
+      copyRegion(lay.openState, min(nOpen, kOpenT) * 4, toShared);
+      copyRegion(lay.vis, (tTop + 1) * 128, toShared);
+      copyRegion(lay.nodeKey, min(nNodes, kNodeT) * 4, toShared);
+      copyRegion(lay.nodePar, min(nNodes, kNodeT) * 2, toShared);
+      copyRegion(lay.hist, kFMaxT * 2, toShared);
+    };
+    int expandedBefore = 0;
+    if (status == -1 && resume) {
+      // the setup above rebuilt everything that does not change during a search; the
+      // search itself continues from the blob
+      const int* hdr = reinterpret_cast<const int*>(blob);
+      nNodes = hdr[0];
+      nOpen = hdr[1];
+      expanded = hdr[2];
+      bestF = hdr[3];
+      tTop = max(tTop, hdr[4]);
+      expandedBefore = expanded;
+      __syncwarp();
+      copyState(true);
+    } else if (status == -1) {
       const int h0 = heur(startTile, 0);
       if (h0 == MRP_INF) {
         status = 1;
@@ -363,6 +411,10 @@ __global__ void __launch_bounds__(32) lowlevel_tile_kernel(LLParams p) {
     while (status == -1) {
       if (nOpen == 0) {
         status = 1;
+        break;
+      }
+      if (blob && p.sliceCap > 0 && expanded - expandedBefore >= p.sliceCap) {
+        status = kTileStatusSuspended;  // the rest of this search belongs to a later launch
         break;
       }
       while (bestF < kFMaxT && sLdU16(aHist + 2u * (uint32_t)bestF) == 0) ++bestF;
@@ -614,6 +666,17 @@ __global__ void __launch_bounds__(32) lowlevel_tile_kernel(LLParams p) {
     }
     __syncwarp();
 
+    if (status == kTileStatusSuspended) {
+      copyState(false);
+      if (lane == 0) {
+        int* hdr = reinterpret_cast<int*>(blob);
+        hdr[0] = nNodes;
+        hdr[1] = nOpen;
+        hdr[2] = expanded;
+        hdr[3] = bestF;
+        hdr[4] = tTop;
+      }
+    }
     // ---- result ----
     mrp_path_info pi;
     pi.status = status;
@@ -677,7 +740,12 @@ __global__ void __launch_bounds__(32) lowlevel_tile_kernel(LLParams p) {
 }
 
 // ---- host side ----
+size_t lowlevelTileBlobBytes(int TB, int maxNodes) {
+  return (64 + (size_t)tileLayout(TB).total + (size_t)maxNodes * 16 + 255) & ~(size_t)255;
+}
+
 static int tileRows(const LLParams& p) {
+  if (p.TB > 0) return p.TB;  // sliced searches: the layout the state blobs were made for
   if (const char* e = getenv("MRP_LL_TILE_TB")) return std::max(32, std::min(512, atoi(e) & ~31));
   if (p.dimx * p.dimy <= 64) return 64;
   return p.Tpad <= 88 ? 128 : (p.Tpad <= 150 ? 192 : 256);

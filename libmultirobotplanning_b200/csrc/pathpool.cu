@@ -26,6 +26,12 @@ struct mrp_pathpool_s {
   int32_t** d_cells = nullptr;       // device copies of the two pointer lists
   int32_t** d_len = nullptr;
   int maxChunks = 0;
+  // state blobs of sliced searches (lowlevel_tile.cu)
+  std::vector<unsigned char*> states;
+  unsigned char** d_states = nullptr;
+  int nStates = 0;
+  size_t blobBytes = 0;
+  int tileTB = 0, stateMaxNodes = 0;
 };
 
 namespace mrp {
@@ -119,7 +125,8 @@ int mrp_pathpool_create(int row_cap, mrp_pathpool* out) {
   p->rowCap = row_cap;
   p->maxChunks = 4096;
   if (cudaMalloc(&p->d_cells, sizeof(void*) * p->maxChunks) != cudaSuccess ||
-      cudaMalloc(&p->d_len, sizeof(void*) * p->maxChunks) != cudaSuccess) {
+      cudaMalloc(&p->d_len, sizeof(void*) * p->maxChunks) != cudaSuccess ||
+      cudaMalloc(&p->d_states, sizeof(void*) * p->maxChunks) != cudaSuccess) {
     if (p->d_cells) cudaFree(p->d_cells);
     delete p;
     return fail(MRP_ERR_NOMEM, "cudaMalloc failed for the path pool");
@@ -132,6 +139,8 @@ int mrp_pathpool_destroy(mrp_pathpool pool) {
   if (!pool) return 0;
   for (int32_t* c : pool->cells) cudaFree(c);
   for (int32_t* l : pool->len) cudaFree(l);
+  for (unsigned char* b : pool->states) cudaFree(b);
+  cudaFree(pool->d_states);
   cudaFree(pool->d_cells);
   cudaFree(pool->d_len);
   delete pool;
@@ -160,6 +169,35 @@ int mrp_pathpool_reserve(mrp_pathpool pool, int n_slots) {
     MRP_CUDA(cudaMemcpy(pool->d_cells + k, &c, sizeof(void*), cudaMemcpyHostToDevice));
     MRP_CUDA(cudaMemcpy(pool->d_len + k, &l, sizeof(void*), cudaMemcpyHostToDevice));
     pool->nSlots += kPoolChunk;
+  }
+  return 0;
+}
+
+int mrp_pathpool_reserve_states(mrp_pathpool pool, int n_states, int dimx, int dimy, int max_expanded) {
+  MRP_CHECK(pool != nullptr && n_states >= 0 && max_expanded > 0 && dimx > 0 && dimy > 0, MRP_ERR_INVALID,
+            "bad arguments");
+  const int TB = dimx * dimy <= 64 ? 64 : 192;
+  const int maxNodes = 5 * max_expanded + 8;
+  if (pool->blobBytes == 0) {
+    pool->tileTB = TB;
+    pool->stateMaxNodes = maxNodes;
+    pool->blobBytes = lowlevelTileBlobBytes(TB, maxNodes);
+  }
+  MRP_CHECK(pool->tileTB == TB && pool->stateMaxNodes >= maxNodes, MRP_ERR_INVALID,
+            "the state blobs of this pool were laid out for another map size / expansion cap");
+  if (n_states <= pool->nStates) return 0;
+  std::lock_guard<std::mutex> lk(apiMutex());
+  if (int rc = ensureInit()) return rc;
+  while (pool->nStates < n_states) {
+    MRP_CHECK((int)pool->states.size() < pool->maxChunks, MRP_ERR_NOMEM, "too many search states (%d)", pool->nStates);
+    unsigned char* b = nullptr;
+    cudaError_t e = cudaMalloc(&b, (size_t)kStateChunk * pool->blobBytes);
+    if (e != cudaSuccess)
+      return fail(MRP_ERR_NOMEM, "cudaMalloc failed for a chunk of search states: %s", cudaGetErrorString(e));
+    const size_t k = pool->states.size();
+    pool->states.push_back(b);
+    MRP_CUDA(cudaMemcpy(pool->d_states + k, &b, sizeof(void*), cudaMemcpyHostToDevice));
+    pool->nStates += kStateChunk;
   }
   return 0;
 }
@@ -259,6 +297,16 @@ int mrp_lowlevel_batch_pool(const mrp_map* maps, int n_maps, mrp_fieldset fs, co
                             const int32_t* ec, int n_ec, mrp_pathpool pool, const int32_t* table_slots,
                             int n_tables, int N, int Tpad, const mrp_job* jobs, int n_jobs,
                             const mrp_lowlevel_params* params, const int32_t* out_slots, mrp_path_info* info) {
+  return mrp_lowlevel_batch_pool_sliced(maps, n_maps, fs, vc, n_vc, ec, n_ec, pool, table_slots, n_tables, N, Tpad,
+                                        jobs, n_jobs, params, out_slots, nullptr, nullptr, 0, info);
+}
+
+int mrp_lowlevel_batch_pool_sliced(const mrp_map* maps, int n_maps, mrp_fieldset fs, const int32_t* vc, int n_vc,
+                                   const int32_t* ec, int n_ec, mrp_pathpool pool, const int32_t* table_slots,
+                                   int n_tables, int N, int Tpad, const mrp_job* jobs, int n_jobs,
+                                   const mrp_lowlevel_params* params, const int32_t* out_slots,
+                                   const int32_t* state_ids, const int32_t* resume, int slice_expanded,
+                                   mrp_path_info* info) {
   MRP_CHECK(pool != nullptr && fs != nullptr, MRP_ERR_INVALID, "pool or field set is NULL");
   MRP_CHECK(n_jobs >= 0 && n_tables >= 0 && N >= 0 && Tpad >= 0, MRP_ERR_INVALID, "negative count");
   if (n_jobs == 0) return 0;
@@ -270,6 +318,20 @@ int mrp_lowlevel_batch_pool(const mrp_map* maps, int n_maps, mrp_fieldset fs, co
   if (int rc = checkSlots(pool, out_slots, (size_t)n_jobs, false)) return rc;
   if (int rc = checkSlots(pool, table_slots, (size_t)n_tables * N, true)) return rc;
   LLPool lp;
+  if (state_ids && slice_expanded > 0) {
+    MRP_CHECK(resume != nullptr && params != nullptr, MRP_ERR_INVALID, "NULL pointer");
+    MRP_CHECK(pool->blobBytes > 0 && 5 * params->max_expanded + 8 <= pool->stateMaxNodes, MRP_ERR_INVALID,
+              "mrp_pathpool_reserve_states first (with this expansion cap)");
+    for (int j = 0; j < n_jobs; ++j)
+      MRP_CHECK(state_ids[j] >= -1 && state_ids[j] < pool->nStates, MRP_ERR_INVALID, "job %d: bad search state %d",
+                j, state_ids[j]);
+    lp.h_jobState = state_ids;
+    lp.h_jobResume = resume;
+    lp.d_stateChunks = pool->d_states;
+    lp.blobBytes = pool->blobBytes;
+    lp.sliceCap = slice_expanded;
+    lp.tileTB = pool->tileTB;
+  }
   lp.d_poolCells = pool->d_cells;
   lp.d_poolLen = pool->d_len;
   lp.h_outSlots = out_slots;

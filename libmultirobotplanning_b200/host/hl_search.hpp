@@ -98,7 +98,7 @@ enum class Algo { CBS = 0, ECBS = 1, CBSTA = 2, ECBSTA = 3 };
 struct HostProfile {
   double gpuConflicts = 0, gpuLowLevel = 0, total = 0, setup = 0;
   double pop = 0, build = 0, llPack = 0, llUnpack = 0, evalPack = 0, absorb = 0;
-  long iterations = 0, nodes = 0, jobs = 0, deferred = 0;
+  long iterations = 0, nodes = 0, jobs = 0, deferred = 0, launches = 0;
 };
 inline double nowSeconds() {
   return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch())
@@ -134,6 +134,7 @@ class BatchSolver {
       m_slowCv.notify_all();
       m_slowThread.join();
     }
+    m_flights.clear();
     for (Node* n : m_slowOut) delete n;
     for (Inst& I : m_inst) {
       for (Node* n : I.open) delete n;
@@ -158,12 +159,19 @@ class BatchSolver {
     };
     std::vector<Node*> fresh;
     const double tRun = nowSeconds();
+    // Sliced replans (pool mode, single-tile maps): every launch gives each unfinished
+    // replan at most m_slice expansions; an instance whose replans are done moves on to
+    // its next expansion while the long searches of the others continue in the next
+    // launches (MRP_HOST_SLICE=0: every launch runs its replans to the end).
+    if (const char* e = getenv("MRP_HOST_SLICE")) m_slice = atoi(e);
+    m_sliced = m_pool && m_slice > 0 && m_dimx <= 32 && m_dimy <= 32;
     buildRoots(fresh);
     // (the path pool belongs to one lane: pool mode keeps to the lock-step launches)
     const bool twoSpeed = m_opt.fastLlExpanded > 0 && m_opt.fastLlExpanded < m_opt.maxLlExpanded &&
                           m_opt.slowLane >= 0 && (m_algo == Algo::CBS || m_algo == Algo::ECBS) && !m_pool;
     if (twoSpeed) m_slowThread = std::thread([this] { slowWorker(); });
     size_t nSuspended = 0;
+    const bool sliced = m_sliced;
     while (true) {
       ++m_prof.iterations;
       if (twoSpeed) nSuspended -= collectSlow(fresh, false);
@@ -183,7 +191,7 @@ class BatchSolver {
 #pragma omp parallel for schedule(dynamic, 16) if (m_inst.size() >= kParallelMin)
       for (long k = 0; k < (long)m_inst.size(); ++k) {
         Inst& I = m_inst[k];
-        if (I.done || I.suspended) continue;
+        if (I.done || I.suspended || I.busy) continue;
         if (I.open.empty()) {
           finish(I, kNoSolution, nullptr, tNow);
           continue;
@@ -210,6 +218,20 @@ class BatchSolver {
       }
       fetchSolutions();
       m_prof.pop += nowSeconds() - tPop;
+      if (sliced) {
+        if (timeUp) {
+          for (auto& f : m_flights) {
+            finish(m_inst[f->pd.inst], kCapped, nullptr, tNow);
+            dropFlight(*f);
+          }
+          m_flights.clear();
+        }
+        startFlights(pending);
+        if (m_flights.empty()) break;
+        runFlights();
+        absorbFlights(fresh);
+        continue;
+      }
       if (!anyRunning) {
         if (nSuspended == 0) break;
         nSuspended -= collectSlow(fresh, true);  // nothing to do but wait for the slow lane
@@ -299,6 +321,7 @@ class BatchSolver {
     std::set<Node*, OpenOrder> open;  // owning
     int nextId = 0;
     bool done = false;
+    bool busy = false;       // sliced replans of its current expansion are still running
     bool suspended = false;  // its expansion is being redone in the slow lane
     int mapIdx = 0;
     int fieldBase = 0;                 // first field of this instance in the set
@@ -318,8 +341,8 @@ class BatchSolver {
     int table, self;
   };
   struct JobOut {
-    int status;
-    long expanded;
+    int status = 1;
+    long expanded = 0;
     PathPtr path;  // set iff status == 0
   };
 
@@ -809,6 +832,25 @@ class BatchSolver {
       }
       roots[k] = std::move(n);
     }
+    if (isFocal() && m_sliced) {
+      // the agents of a root are planned one after the other (ecbs.hpp:118-136), but the
+      // instances need not wait for each other: one flight per root, one sliced replan
+      // at a time, and the finished root joins `fresh` in the main loop
+      for (size_t k = 0; k < m_inst.size(); ++k) {
+        if (!roots[k]) continue;
+        std::unique_ptr<Flight> f(new Flight());
+        f->pd.inst = (int)k;
+        f->root = std::move(roots[k]);
+        f->nextAgent = 0;
+        if (!nextRootJob(*f)) {  // no agents: the empty root is complete
+          fresh.push_back(f->root.release());
+          continue;
+        }
+        m_inst[k].busy = true;
+        m_flights.push_back(std::move(f));
+      }
+      return;
+    }
     if (isFocal()) {
       planSequential(roots, true);
       for (size_t k = 0; k < m_inst.size(); ++k)
@@ -908,6 +950,258 @@ class BatchSolver {
       if (triggered[k] && !I.done && !I.open.empty())
         I.nextRootNodeCost = (long)((float)(*I.open.begin())->LB * m_opt.w);
     }
+  }
+
+  // ---- sliced expansions (pool mode) ---------------------------------------------
+  struct FlightJob {
+    JobSpec spec;
+    int32_t outRow = -1, state = -1;
+    bool started = false, done = false;
+    JobOut out;
+  };
+  struct FlightChild {
+    int agent = 0;
+    std::unique_ptr<Node> node;
+  };
+  // one high-level expansion in progress: the parent, its two children and their replans
+  struct Flight {
+    Pending pd;
+    std::vector<FlightChild> kids;  // kids[q] is replanned by jobs[q]
+    std::vector<FlightJob> jobs;
+    // a root under construction (ecbs): its agents are planned one by one, jobs[0] is
+    // the replan of agent nextAgent and sees the agents planned so far
+    std::unique_ptr<Node> root;
+    int nextAgent = 0;
+  };
+  bool nextRootJob(Flight& f) {
+    const Inst& I = m_inst[f.pd.inst];
+    if ((size_t)f.nextAgent >= I.in->numAgents()) return false;
+    const int a = f.nextAgent;
+    FlightJob j;
+    j.spec = {f.pd.inst, a, f.root->task[a], fieldFor(I, a, f.root->task[a]), f.root->cons[a].get(), -1, a};
+    f.jobs.clear();
+    f.jobs.push_back(std::move(j));
+    return true;
+  }
+  void takeStates(size_t n, std::vector<int32_t>& ids) {
+    ids.resize(n);
+    for (size_t i = 0; i < n; ++i) {
+      if (!m_freeStates.empty()) {
+        ids[i] = m_freeStates.back();
+        m_freeStates.pop_back();
+      } else {
+        ids[i] = m_nextState++;
+      }
+    }
+  }
+  void dropFlight(Flight& f) {
+    for (FlightJob& j : f.jobs) {
+      if (j.state >= 0) m_freeStates.push_back(j.state);
+      if (j.outRow >= 0 && !j.out.path) giveRow(j.outRow);
+      j.state = j.outRow = -1;
+    }
+    m_inst[f.pd.inst].busy = false;
+  }
+  // createConstraintsFromConflict (example/cbs.cpp:388-406) for every popped parent:
+  // two children in ascending agent order, one replan each
+  void startFlights(std::vector<Pending>& pending) {
+    if (pending.empty()) return;
+    const double tBuild = nowSeconds();
+    std::vector<std::unique_ptr<Flight> > made(pending.size());
+#pragma omp parallel for schedule(dynamic, 16) if (pending.size() >= kParallelMin)
+    for (long pi = 0; pi < (long)pending.size(); ++pi) {
+      std::unique_ptr<Flight> f(new Flight());
+      Inst& I = m_inst[pending[pi].inst];
+      const Node& P = *pending[pi].parent;
+      const mrp_conflict& c = P.conflict;
+      const int c1 = c.x1 + m_dimx * c.y1;
+      const int c2 = c.type == 1 ? c.x2 + m_dimx * c.y2 : -1;
+      for (int side = 0; side < 2; ++side) {
+        const int agent = side == 0 ? c.agent1 : c.agent2;
+        std::unique_ptr<Node> n(new Node(P));  // shares paths / constraint lists
+        std::shared_ptr<ConsList> cl = std::make_shared<ConsList>(*P.cons[agent]);
+        if (c.type == 0) {
+          cl->vc.push_back(c.time);
+          cl->vc.push_back(c1);
+        } else {
+          cl->ec.push_back(c.time);
+          cl->ec.push_back(side == 0 ? c1 : c2);
+          cl->ec.push_back(side == 0 ? c2 : c1);
+        }
+        n->cons[agent] = cl;
+        n->cost -= n->paths[agent]->cost;
+        n->LB -= n->paths[agent]->fmin;
+        FlightJob j;
+        j.spec = {pending[pi].inst, agent, n->task[agent], fieldFor(I, agent, n->task[agent]),
+                  n->cons[agent].get(), -1, agent};
+        f->jobs.push_back(std::move(j));
+        FlightChild k;
+        k.agent = agent;
+        k.node = std::move(n);
+        f->kids.push_back(std::move(k));
+      }
+      f->pd = std::move(pending[pi]);
+      I.busy = true;
+      made[pi] = std::move(f);
+    }
+    for (auto& f : made) m_flights.push_back(std::move(f));
+    m_prof.build += nowSeconds() - tBuild;
+  }
+  // one launch: every unfinished replan of every flight gets (at most) one slice
+  void runFlights() {
+    const double tPack = nowSeconds();
+    std::vector<std::pair<Flight*, FlightJob*> > run;
+    std::vector<const Node*> tabs;
+    std::vector<mrp_job> jobs;
+    std::vector<int32_t> vc, ec, outRows, states, resume;
+    size_t needRows = 0, needStates = 0;
+    for (auto& f : m_flights)
+      for (FlightJob& j : f->jobs)
+        if (!j.done) {
+          if (j.outRow < 0) ++needRows;
+          if (j.state < 0) ++needStates;
+        }
+    std::vector<int32_t> newRows, newStates;
+    takeRows(needRows, newRows);
+    takeStates(needStates, newStates);
+    size_t ir = 0, is = 0;
+    for (auto& f : m_flights) {
+      int table = -1;
+      for (FlightJob& j : f->jobs) {
+        if (j.done) continue;
+        if (isFocal() && table < 0) {
+          table = (int)tabs.size();
+          tabs.push_back(f->root ? f->root.get() : f->pd.parent.get());
+        }
+        if (j.outRow < 0) j.outRow = newRows[ir++];
+        if (j.state < 0) j.state = newStates[is++];
+        const JobSpec& sp = j.spec;
+        mrp_job mj;
+        mj.map = m_inst[sp.inst].mapIdx;
+        mj.start_cell = m_inst[sp.inst].in->starts[sp.agent];
+        mj.goal_cell = sp.goal;
+        mj.field = sp.field;
+        mj.vc_begin = (int)vc.size() / 2;
+        vc.insert(vc.end(), sp.cons->vc.begin(), sp.cons->vc.end());
+        mj.vc_end = (int)vc.size() / 2;
+        mj.ec_begin = (int)ec.size() / 3;
+        ec.insert(ec.end(), sp.cons->ec.begin(), sp.cons->ec.end());
+        mj.ec_end = (int)ec.size() / 3;
+        mj.table = table;
+        mj.self = sp.self;
+        jobs.push_back(mj);
+        outRows.push_back(j.outRow);
+        states.push_back(j.state);
+        resume.push_back(j.started ? 1 : 0);
+        run.push_back(std::make_pair(f.get(), &j));
+      }
+    }
+    if (jobs.empty()) return;
+    int N = 0, Tpad = 0;
+    std::vector<int32_t>& rowsOf = m_mainBuf.tables;
+    slotTables(tabs, rowsOf, N, Tpad);
+    gpuCheck(mrp_pathpool_reserve(m_pool, m_nextRow));
+    gpuCheck(mrp_pathpool_reserve_states(m_pool, m_nextState, m_dimx, m_dimy, m_opt.maxLlExpanded));
+    mrp_lowlevel_params prm;
+    prm.variant = 0;
+    prm.w = isFocal() ? m_opt.w : 0.0f;
+    prm.max_expanded = m_opt.maxLlExpanded;
+    prm.path_cap = m_pathCap;
+    std::vector<mrp_path_info> info(jobs.size());
+    const double tg = nowSeconds();
+    m_prof.llPack += tg - tPack;
+    // few replans left (the stragglers of a batch): nobody gains from short launches, the
+    // per-launch overhead is all that is left to save
+    const int slice = jobs.size() <= 16 ? 4 * m_slice : (jobs.size() <= 64 ? 2 * m_slice : m_slice);
+    gpuCheck(mrp_lowlevel_batch_pool_sliced(m_maps.data(), (int)m_maps.size(), m_fields, vc.data(),
+                                            (int)vc.size() / 2, ec.data(), (int)ec.size() / 3, m_pool,
+                                            rowsOf.data(), (int)tabs.size(), N, Tpad, jobs.data(),
+                                            (int)jobs.size(), &prm, outRows.data(), states.data(),
+                                            resume.data(), slice, info.data()));
+    const double tUn = nowSeconds();
+    m_prof.gpuLowLevel += tUn - tg;
+    ++m_prof.launches;
+    for (size_t k = 0; k < run.size(); ++k) {
+      FlightJob& j = *run[k].second;
+      if (info[k].status == MRP_SUSPENDED) {
+        j.started = true;
+        continue;
+      }
+      j.done = true;
+      ++m_prof.jobs;
+      j.out.status = info[k].status;
+      j.out.expanded = info[k].expanded;
+      m_inst[j.spec.inst].res.llExpanded += info[k].expanded;
+      if (j.out.status == 0) {
+        AgentPath ap;
+        ap.cost = info[k].cost;
+        ap.fmin = info[k].fmin;
+        ap.slot = j.outRow;
+        ap.length = info[k].length;
+        j.out.path = adopt(std::move(ap));
+      } else {
+        giveRow(j.outRow);
+      }
+      j.outRow = -1;
+      m_freeStates.push_back(j.state);
+      j.state = -1;
+    }
+    m_prof.llUnpack += nowSeconds() - tUn;
+  }
+  // flights whose replans are all done hand their children over (cbs.hpp:146-167)
+  void absorbFlights(std::vector<Node*>& fresh) {
+    const double tAbs = nowSeconds();
+    size_t keep = 0;
+    for (size_t i = 0; i < m_flights.size(); ++i) {
+      Flight& f = *m_flights[i];
+      bool all = true;
+      for (const FlightJob& j : f.jobs) all = all && j.done;
+      if (!all) {
+        if (keep != i) m_flights[keep] = std::move(m_flights[i]);
+        ++keep;
+        continue;
+      }
+      Inst& I = m_inst[f.pd.inst];
+      if (f.root) {
+        FlightJob& j = f.jobs[0];
+        if (j.out.status != 0) {  // cbs.hpp:96-100: a failing root search ends the search
+          finish(I, j.out.status == 2 ? kCapped : kNoSolution, nullptr, 0);
+          I.busy = false;
+          continue;
+        }
+        f.root->cost += j.out.path->cost;
+        f.root->LB += j.out.path->fmin;
+        f.root->paths[f.nextAgent] = std::move(j.out.path);
+        ++f.nextAgent;
+        if (nextRootJob(f)) {  // the next agent of this root
+          if (keep != i) m_flights[keep] = std::move(m_flights[i]);
+          ++keep;
+          continue;
+        }
+        fresh.push_back(f.root.release());
+        I.busy = false;
+        continue;
+      }
+      I.busy = false;
+      bool capped = false;
+      for (const FlightJob& j : f.jobs) capped = capped || j.out.status == 2;
+      if (capped) {  // a capped replan could hide the optimum: give up honestly
+        finish(I, kCapped, nullptr, 0);
+        continue;
+      }
+      for (size_t q = 0; q < f.kids.size(); ++q) {
+        FlightJob& j = f.jobs[q];
+        if (j.out.status != 0) continue;  // no path under these constraints: the child is dropped
+        Node& n = *f.kids[q].node;
+        n.cost += j.out.path->cost;
+        n.LB += j.out.path->fmin;
+        n.paths[f.kids[q].agent] = std::move(j.out.path);
+        n.id = I.nextId++;
+        fresh.push_back(f.kids[q].node.release());
+      }
+    }
+    m_flights.resize(keep);
+    m_prof.absorb += nowSeconds() - tAbs;
   }
 
   // ---- one expansion step for every pending parent -----------------------------
@@ -1074,6 +1368,11 @@ class BatchSolver {
   mrp_pathpool m_pool = nullptr;  // device rows of the paths (cbs / ecbs)
   std::vector<int32_t> m_freeRows;
   int m_nextRow = 0;
+  std::vector<std::unique_ptr<Flight> > m_flights;  // expansions whose replans are in progress
+  std::vector<int32_t> m_freeStates;
+  int m_nextState = 0;
+  int m_slice = 256;  // expansions per replan and launch (MRP_HOST_SLICE)
+  bool m_sliced = false;
   std::mutex m_rowMutex;
   const ConsPtr m_noCons = std::make_shared<const ConsList>();
   HostProfile m_prof;

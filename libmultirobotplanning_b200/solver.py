@@ -111,11 +111,13 @@ def solve_batch(algo, instances, w=1.0, max_hl=0, max_ll=8000, max_seconds=0.0,
              "lower_bound": int(lb[k]), "hl_expanded": int(hl[k]), "ll_expanded": int(ll[k]),
              "n_task_assignments": int(nta[k]), "runtime": float(rt[k])}
         if r["status"] == SOLVED:
-            paths = []
-            for a in range(aoff[k], aoff[k + 1]):
-                c = pcell[poff[a]:poff[a + 1]]
-                paths.append(np.stack([c % inst.dimx, c // inst.dimx, pg_[poff[a]:poff[a + 1]]], 1))
-            r["paths"] = paths
+            # one (x, y, g) array per instance, the agents' paths are views into it
+            a0, a1 = int(aoff[k]), int(aoff[k + 1])
+            lo, hi = int(poff[a0]), int(poff[a1])
+            c = pcell[lo:hi]
+            xyg = np.stack([c % inst.dimx, c // inst.dimx, pg_[lo:hi]], 1)
+            cut = poff[a0:a1 + 1] - lo
+            r["paths"] = [xyg[cut[i]:cut[i + 1]] for i in range(a1 - a0)]
         out.append(r)
     return out
 

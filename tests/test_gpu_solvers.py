@@ -448,11 +448,18 @@ def test_path_pool_gives_the_same_answers(capi, set8, set32, monkeypatch):
         monkeypatch.setenv("MRP_HOST_POOL", "0")
         ref = solver.solve_batch(algo, insts, **kw)
         monkeypatch.delenv("MRP_HOST_POOL")
-        got = solver.solve_batch(algo, insts, **kw)
         assert sum(r["status"] == 0 for r in ref) >= len(insts) // 3
-        for a, b in zip(got, ref):
-            for key in ("status", "cost", "makespan", "lower_bound", "hl_expanded", "ll_expanded"):
-                assert a[key] == b[key], key
-            assert len(a["paths"]) == len(b["paths"])
-            for pa, pb in zip(a["paths"], b["paths"]):
-                assert np.array_equal(np.asarray(pa), np.asarray(pb))
+        # default: replans cut into slices of 256 expansions per launch (instances move on
+        # as soon as their own replans are done); 0: every launch runs to its end; 5: a
+        # search is suspended to its state blob and resumed dozens of times
+        for slice_ in (None, "0", "5"):
+            if slice_ is not None:
+                monkeypatch.setenv("MRP_HOST_SLICE", slice_)
+            got = solver.solve_batch(algo, insts, **kw)
+            monkeypatch.delenv("MRP_HOST_SLICE", raising=False)
+            for a, b in zip(got, ref):
+                for key in ("status", "cost", "makespan", "lower_bound", "hl_expanded", "ll_expanded"):
+                    assert a[key] == b[key], (slice_, key)
+                assert len(a["paths"]) == len(b["paths"])
+                for pa, pb in zip(a["paths"], b["paths"]):
+                    assert np.array_equal(np.asarray(pa), np.asarray(pb))
