@@ -140,7 +140,7 @@ class BatchSolver {
       for (Node* n : I.open) delete n;
       I.solution.clear();
     }
-    if (m_pool) mrp_pathpool_destroy(m_pool);
+    if (m_pool) poolCache(m_pathCap, m_dimx, m_dimy, m_opt.maxLlExpanded, m_pool);
     if (m_fields) mrp_fieldset_destroy(m_fields);
     for (mrp_map m : m_maps) mrp_map_destroy(m);
   }
@@ -346,6 +346,36 @@ class BatchSolver {
     PathPtr path;  // set iff status == 0
   };
 
+  // Pools outlive their batch: creating one costs a dozen device allocations (tens of
+  // milliseconds), which a single small instance would pay on every call.  give != NULL
+  // stores a pool, give == NULL takes one of that shape (or returns NULL).  The rows and
+  // state blobs of a cached pool hold garbage; the next batch numbers them from 0 again.
+  static mrp_pathpool poolCache(int rowCap, int dimx, int dimy, int maxLl, mrp_pathpool give) {
+    struct Entry {
+      int rowCap, tb, maxLl;
+      mrp_pathpool pool;
+    };
+    static std::mutex mu;
+    static std::vector<Entry> cache;
+    const int tb = dimx * dimy <= 64 ? 0 : 1;  // layout class of the state blobs
+    std::lock_guard<std::mutex> lk(mu);
+    if (give) {
+      if (cache.size() >= 16) {
+        mrp_pathpool_destroy(give);
+      } else {
+        cache.push_back({rowCap, tb, maxLl, give});
+      }
+      return nullptr;
+    }
+    for (size_t i = 0; i < cache.size(); ++i)
+      if (cache[i].rowCap == rowCap && cache[i].tb == tb && cache[i].maxLl == maxLl) {
+        mrp_pathpool p = cache[i].pool;
+        cache.erase(cache.begin() + i);
+        return p;
+      }
+    return nullptr;
+  }
+
   // ---- device path pool (cbs / ecbs): rows are handed out and taken back here ----
   bool poolWanted() const {
     if (!(m_algo == Algo::CBS || m_algo == Algo::ECBS)) return false;
@@ -434,7 +464,15 @@ class BatchSolver {
         }
       }
     }
-    if (poolWanted()) gpuCheck(mrp_pathpool_create(m_pathCap, &m_pool));
+    if (poolWanted()) {
+      // device allocations are made here, outside the search timer (like the heuristic
+      // precompute below); a pool left by an earlier batch of the same shape is reused
+      m_pool = poolCache(m_pathCap, m_dimx, m_dimy, m_opt.maxLlExpanded, nullptr);
+      if (!m_pool) gpuCheck(mrp_pathpool_create(m_pathCap, &m_pool));
+      gpuCheck(mrp_pathpool_reserve(m_pool, 1));
+      if (m_dimx <= 32 && m_dimy <= 32)
+        gpuCheck(mrp_pathpool_reserve_states(m_pool, 1, m_dimx, m_dimy, m_opt.maxLlExpanded));
+    }
     // the heuristic precompute sits outside the reference's timer as well
     // (Environment ctor, example/cbs_ta.cpp:254-281,570-578)
     gpuCheck(mrp_fieldset_create(m_maps.data(), (int)m_maps.size(), goalMap.data(),
@@ -1148,17 +1186,21 @@ class BatchSolver {
     }
     m_prof.llUnpack += nowSeconds() - tUn;
   }
-  // flights whose replans are all done hand their children over (cbs.hpp:146-167)
+  // flights whose replans are all done hand their children over (cbs.hpp:146-167); the
+  // flights belong to different instances, so they are absorbed (and their parents
+  // released) on all host cores, the children join `fresh` in flight order
   void absorbFlights(std::vector<Node*>& fresh) {
     const double tAbs = nowSeconds();
-    size_t keep = 0;
-    for (size_t i = 0; i < m_flights.size(); ++i) {
+    const size_t nF = m_flights.size();
+    std::vector<std::array<Node*, 2> > made(nF, std::array<Node*, 2>{{nullptr, nullptr}});
+    std::vector<char> keepIt(nF, 0);
+#pragma omp parallel for schedule(dynamic, 16) if (nF >= kParallelMin)
+    for (long i = 0; i < (long)nF; ++i) {
       Flight& f = *m_flights[i];
       bool all = true;
       for (const FlightJob& j : f.jobs) all = all && j.done;
       if (!all) {
-        if (keep != i) m_flights[keep] = std::move(m_flights[i]);
-        ++keep;
+        keepIt[i] = 1;
         continue;
       }
       Inst& I = m_inst[f.pd.inst];
@@ -1167,6 +1209,7 @@ class BatchSolver {
         if (j.out.status != 0) {  // cbs.hpp:96-100: a failing root search ends the search
           finish(I, j.out.status == 2 ? kCapped : kNoSolution, nullptr, 0);
           I.busy = false;
+          m_flights[i].reset();
           continue;
         }
         f.root->cost += j.out.path->cost;
@@ -1174,12 +1217,12 @@ class BatchSolver {
         f.root->paths[f.nextAgent] = std::move(j.out.path);
         ++f.nextAgent;
         if (nextRootJob(f)) {  // the next agent of this root
-          if (keep != i) m_flights[keep] = std::move(m_flights[i]);
-          ++keep;
+          keepIt[i] = 1;
           continue;
         }
-        fresh.push_back(f.root.release());
+        made[i][0] = f.root.release();
         I.busy = false;
+        m_flights[i].reset();
         continue;
       }
       I.busy = false;
@@ -1187,9 +1230,10 @@ class BatchSolver {
       for (const FlightJob& j : f.jobs) capped = capped || j.out.status == 2;
       if (capped) {  // a capped replan could hide the optimum: give up honestly
         finish(I, kCapped, nullptr, 0);
+        m_flights[i].reset();
         continue;
       }
-      for (size_t q = 0; q < f.kids.size(); ++q) {
+      for (size_t q = 0; q < f.kids.size() && q < 2; ++q) {
         FlightJob& j = f.jobs[q];
         if (j.out.status != 0) continue;  // no path under these constraints: the child is dropped
         Node& n = *f.kids[q].node;
@@ -1197,7 +1241,17 @@ class BatchSolver {
         n.LB += j.out.path->fmin;
         n.paths[f.kids[q].agent] = std::move(j.out.path);
         n.id = I.nextId++;
-        fresh.push_back(f.kids[q].node.release());
+        made[i][q] = f.kids[q].node.release();
+      }
+      m_flights[i].reset();  // releases the parent
+    }
+    size_t keep = 0;
+    for (size_t i = 0; i < nF; ++i) {
+      for (Node* n : made[i])
+        if (n) fresh.push_back(n);
+      if (keepIt[i]) {
+        if (keep != i) m_flights[keep] = std::move(m_flights[i]);
+        ++keep;
       }
     }
     m_flights.resize(keep);
