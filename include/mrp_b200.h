@@ -180,7 +180,11 @@ int mrp_focal_counts(const int32_t* cell, const int32_t* len, int N, int Tpad,
                      int32_t* trans_cnt);
 /* Device-resident variant of first-conflict + count.  d_result is 4 x int64:
  * [0] packed first-conflict key (t<<41 | type<<40 | i<<20 | j), ~0 if none;
- * [1] conflict count; [2],[3] scratch.  The call resets d_result itself. */
+ * [1] conflict count; [2],[3] scratch.  The call resets d_result itself.
+ * The hashed kernels (256 < N <= 4096) keep their transposed table in a scratch
+ * buffer of the calling thread's lane: calls of one lane must use one stream (or
+ * be ordered by the caller); calls from different lanes are independent.
+ * len[i] <= Tpad is the caller's contract for device tables (not checked). */
 int mrp_conflicts_dev(const int32_t* d_cell, const int32_t* d_len, int N,
                       int Tpad, int mode, int want_first, int want_count,
                       unsigned long long* d_result, void* stream);

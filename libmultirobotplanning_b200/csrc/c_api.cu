@@ -1180,6 +1180,8 @@ int mrp_focal_counts(const int32_t* cell, const int32_t* len, int N, int Tpad, i
   if (n_cand == 0) return 0;
   MRP_CHECK(cand_t && cand_from && cand_to && state_cnt && trans_cnt, MRP_ERR_INVALID,
             "NULL pointer");
+  for (int k = 0; k < n_cand; ++k)
+    MRP_CHECK(cand_t[k] >= 0, MRP_ERR_INVALID, "candidate %d: negative time %d", k, cand_t[k]);
   if (N == 0 || Tpad == 0) {
     std::memset(state_cnt, 0, (size_t)n_cand * 4);
     std::memset(trans_cnt, 0, (size_t)n_cand * 4);
