@@ -279,7 +279,8 @@ def search_metrics(pkg, rank=0, world=1, dist=None, dev=None):
     from oracle import orc
     s8 = pkg.instances.load_set(os.path.join(g, "bench_8x8.npz"))
     out["ecbs_w1.3_instances_per_s"] = n_ok / dt_max
-    out["ecbs_config"] = "32x32_obst204, 100 agents, %d instances per GPU in one lock-step batch per rank " \
+    out["ecbs_config"] = "32x32_obst204, 100 agents, %d instances per GPU in one batch per rank (paths in a device pool, replans in " \
+                         "slices of 256 expansions, instances advance independently; 4 lanes) " \
                          "(rank 0: %d benchmark files + %d scaled by synthetic_c3; other ranks: the same maps, " \
                          "agents redrawn), cap %d high-level expansions, %d rank(s)" % (
                              len(insts), n_files, len(insts) - n_files, cap_hl, world)
@@ -296,6 +297,10 @@ def search_metrics(pkg, rank=0, world=1, dist=None, dev=None):
     out["ecbs_invalid_solutions"] = len(invalid)
     assert not invalid, "invalid ECBS solutions: %s" % invalid[:3]
     out["ecbs_unsolved"] = [i.name for i, r in zip(insts, res) if r["status"] != 0][:40]
+    # what the unmodified reference binary does on the instances this path gives up on (its search
+    # has no caps: 10 s of wall clock per instance, ten times what the whole batch takes here)
+    out["ecbs_unsolved_by_reference_binary"] = reference_on_unsolved(
+        "ecbs", [i for i, r in zip(insts, res) if r["status"] != 0][:32], ("-w", "1.3"), 10.0)
     n_cpu = 6
     t0 = time.perf_counter()
     cres = [orc.ecbs(i.dimx, i.dimy, i.obstacles, i.starts, i.goals, 1.3, (cap_hl, 0, 30.0))
@@ -458,6 +463,40 @@ def reference_binary_rate(tool, insts, extra, timeout=60.0):
                     total += float(yaml.safe_load(f)["statistics"]["runtime"])
                 solved += 1
     return solved / total if total > 0 else None
+
+
+def reference_on_unsolved(tool, insts, extra, wall):
+    """Runs oracle/_ref/<tool> on every instance of `insts` with `wall` seconds each, in parallel
+    on the host cores; returns how many it solves and their costs."""
+    import tempfile
+    import yaml
+    from concurrent.futures import ThreadPoolExecutor
+    from libmultirobotplanning_b200 import instances as I
+    exe = os.path.join(ROOT, "oracle", "_ref", tool)
+    if not os.path.exists(exe) or not insts:
+        return None
+
+    def one(args):
+        k, inst, d = args
+        inp, outp = os.path.join(d, "i%d.yaml" % k), os.path.join(d, "o%d.yaml" % k)
+        I.save_yaml(inst, inp)
+        try:
+            subprocess.run([exe, "-i", inp, "-o", outp, *extra], stdout=subprocess.DEVNULL,
+                           stderr=subprocess.DEVNULL, timeout=wall, check=True)
+        except Exception:
+            return None
+        if not os.path.exists(outp):
+            return None
+        with open(outp) as f:
+            st = yaml.safe_load(f)["statistics"]
+        return [int(st["cost"]), float(st["runtime"])]
+
+    with tempfile.TemporaryDirectory() as d:
+        with ThreadPoolExecutor(max_workers=max(1, min(16, (os.cpu_count() or 2) - 1))) as ex:
+            got = list(ex.map(one, [(k, inst, d) for k, inst in enumerate(insts)]))
+    return {"instances": len(insts), "wall_cap_s_each": wall,
+            "solved_by_reference": sum(g is not None for g in got),
+            "cost_and_runtime": {i.name: g for i, g in zip(insts, got) if g is not None}}
 
 
 def run_ours(args):

@@ -332,3 +332,52 @@ def test_path_pool_rows_and_conflicts(capi, orc):
     with pytest.raises(capi.MrpError):
         pool.read(np.array([10 ** 6], np.int32))
     pool.close()
+
+
+def test_hashed_sweep_with_parked_agents(capi, orc, monkeypatch):
+    """Paths of very different lengths on a small map: agents that walk over, wait on and
+    park on parked agents, several paths ending on one cell, paths of one state and agents
+    without a path, a pile-up that overflows the sieve's exact table.  The hashed sweep
+    (256 < N <= 4096) must equal the all-pairs kernel and the oracle, both loop bounds,
+    first conflict and counts.  (Written for a sweep over the moving agents only — sorted by
+    path length, parked agents in a static table — which passed it but was slower than the
+    full sieve on the C5 table, 0.111 against 0.054 ms: profiles/README.md.)"""
+    rng = np.random.default_rng(123)
+    for N, T, cells, dimx in ((300, 90, 400, 20), (700, 60, 900, 30), (3000, 48, 4096, 64)):
+        dimy = cells // dimx
+        cell = np.zeros((N, T), np.int32)
+        ln = rng.integers(1, T + 1, N).astype(np.int32)
+        ln[rng.integers(0, N, N // 10)] = 1      # parked from the start
+        ln[rng.integers(0, N, N // 20)] = T      # move until the end
+        ln[5] = 0
+        ln[6] = 0
+        for i in range(N):                       # random walks (with waits) on a small map: real conflicts
+            c = int(rng.integers(0, cells))
+            for t in range(T):
+                cell[i, t] = c
+                x, y = c % dimx, c // dimx
+                dx, dy = [(0, 0), (0, 0), (1, 0), (-1, 0), (0, 1), (0, -1)][int(rng.integers(0, 6))]
+                x, y = min(max(x + dx, 0), dimx - 1), min(max(y + dy, 0), dimy - 1)
+                c = x + dimx * y
+        # several paths ending on one cell at different times, one of them waiting there
+        goal = int(cell[20, ln[20] - 1])
+        for k, i in enumerate((21, 22, 23)):
+            ln[i] = max(2, min(T, ln[20] + 3 * k - 2))
+            cell[i, ln[i] - 1] = goal
+            cell[i, ln[i] - 2] = goal if k == 1 else cell[i, ln[i] - 2]
+        if N >= 3000:
+            cell[1000:2400, 7] = rng.integers(0, 40, 1400)   # a pile-up among moving agents
+            ln[1000:2400] = np.maximum(ln[1000:2400], 12)
+        for mode in (0, 1):
+            got = (capi.first_conflict(cell, ln, dimx, mode), capi.count_conflicts(cell, ln, mode))
+            monkeypatch.setenv("MRP_CONFLICTS_HASH2", "1")
+            full = (capi.first_conflict(cell, ln, dimx, mode), capi.count_conflicts(cell, ln, mode))
+            monkeypatch.delenv("MRP_CONFLICTS_HASH2")
+            monkeypatch.setenv("MRP_CONFLICTS_ALLPAIRS", "1")
+            pairs = (capi.first_conflict(cell, ln, dimx, mode), capi.count_conflicts(cell, ln, mode))
+            monkeypatch.delenv("MRP_CONFLICTS_ALLPAIRS")
+            assert full == pairs, (N, mode)
+            assert got == pairs, (N, mode, got, pairs)
+            if N <= 700:
+                assert got == (orc.first_conflict(cell, ln, dimx, mode), orc.count_conflicts(cell, ln, mode))
+            assert got[1] > 50

@@ -27,7 +27,9 @@ starts = (inst.starts[:, 0] + DIM * inst.starts[:, 1]).astype(np.int64)
 table, length = bench.descend_paths(torch, d_out, inst, starts, N, 4096)
 d_res = torch.zeros(4, dtype=torch.int64, device="cuda")
 lib = capi.lib()
-for r in range(3):
+print("sum of (len - 1) = %d moving agent-steps of %d x %d" % (int((length.clamp(min=1) - 1).sum().item()), N,
+                                                               int(length.max().item()) - 1))
+for r in range(5):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     capi.check(lib.mrp_conflicts_dev(table.data_ptr(), length.data_ptr(), N, table.shape[1], 0, 1, 1,
@@ -36,3 +38,13 @@ for r in range(3):
     torch.cuda.synchronize()
     print("sweep %d: %.3f ms, count %d, max_t %d" % (r, e0.elapsed_time(e1), int(d_res[1].item()),
                                                     int(length.max().item()) - 1))
+first = []
+for r in range(5):
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    capi.check(lib.mrp_conflicts_dev(table.data_ptr(), length.data_ptr(), N, table.shape[1], 0, 1, 0,
+                                     d_res.data_ptr(), s.cuda_stream))
+    e1.record()
+    torch.cuda.synchronize()
+    first.append(e0.elapsed_time(e1))
+print("first conflict only: %s ms, key %d" % (" ".join("%.3f" % x for x in first), int(d_res[0].item())))
