@@ -3,6 +3,7 @@
 // copies around the kernels of bfs_small.cu / bfs_large.cu / conflicts.cu /
 // lowlevel.cu).  No CPU fallback anywhere: without a device every call fails.
 #include <algorithm>
+#include <chrono>
 #include <condition_variable>
 #include <cstdlib>
 #include <cstring>
@@ -105,6 +106,23 @@ cudaError_t waitStream(cudaStream_t st) {
   if (!c.doneEvent) return cudaStreamSynchronize(st);
   cudaError_t e = cudaEventRecord(c.doneEvent, st);
   if (e != cudaSuccess) return e;
+  // MRP_WAIT_SPIN_US=n polls for n microseconds before sleeping on the blocking-sync event
+  // (a blocking wait costs a wake-up of 50-100 us).  Off by default: with the lanes' OpenMP
+  // teams on the same cores polling made the batch times erratic (ECBS batch 0.91 s without,
+  // 0.81-2.35 s with 300-1000 us; CBS 8x8 set 0.97 / 0.85 / 2.01 s at 0 / 300 / 1000 us).
+  static const int spinUs = [] {
+    const char* v = getenv("MRP_WAIT_SPIN_US");
+    return v ? atoi(v) : 0;
+  }();
+  if (spinUs > 0) {
+    const auto t0 = std::chrono::steady_clock::now();
+    while (true) {
+      e = cudaEventQuery(c.doneEvent);
+      if (e != cudaErrorNotReady) return e;
+      if (std::chrono::duration_cast<std::chrono::microseconds>(std::chrono::steady_clock::now() - t0).count() >= spinUs)
+        break;
+    }
+  }
   return cudaEventSynchronize(c.doneEvent);
 }
 #define g_scratch (lane().scratch)
