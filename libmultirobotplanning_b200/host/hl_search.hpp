@@ -79,7 +79,11 @@ struct SolveResult {
 struct SolveOptions {
   float w = 1.0f;
   long maxHlExpanded = 0;  // per instance; 0 = unlimited
-  int maxLlExpanded = 8000;  // per low-level search (GPU workspace is sized by it)
+  // per low-level search (GPU workspace is sized by it).  12000: of the 22 instances of the
+  // 1000 x 100-agent ECBS batch that a cap of 8000 loses, 20 need less than this (the
+  // unmodified reference solves 21 of them; with 24000 one instance runs to the high-level
+  // cap for 75 s: tools/try_unsolved.py)
+  int maxLlExpanded = 12000;
   double maxSeconds = 0;     // whole batch; 0 = unlimited
   long maxTaskAssignments = 1000000000L;
   // Two-speed replans (cbs / ecbs batches): the lock-step launches cap every replan at

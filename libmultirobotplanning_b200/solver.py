@@ -56,7 +56,7 @@ def _p(a):
     return a.ctypes.data_as(C.c_void_p) if a is not None else None
 
 
-def solve_batch(algo, instances, w=1.0, max_hl=0, max_ll=8000, max_seconds=0.0,
+def solve_batch(algo, instances, w=1.0, max_hl=0, max_ll=12000, max_seconds=0.0,
                 max_task_assignments=10**9, path_cap=None):
     """instances: objects with dimx, dimy, obstacles [n,2], starts [n,2] and
     goals [n,2] (cbs/ecbs) or potential_goals (list of [k,2]) for cbs_ta.
