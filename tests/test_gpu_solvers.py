@@ -463,3 +463,28 @@ def test_path_pool_gives_the_same_answers(capi, set8, set32, monkeypatch):
                 assert len(a["paths"]) == len(b["paths"])
                 for pa, pb in zip(a["paths"], b["paths"]):
                     assert np.array_equal(np.asarray(pa), np.asarray(pb))
+
+
+def test_sliced_searches_with_spill_on_100_agent_instances(capi, set32, monkeypatch):
+    """100-agent ECBS instances have replans of thousands of expansions: OPEN and the node pool
+    outgrow their shared-memory parts (768 entries / 1024 nodes) and live on in the state blob,
+    and a search is suspended and resumed dozens of times at a slice of 64.  Same answers as
+    with replans that run to their end and as with the round-1 driver (whole path tables per
+    launch, general kernel excluded by nothing: it takes what the tile kernel hands back)."""
+    from libmultirobotplanning_b200 import solver
+    insts = [i for i in set32 if i.n_agents == 100][:6]
+    kw = dict(w=1.3, max_hl=400)
+    monkeypatch.setenv("MRP_HOST_POOL", "0")
+    ref = solver.solve_batch(solver.ECBS, insts, **kw)
+    monkeypatch.delenv("MRP_HOST_POOL")
+    assert sum(r["status"] == 0 for r in ref) >= 4
+    assert max(r["ll_expanded"] for r in ref) > 20000
+    for slice_ in ("64", "0", "1000"):
+        monkeypatch.setenv("MRP_HOST_SLICE", slice_)
+        got = solver.solve_batch(solver.ECBS, insts, **kw)
+        monkeypatch.delenv("MRP_HOST_SLICE")
+        for a, b in zip(got, ref):
+            for key in ("status", "cost", "makespan", "lower_bound", "hl_expanded", "ll_expanded"):
+                assert a[key] == b[key], (slice_, key)
+            for pa, pb in zip(a["paths"], b["paths"]):
+                assert np.array_equal(np.asarray(pa), np.asarray(pb))
