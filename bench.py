@@ -218,6 +218,10 @@ def descend_paths(torch, fields, inst, starts_cell, n_agents, max_t):
 
 
 ECBS_BATCH = 1000  # replans of a lock-step iteration share one launch: throughput grows with the batch
+# low-level expansions an instance may use in total before it is given up as capped: the solved
+# instances of the batch need up to 2.4*10^5; without it one instance in a few thousand runs to the
+# high-level cap with 6*10^7 expansions (27 s) and every rank waits for it
+LL_TOTAL = 500000
 
 
 def c3_shard(pkg, s32, rank):
@@ -262,7 +266,8 @@ def search_metrics(pkg, rank=0, world=1, dist=None, dev=None):
     runs = []
     for _ in range(2):
         t0 = time.perf_counter()
-        res = pkg.solver.solve_batch(pkg.solver.ECBS, insts, w=1.3, max_hl=cap_hl, max_seconds=120)
+        res = pkg.solver.solve_batch(pkg.solver.ECBS, insts, w=1.3, max_hl=cap_hl, max_seconds=120,
+                                     max_ll_total=LL_TOTAL)
         runs.append(time.perf_counter() - t0)
     dt = min(runs)
     ok = [r for r in res if r["status"] == 0]
@@ -282,8 +287,9 @@ def search_metrics(pkg, rank=0, world=1, dist=None, dev=None):
     out["ecbs_config"] = "32x32_obst204, 100 agents, %d instances per GPU in one batch per rank (paths in a device pool, replans in " \
                          "slices of 256 expansions, instances advance independently; 4 lanes) " \
                          "(rank 0: %d benchmark files + %d scaled by synthetic_c3; other ranks: the same maps, " \
-                         "agents redrawn), cap %d high-level expansions, %d rank(s)" % (
-                             len(insts), n_files, len(insts) - n_files, cap_hl, world)
+                         "agents redrawn), caps: %d high-level expansions, 12000 expansions per replan, %d low-level " \
+                         "expansions per instance; %d rank(s)" % (
+                             len(insts), n_files, len(insts) - n_files, cap_hl, LL_TOTAL, world)
     out["ecbs_solved"] = "%d/%d" % (n_ok, n_all)
     out["ecbs_seconds"] = dt_max
     out["ecbs_seconds_runs_rank0"] = runs
@@ -324,7 +330,8 @@ def search_metrics(pkg, rank=0, world=1, dist=None, dev=None):
         bruns = []
         for _ in range(2):
             t0 = time.perf_counter()
-            bres = pkg.solver.solve_batch(pkg.solver.ECBS, big, w=1.3, max_hl=cap_hl, max_seconds=120)
+            bres = pkg.solver.solve_batch(pkg.solver.ECBS, big, w=1.3, max_hl=cap_hl, max_seconds=120,
+                                          max_ll_total=LL_TOTAL)
             bruns.append(time.perf_counter() - t0)
         bok = sum(r["status"] == 0 for r in bres)
         assert [(r["status"], r["cost"]) for r in bres[:len(insts)]] == [(r["status"], r["cost"]) for r in res]

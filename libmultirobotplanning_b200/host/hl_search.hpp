@@ -84,6 +84,12 @@ struct SolveOptions {
   // unmodified reference solves 21 of them; with 24000 one instance runs to the high-level
   // cap for 75 s: tools/try_unsolved.py)
   int maxLlExpanded = 12000;
+  // low-level expansions of ONE instance in total (0 = unlimited): an instance whose replans
+  // have used more than this is given up as capped.  The reference has no such limit (and does
+  // not return on those instances either); in a batch one runaway instance would otherwise keep
+  // every GPU lane waiting: with a replan cap of 12000 one of 4000 ECBS instances ran to the
+  // high-level cap with 6*10^7 expansions (27 s) where the whole batch takes 1 s.
+  long maxLlTotal = 0;
   double maxSeconds = 0;     // whole batch; 0 = unlimited
   long maxTaskAssignments = 1000000000L;
   // Two-speed replans (cbs / ecbs batches): the lock-step launches cap every replan at
@@ -200,7 +206,8 @@ class BatchSolver {
           finish(I, kNoSolution, nullptr, tNow);
           continue;
         }
-        if (timeUp || (m_opt.maxHlExpanded > 0 && I.res.hlExpanded >= m_opt.maxHlExpanded)) {
+        if (timeUp || (m_opt.maxHlExpanded > 0 && I.res.hlExpanded >= m_opt.maxHlExpanded) ||
+            (m_opt.maxLlTotal > 0 && I.res.llExpanded >= m_opt.maxLlTotal)) {
           finish(I, kCapped, nullptr, tNow);
           continue;
         }

@@ -3,6 +3,7 @@
 #include <algorithm>
 #include <cstdint>
 #include <cstdlib>
+#include <atomic>
 #include <map>
 #include <string>
 #include <thread>
@@ -28,6 +29,10 @@ const char* mrph_last_error(void) { return g_err.c_str(); }
 // dims[n][2]; obst_off[n+1] into obst_xy[][2]; agent_off[n+1] into
 // start_cell[] / goal_cell[]; cbs_ta: pg_off[total_agents+1] into pg_cell[].
 // Outputs per instance; paths: path_off[total_agents+1] into path_cell/path_g.
+// per-instance budget of low-level expansions for the batches that follow (SolveOptions::maxLlTotal)
+static std::atomic<long long> g_llTotal{0};
+void mrph_set_ll_total(int64_t n) { g_llTotal.store(n); }
+
 int mrph_solve_batch(int algo, int n_inst, const int32_t* dims, const int32_t* obst_off,
                      const int32_t* obst_xy, const int32_t* agent_off,
                      const int32_t* start_cell, const int32_t* goal_cell,
@@ -55,6 +60,7 @@ int mrph_solve_batch(int algo, int n_inst, const int32_t* dims, const int32_t* o
     opt.w = w;
     opt.maxHlExpanded = max_hl;
     opt.maxLlExpanded = max_ll;
+    opt.maxLlTotal = (long)g_llTotal.load();
     opt.maxSeconds = max_seconds;
     opt.maxTaskAssignments = max_ta;
     // One lock-step batch per map size, cut into sub-batches that run in their

@@ -57,7 +57,7 @@ def _p(a):
 
 
 def solve_batch(algo, instances, w=1.0, max_hl=0, max_ll=12000, max_seconds=0.0,
-                max_task_assignments=10**9, path_cap=None):
+                max_task_assignments=10**9, path_cap=None, max_ll_total=0):
     """instances: objects with dimx, dimy, obstacles [n,2], starts [n,2] and
     goals [n,2] (cbs/ecbs) or potential_goals (list of [k,2]) for cbs_ta.
     Returns a list of dicts (status, cost, makespan, lower_bound, hl_expanded,
@@ -97,6 +97,7 @@ def solve_batch(algo, instances, w=1.0, max_hl=0, max_ll=12000, max_seconds=0.0,
     poff = np.zeros(total + 1, np.int32)
     pcell = np.zeros(path_cap, np.int32)
     pg_ = np.zeros(path_cap, np.int32)
+    lib().mrph_set_ll_total(C.c_int64(max_ll_total))
     rc = lib().mrph_solve_batch(algo, n, _p(dims), _p(ooff), _p(obst), _p(aoff), _p(starts),
                                 _p(goals), _p(pg_off), _p(pg_cell), C.c_float(w),
                                 C.c_int64(max_hl), C.c_int32(max_ll), C.c_double(max_seconds),

@@ -488,3 +488,18 @@ def test_sliced_searches_with_spill_on_100_agent_instances(capi, set32, monkeypa
                 assert a[key] == b[key], (slice_, key)
             for pa, pb in zip(a["paths"], b["paths"]):
                 assert np.array_equal(np.asarray(pa), np.asarray(pb))
+
+
+def test_total_expansion_budget_caps_an_instance(capi, set32):
+    """max_ll_total: an instance whose replans have used more low-level expansions than the
+    budget is given up as capped (status 2) at its next high-level expansion; a generous budget
+    changes nothing."""
+    from libmultirobotplanning_b200 import solver
+    insts = [i for i in set32 if i.n_agents == 50][:4]
+    ref = solver.solve_batch(solver.ECBS, insts, w=1.3, max_hl=500)
+    assert all(r["status"] == 0 and r["hl_expanded"] > 1 for r in ref)
+    tight = solver.solve_batch(solver.ECBS, insts, w=1.3, max_hl=500, max_ll_total=100)
+    assert all(r["status"] == 2 for r in tight)
+    wide = solver.solve_batch(solver.ECBS, insts, w=1.3, max_hl=500, max_ll_total=10 ** 8)
+    assert [(r["status"], r["cost"], r["ll_expanded"]) for r in wide] == \
+        [(r["status"], r["cost"], r["ll_expanded"]) for r in ref]
