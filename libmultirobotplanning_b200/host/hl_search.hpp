@@ -371,11 +371,14 @@ class BatchSolver {
     const int tb = dimx * dimy <= 64 ? 0 : 1;  // layout class of the state blobs
     std::lock_guard<std::mutex> lk(mu);
     if (give) {
-      if (cache.size() >= 16) {
-        mrp_pathpool_destroy(give);
-      } else {
-        cache.push_back({rowCap, tb, maxLl, give});
+      // keep the most recently used ones: a process that alternates between batch shapes
+      // (bench.py: 4 lanes of 100-agent ECBS, then 16 lanes of 8x8 CBS) would otherwise
+      // create and destroy sixteen pools per call (a dozen device allocations each)
+      if (cache.size() >= 40) {
+        mrp_pathpool_destroy(cache.front().pool);
+        cache.erase(cache.begin());
       }
+      cache.push_back({rowCap, tb, maxLl, give});
       return nullptr;
     }
     for (size_t i = 0; i < cache.size(); ++i)
