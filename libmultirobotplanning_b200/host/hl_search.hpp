@@ -26,9 +26,7 @@
 #include <algorithm>
 #include <array>
 #include <chrono>
-#include <condition_variable>
 #include <mutex>
-#include <thread>
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
@@ -92,14 +90,6 @@ struct SolveOptions {
   long maxLlTotal = 0;
   double maxSeconds = 0;     // whole batch; 0 = unlimited
   long maxTaskAssignments = 1000000000L;
-  // Two-speed replans (cbs / ecbs batches): the lock-step launches cap every replan at
-  // fastLlExpanded expansions; an instance with a replan that needs more is SUSPENDED and
-  // its expansion is redone with the full cap by a background thread in lane slowLane,
-  // while the other instances go on — a lock-step iteration no longer lasts as long as the
-  // slowest replan of the whole batch.  Results do not change (instances are independent
-  // and their searches deterministic).  0 / -1: off.
-  int fastLlExpanded = 0;
-  int slowLane = -1;
 };
 
 enum class Algo { CBS = 0, ECBS = 1, CBSTA = 2, ECBSTA = 3 };
@@ -108,7 +98,7 @@ enum class Algo { CBS = 0, ECBS = 1, CBSTA = 2, ECBSTA = 3 };
 struct HostProfile {
   double gpuConflicts = 0, gpuLowLevel = 0, total = 0, setup = 0;
   double pop = 0, build = 0, llPack = 0, llUnpack = 0, evalPack = 0, absorb = 0;
-  long iterations = 0, nodes = 0, jobs = 0, deferred = 0, launches = 0;
+  long iterations = 0, nodes = 0, jobs = 0, launches = 0;
 };
 inline double nowSeconds() {
   return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch())
@@ -136,16 +126,7 @@ class BatchSolver {
     }
   }
   ~BatchSolver() {
-    if (m_slowThread.joinable()) {
-      {
-        std::lock_guard<std::mutex> lk(m_slowMutex);
-        m_slowStop = true;
-      }
-      m_slowCv.notify_all();
-      m_slowThread.join();
-    }
     m_flights.clear();
-    for (Node* n : m_slowOut) delete n;
     for (Inst& I : m_inst) {
       for (Node* n : I.open) delete n;
       I.solution.clear();
@@ -176,15 +157,9 @@ class BatchSolver {
     if (const char* e = getenv("MRP_HOST_SLICE")) m_slice = atoi(e);
     m_sliced = m_pool && m_slice > 0 && m_dimx <= 32 && m_dimy <= 32;
     buildRoots(fresh);
-    // (the path pool belongs to one lane: pool mode keeps to the lock-step launches)
-    const bool twoSpeed = m_opt.fastLlExpanded > 0 && m_opt.fastLlExpanded < m_opt.maxLlExpanded &&
-                          m_opt.slowLane >= 0 && (m_algo == Algo::CBS || m_algo == Algo::ECBS) && !m_pool;
-    if (twoSpeed) m_slowThread = std::thread([this] { slowWorker(); });
-    size_t nSuspended = 0;
     const bool sliced = m_sliced;
     while (true) {
       ++m_prof.iterations;
-      if (twoSpeed) nSuspended -= collectSlow(fresh, false);
       evaluate(fresh);
       insertFresh(fresh);
       fresh.clear();
@@ -201,7 +176,7 @@ class BatchSolver {
 #pragma omp parallel for schedule(dynamic, 16) if (m_inst.size() >= kParallelMin)
       for (long k = 0; k < (long)m_inst.size(); ++k) {
         Inst& I = m_inst[k];
-        if (I.done || I.suspended || I.busy) continue;
+        if (I.done || I.busy) continue;
         if (I.open.empty()) {
           finish(I, kNoSolution, nullptr, tNow);
           continue;
@@ -243,46 +218,22 @@ class BatchSolver {
         absorbFlights(fresh);
         continue;
       }
-      if (!anyRunning) {
-        if (nSuspended == 0) break;
-        nSuspended -= collectSlow(fresh, true);  // nothing to do but wait for the slow lane
-        continue;
-      }
-      std::vector<Pending> deferred;
-      expand(pending, fresh, twoSpeed ? m_opt.fastLlExpanded : m_opt.maxLlExpanded,
-             twoSpeed ? &deferred : nullptr, m_mainBuf, m_prof);
+      if (!anyRunning) break;
+      expand(pending, fresh, m_opt.maxLlExpanded, m_mainBuf, m_prof);
       // the expanded parents are released on all cores as well
 #pragma omp parallel for schedule(dynamic, 16) if (pending.size() >= kParallelMin)
       for (long pi = 0; pi < (long)pending.size(); ++pi) pending[pi].parent.reset();
-      if (!deferred.empty()) {
-        nSuspended += deferred.size();
-        m_prof.deferred += (long)deferred.size();
-        {
-          std::lock_guard<std::mutex> lk(m_slowMutex);
-          for (Pending& d : deferred) m_slowIn.push_back(std::move(d));
-        }
-        m_slowCv.notify_all();
-      }
-    }
-    if (twoSpeed) {
-      {
-        std::lock_guard<std::mutex> lk(m_slowMutex);
-        m_slowStop = true;
-      }
-      m_slowCv.notify_all();
-      m_slowThread.join();
-      if (!m_slowError.empty()) throw std::runtime_error(m_slowError);
     }
     fetchSolutions();
     for (size_t k = 0; k < m_inst.size(); ++k) out[k] = std::move(m_inst[k].res);
     m_prof.total = nowSeconds() - tRun;
     if (getenv("MRP_HOST_PROFILE"))
       fprintf(stderr,
-              "[mrp_host] %zu instances, %ld lock-step iterations, %ld nodes, %ld replans, %ld expansions redone in the slow lane: "
+              "[mrp_host] %zu instances, %ld lock-step iterations, %ld nodes, %ld replans in %ld sliced launches: "
               "total %.3fs = conflicts(gpu call) %.3fs + replans(gpu call) %.3fs + host %.3fs "
               "[pop %.2f build %.2f llPack %.2f llUnpack %.2f evalPack %.2f absorb %.2f]; "
               "setup (maps + distance fields, outside the reference's timer too) %.3fs\n",
-              m_inst.size(), m_prof.iterations, m_prof.nodes, m_prof.jobs, m_prof.deferred, m_prof.total,
+              m_inst.size(), m_prof.iterations, m_prof.nodes, m_prof.jobs, m_prof.launches, m_prof.total,
               m_prof.gpuConflicts, m_prof.gpuLowLevel,
               m_prof.total - m_prof.gpuConflicts - m_prof.gpuLowLevel, m_prof.pop, m_prof.build,
               m_prof.llPack, m_prof.llUnpack, m_prof.evalPack, m_prof.absorb, m_prof.setup);
@@ -333,7 +284,6 @@ class BatchSolver {
     int nextId = 0;
     bool done = false;
     bool busy = false;       // sliced replans of its current expansion are still running
-    bool suspended = false;  // its expansion is being redone in the slow lane
     int mapIdx = 0;
     int fieldBase = 0;                 // first field of this instance in the set
     std::map<int, int> fieldOfGoal;    // goal cell -> field index (cbs_ta)
@@ -721,50 +671,6 @@ class BatchSolver {
       }
     }
     prof.llUnpack += nowSeconds() - tUn;
-  }
-
-  // ---- the slow lane of the two-speed replans ---------------------------------
-  void slowWorker() {
-    try {
-      gpuCheck(mrp_set_lane(m_opt.slowLane));
-      LLBuffers buf;
-      HostProfile prof;
-      while (true) {
-        std::vector<Pending> items;
-        {
-          std::unique_lock<std::mutex> lk(m_slowMutex);
-          m_slowCv.wait(lk, [this] { return !m_slowIn.empty() || m_slowStop; });
-          if (m_slowIn.empty()) return;
-          items.swap(m_slowIn);
-        }
-        std::vector<Node*> fresh;
-        expand(items, fresh, m_opt.maxLlExpanded, nullptr, buf, prof);
-        {
-          std::lock_guard<std::mutex> lk(m_slowMutex);
-          for (Node* n : fresh) m_slowOut.push_back(n);
-          for (Pending& p : items) m_slowDone.push_back(p.inst);
-        }
-        m_slowCv.notify_all();
-      }
-    } catch (const std::exception& e) {
-      std::lock_guard<std::mutex> lk(m_slowMutex);
-      m_slowError = e.what();
-      if (m_slowError.empty()) m_slowError = "slow lane failed";
-      m_slowCv.notify_all();
-    }
-  }
-  // takes what the slow lane finished: its children join `fresh`, its instances run again;
-  // returns the number of instances that came back (wait: block until at least one did)
-  size_t collectSlow(std::vector<Node*>& fresh, bool wait) {
-    std::unique_lock<std::mutex> lk(m_slowMutex);
-    if (wait) m_slowCv.wait(lk, [this] { return !m_slowDone.empty() || !m_slowError.empty(); });
-    if (!m_slowError.empty()) throw std::runtime_error(m_slowError);
-    for (Node* n : m_slowOut) fresh.push_back(n);
-    m_slowOut.clear();
-    const size_t n = m_slowDone.size();
-    for (int k : m_slowDone) m_inst[k].suspended = false;
-    m_slowDone.clear();
-    return n;
   }
 
   // pool mode: the tables of `nodes` as pool rows [B][N] (-1: no path yet) and the
@@ -1273,10 +1179,9 @@ class BatchSolver {
   }
 
   // ---- one expansion step for every pending parent -----------------------------
-  // maxExpanded: cap of the replans of this call; deferred != nullptr: an instance one of whose
-  // replans hit that cap makes no children here — it is suspended and handed back in *deferred
+  // maxExpanded: cap of the replans of this call
   void expand(std::vector<Pending>& pending, std::vector<Node*>& fresh, int maxExpanded,
-              std::vector<Pending>* deferred, LLBuffers& buf, HostProfile& prof) {
+              LLBuffers& buf, HostProfile& prof) {
     struct ChildPlan {
       int pendingIdx;
       int agent;        // replanned agent; -1: a whole new root (cbs_ta)
@@ -1369,23 +1274,9 @@ class BatchSolver {
     runLowLevel(specs, tabs, outs, maxExpanded, buf, prof);
     const double tAbs = nowSeconds();
     std::vector<Node*> made(plans.size(), nullptr);
-    std::vector<char> defer(pending.size(), 0);
 #pragma omp parallel for schedule(dynamic, 16) if (pending.size() >= kParallelMin)
     for (long pi = 0; pi < (long)pending.size(); ++pi) {
       Inst& I = m_inst[pending[pi].inst];
-      if (deferred) {
-        // a replan that needs more than the fast cap: the whole expansion is redone in the slow lane
-        for (size_t q = firstPlan[pi]; q < firstPlan[pi + 1] && !defer[pi]; ++q)
-          for (size_t j = plans[q].firstJob; j < plans[q].firstJob + plans[q].nJobs; ++j)
-            if (outs[j].status == 2) defer[pi] = 1;
-        if (defer[pi]) {
-          for (size_t q = firstPlan[pi]; q < firstPlan[pi + 1]; ++q)
-            for (size_t j = plans[q].firstJob; j < plans[q].firstJob + plans[q].nJobs; ++j)
-              I.res.llExpanded -= outs[j].expanded;  // counted again by the slow lane
-          I.suspended = true;
-          continue;
-        }
-      }
       for (size_t q = firstPlan[pi]; q < firstPlan[pi + 1]; ++q) {
         ChildPlan& cp = plans[q];
         if (I.done) continue;
@@ -1412,9 +1303,6 @@ class BatchSolver {
     }
     for (Node* n : made)
       if (n) fresh.push_back(n);
-    if (deferred)
-      for (size_t pi = 0; pi < pending.size(); ++pi)
-        if (defer[pi]) deferred->push_back(std::move(pending[pi]));
     prof.absorb += nowSeconds() - tAbs;
     // children of instances that were finished meanwhile must not leak
     size_t keep = 0;
@@ -1447,15 +1335,6 @@ class BatchSolver {
   // staging buffers reused across lock-step iterations
   mutable std::vector<int32_t> m_evTables, m_evTlen;
   LLBuffers m_mainBuf;
-  // slow lane of the two-speed replans
-  std::thread m_slowThread;
-  std::mutex m_slowMutex;
-  std::condition_variable m_slowCv;
-  std::vector<Pending> m_slowIn;
-  std::vector<Node*> m_slowOut;
-  std::vector<int> m_slowDone;
-  std::string m_slowError;
-  bool m_slowStop = false;
 };
 
 }  // namespace mrp_host

@@ -96,20 +96,9 @@ int mrph_solve_batch(int algo, int n_inst, const int32_t* dims, const int32_t* o
 #ifdef _OPENMP
     const int ompBudget = omp_get_max_threads();  // OMP_NUM_THREADS: ranks that share a host divide the cores
 #endif
-    // two-speed replans (hl_search.hpp): lock-step launches capped at MRP_HOST_FAST_CAP expansions
-    // per replan, stragglers redone with the full cap in the second half of the lanes.  Off by
-    // default: identical results, but 40 % of the expansions of the 100-agent ECBS batch hold a
-    // replan of more than 384 expansions, so the slow lane becomes the new lock-step (measured
-    // 174 -> 198 instances/s at 4 lanes, within the box-to-box spread; profiles/README.md).
-    int fastCap = 0;
-    if (const char* e = getenv("MRP_HOST_FAST_CAP")) fastCap = (algo == 0 || algo == 1) ? atoi(e) : 0;
     auto work = [&](int t) {
       try {
         SolveOptions myOpt = opt;
-        if (fastCap > 0 && mrp_max_lanes() >= 64) {
-          myOpt.fastLlExpanded = fastCap;
-          myOpt.slowLane = 32 + t;
-        }
         if (nThreads > 1) {
           mrp_set_lane(t);
 #ifdef _OPENMP
