@@ -217,7 +217,7 @@ def descend_paths(torch, fields, inst, starts_cell, n_agents, max_t):
     return table.contiguous(), length.contiguous()
 
 
-ECBS_BATCH = 1000  # replans of a lock-step iteration share one launch: throughput grows with the batch
+ECBS_BATCH = 1000  # instances of one call
 # low-level expansions an instance may use in total before it is given up as capped: the solved
 # instances of the batch need up to 2.4*10^5; without it one instance in a few thousand runs to the
 # high-level cap with 6*10^7 expansions (27 s) and every rank waits for it
@@ -248,7 +248,8 @@ def c3_shard(pkg, s32, rank):
 def search_metrics(pkg, rank=0, world=1, dist=None, dev=None):
     """Instance throughput of the batched searches next to the oracle on one
     host core (same caps).  ECBS (config C3): 1000 instances per GPU on the
-    32x32_obst204 maps at 100 agents, w = 1.3, one lock-step batch per rank,
+    32x32_obst204 maps at 100 agents, w = 1.3, one batch per rank (paths in a
+    device pool, replans in resumable slices, instances advance independently),
     no collective on the data path (the ranks only add up their counts); the
     host driver of a rank gets cores / world threads.  CBS: the full 8x8 set
     (config C2) under an expansion cap, rank 0."""
