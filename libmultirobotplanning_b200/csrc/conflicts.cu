@@ -343,8 +343,17 @@ conflict_hash2_kernel(const int32_t* __restrict__ posT, int N, int mode, int H,
   for (int t = blockIdx.x; t < max_t; t += gridDim.x) {
   if (todo && !todo[t]) continue;
   if (kFirst && !kCount) {
-    const unsigned long long b = *(volatile unsigned long long*)&result[0];
-    if (b != kNoConflict && (int)(b >> 41) < t) continue;
+    // an earlier conflict is already known: skip the step.  One thread looks, so that the
+    // whole block takes the same branch around the barriers below.
+    __shared__ int sSkip;
+    if (threadIdx.x == 0) {
+      const unsigned long long b = *(volatile unsigned long long*)&result[0];
+      sSkip = b != kNoConflict && (int)(b >> 41) < t;
+    }
+    __syncthreads();
+    const int skip = sSkip;
+    __syncthreads();  // the next iteration writes sSkip again
+    if (skip) continue;
   }
   const uint32_t mask = (uint32_t)H - 1u;
   const int32_t* rowA = posT + (size_t)t * rowStride(N);
@@ -473,8 +482,14 @@ conflict_sieve_kernel(const int32_t* __restrict__ posT, int N, int mode,
   const int max_t = maxLen - (mode == 0 ? 1 : 0);
   if (t >= max_t) return;
   if (kFirst && !kCount) {
-    const unsigned long long b = *(volatile unsigned long long*)&result[0];
-    if (b != kNoConflict && (int)(b >> 41) < t) return;
+    // block-uniform early exit: one thread reads the best key so far
+    __shared__ int sSkip;
+    if (threadIdx.x == 0) {
+      const unsigned long long b = *(volatile unsigned long long*)&result[0];
+      sSkip = b != kNoConflict && (int)(b >> 41) < t;
+    }
+    __syncthreads();
+    if (sSkip) return;
   }
   const int ld = rowStride(N);
   const int32_t* rowA = posT + (size_t)t * ld;
