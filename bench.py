@@ -836,6 +836,25 @@ def run_ours(args):
         got = capi.unpack_field(hp_np[probe], DIM, DIM, gxy_p[probe])
         assert np.array_equal(got, want), "packed e2e output differs from the oracle"
     del h_packed, hp_np
+    # (i') the compact result: the same bytes for the free cells only (mrp_bfs_fields_compact,
+    #      mrp_compact_value = getValue): an obstacle cell is INF in every field and the caller has the map
+    fbits, fprefix, n_free = capi.free_cell_index(DIM, DIM, obst)
+    h_compact = torch.empty((Gp, n_free), dtype=torch.uint8).pin_memory()
+    hc_np = h_compact.numpy()
+
+    def compact_call():
+        _, ovf = capi.bfs_fields_compact(DIM, DIM, obst, gxy_p, n_free, out=hc_np)
+        ovf_box.append(int(ovf.sum()))
+    te_compact = timed(compact_call, e2e_steps)
+    compact_d2h = capi.bfs_d2h_bytes()
+    assert ovf_box[-1] == 0
+    if rank == 0:
+        from oracle import orc
+        probe = [0, 1, Gp // 2, Gp - 1]
+        want = orc.bfs_fields(DIM, DIM, inst.obstacles, gxy_p[probe])
+        got = capi.unpack_compact(hc_np[probe], fbits, DIM, DIM, gxy_p[probe])
+        assert np.array_equal(got, want), "compact e2e output differs from the oracle"
+    del h_compact, hc_np
 
     Ge = min(E2E_GOALS, G)
     h_out = torch.empty((Ge, cells), dtype=torch.int32).pin_memory()
@@ -855,14 +874,19 @@ def run_ours(args):
     os.environ.pop("MRP_BFS_FMT")
     h_out.zero_()
     te = e2e_rate(e2e_steps)
-    e2e = {"value": world * Gp * cells / te_packed, "unit": "cells/s",
+    e2e = {"value": world * Gp * cells / te_compact, "unit": "cells/s",
            "h2d_bytes_per_step": int(obst.nbytes + gxy_p.nbytes),
-           "d2h_bytes_per_step": int(packed_d2h), "goals_per_step": Gp,
-           "ms_per_step": te_packed * 1e3,
-           "host_result_bytes_per_step": int(Gp * cells),
-           "api": "mrp_bfs_fields_packed (host pointers, page-locked uint8 output: one detour byte per cell, "
-                  "(distance - Manhattan) / 2, 255 = INF, read with mrp_packed_value = getValue; obstacles and "
+           "d2h_bytes_per_step": int(compact_d2h), "goals_per_step": Gp,
+           "ms_per_step": te_compact * 1e3,
+           "host_result_bytes_per_step": int(Gp * n_free),
+           "api": "mrp_bfs_fields_compact (host pointers, page-locked uint8 output: one detour byte, (distance - "
+                  "Manhattan) / 2, 255 = INF, per FREE cell of the map in cell order, read with mrp_compact_value "
+                  "= getValue through the free mask and its prefix sums from mrp_free_cell_index; obstacles and "
                   "goals go up, the map is built and every field comes down inside the timed region)",
+           "packed_all_cells": {
+               "value": world * Gp * cells / te_packed, "unit": "cells/s", "ms_per_step": te_packed * 1e3,
+               "d2h_bytes_per_step": int(packed_d2h),
+               "api": "mrp_bfs_fields_packed: one detour byte for every cell, obstacles included"},
            "int32_contract": {
                "value": world * Ge * cells / te, "unit": "cells/s", "goals_per_step": Ge,
                "ms_per_step": te * 1e3, "d2h_bytes_per_step": capi.bfs_d2h_bytes(),

@@ -61,6 +61,7 @@ EXPORTS = [
     "mrp_pathpool_create", "mrp_pathpool_destroy", "mrp_pathpool_reserve", "mrp_pathpool_write",
     "mrp_pathpool_read", "mrp_conflicts_batch_pool", "mrp_lowlevel_batch_pool",
     "mrp_pathpool_reserve_states", "mrp_lowlevel_batch_pool_sliced",
+    "mrp_free_cell_index", "mrp_bfs_fields_compact",
 ]
 COMM_ID_BYTES = 128
 
@@ -224,6 +225,42 @@ def bfs_fields_packed(dimx, dimy, obst_xy, goal_xy, out=None):
     check(lib().mrp_bfs_fields_packed(dimx, dimy, _p(obst), len(obst), _p(goals), len(goals),
                                       _p(out), _p(ovf)))
     return out, ovf
+
+
+def free_cell_index(dimx, dimy, obst_xy):
+    """(free_bits uint32 [ceil(cells/32)], prefix int32 [ceil(cells/32)+1], n_free): mrp_free_cell_index
+    (host only: works without a device)."""
+    obst = _i32(obst_xy).reshape(-1, 2)
+    nw = (dimx * dimy + 31) // 32
+    bits = np.zeros(nw, np.uint32)
+    prefix = np.zeros(nw + 1, np.int32)
+    n = lib().mrp_free_cell_index(dimx, dimy, _p(obst), len(obst), _p(bits), _p(prefix))
+    check(min(n, 0))
+    return bits, prefix, int(n)
+
+
+def bfs_fields_compact(dimx, dimy, obst_xy, goal_xy, n_free, out=None):
+    """Detour bytes of the free cells only (mrp_bfs_fields_compact): (bytes [n][n_free], overflowed [n])."""
+    obst = _i32(obst_xy).reshape(-1, 2)
+    goals = _i32(goal_xy).reshape(-1, 2)
+    if out is None:
+        out = np.empty((len(goals), n_free), np.uint8)
+    ovf = np.zeros(len(goals), np.int32)
+    check(lib().mrp_bfs_fields_compact(dimx, dimy, _p(obst), len(obst), _p(goals), len(goals),
+                                       _p(out), _p(ovf)))
+    return out, ovf
+
+
+def unpack_compact(compact, free_bits, dimx, dimy, goal_xy):
+    """numpy mirror of mrp_compact_value over whole fields: int32 [n][cells]."""
+    cells = dimx * dimy
+    free = np.unpackbits(free_bits.view(np.uint8), bitorder="little")[:cells].astype(bool)
+    full = np.full((len(compact), cells), 255, np.uint8)
+    full[:, free] = compact
+    out = unpack_field(full, dimx, dimy, goal_xy)
+    goals = _i32(goal_xy).reshape(-1, 2)
+    out[np.arange(len(goals)), goals[:, 0] + dimx * goals[:, 1]] = 0  # also for a goal on an obstacle
+    return out
 
 
 def unpack_field(packed, dimx, dimy, goal_xy):

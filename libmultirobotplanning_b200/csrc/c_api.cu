@@ -474,6 +474,40 @@ pack_fields_u8_kernel(const int32_t* __restrict__ in, uint8_t* __restrict__ out,
 }  // extern "C++"
 
 extern "C++" {
+// Compact variant: only the free cells of the map, in cell order.  One warp per (field, word
+// of 32 cells): the byte of cell c goes to position prefix[c / 32] + popc(free bits below c).
+__global__ void __launch_bounds__(256)
+pack_fields_compact_kernel(const int32_t* __restrict__ in, uint8_t* __restrict__ out, int nFields,
+                           int dimx, int cells, int nWords, int nFree,
+                           const uint32_t* __restrict__ freeBits, const int32_t* __restrict__ prefix,
+                           const int32_t* __restrict__ goalCell, int* __restrict__ overflow) {
+  const int lane = threadIdx.x & 31;
+  const size_t warp0 = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const size_t nWarps = ((size_t)gridDim.x * blockDim.x) >> 5;
+  const size_t total = (size_t)nFields * nWords;
+  bool ovf = false;
+  for (size_t k = warp0; k < total; k += nWarps) {
+    const int f = (int)(k / (size_t)nWords), w = (int)(k - (size_t)f * nWords);
+    const uint32_t bits = __ldg(freeBits + w);
+    if (bits == 0u) continue;
+    const int cell = 32 * w + lane;
+    if (cell < cells && ((bits >> lane) & 1u)) {
+      const int v = __ldcs(in + (size_t)f * cells + cell);
+      uint32_t b = 255u;
+      if (v != MRP_INF) {
+        const int g = __ldg(goalCell + f);
+        const int h = (v - abs(cell % dimx - g % dimx) - abs(cell / dimx - g / dimx)) >> 1;
+        if (h >= 255) ovf = true;
+        b = (uint32_t)h & 255u;
+      }
+      out[(size_t)f * nFree + __ldg(prefix + w) + __popc(bits & ((1u << lane) - 1u))] = (uint8_t)b;
+    }
+  }
+  if (__syncthreads_or(ovf) && threadIdx.x == 0) atomicOr(overflow, 1);
+}
+}  // extern "C++"
+
+extern "C++" {
 namespace mrp {
 // widen.cpp
 void widenFieldU16(const uint16_t* src, int32_t* dst, size_t n, int threads);
@@ -747,8 +781,46 @@ int mrp_bfs_fields(int dimx, int dimy, const int32_t* obst_xy, int n_obst,
 
 // The packed result mode: one detour byte per cell, copied straight into the
 // caller's buffer (no host expansion); see include/mrp_b200.h.
+int mrp_free_cell_index(int dimx, int dimy, const int32_t* obst_xy, int n_obst, uint32_t* free_bits,
+                        int32_t* prefix) {
+  MRP_CHECK(dimx > 0 && dimy > 0 && n_obst >= 0 && (n_obst == 0 || obst_xy) && free_bits && prefix,
+            MRP_ERR_INVALID, "bad arguments");
+  MRP_CHECK((long long)dimx * dimy < (1ll << 31), MRP_ERR_UNSUPPORTED, "map too large");
+  const int cells = dimx * dimy, nWords = (cells + 31) / 32;
+  for (int w = 0; w < nWords; ++w) {
+    const int n = std::min(32, cells - 32 * w);
+    free_bits[w] = n == 32 ? 0xffffffffu : ((1u << n) - 1u);
+  }
+  for (int k = 0; k < n_obst; ++k) {
+    const int x = obst_xy[2 * k], y = obst_xy[2 * k + 1];
+    if (x < 0 || y < 0 || x >= dimx || y >= dimy) continue;
+    const int c = x + dimx * y;
+    free_bits[c >> 5] &= ~(1u << (c & 31));
+  }
+  int run = 0;
+  for (int w = 0; w < nWords; ++w) {
+    prefix[w] = run;
+    run += __builtin_popcount(free_bits[w]);
+  }
+  prefix[nWords] = run;
+  return run;
+}
+
+static int packedFieldsImpl(int dimx, int dimy, const int32_t* obst_xy, int n_obst, const int32_t* goal_xy,
+                            int n_goals, uint8_t* out, int32_t* overflowed, bool compact);
+
 int mrp_bfs_fields_packed(int dimx, int dimy, const int32_t* obst_xy, int n_obst,
                           const int32_t* goal_xy, int n_goals, uint8_t* out, int32_t* overflowed) {
+  return packedFieldsImpl(dimx, dimy, obst_xy, n_obst, goal_xy, n_goals, out, overflowed, false);
+}
+
+int mrp_bfs_fields_compact(int dimx, int dimy, const int32_t* obst_xy, int n_obst,
+                           const int32_t* goal_xy, int n_goals, uint8_t* out, int32_t* overflowed) {
+  return packedFieldsImpl(dimx, dimy, obst_xy, n_obst, goal_xy, n_goals, out, overflowed, true);
+}
+
+static int packedFieldsImpl(int dimx, int dimy, const int32_t* obst_xy, int n_obst, const int32_t* goal_xy,
+                            int n_goals, uint8_t* out, int32_t* overflowed, bool compact) {
   MRP_CHECK(n_goals >= 0, MRP_ERR_INVALID, "n_goals < 0");
   MRP_CHECK(n_goals == 0 || (goal_xy && out), MRP_ERR_INVALID, "NULL pointer");
   if (int rc = validateGoals(dimx, dimy, goal_xy, n_goals)) return rc;
@@ -756,6 +828,21 @@ int mrp_bfs_fields_packed(int dimx, int dimy, const int32_t* obst_xy, int n_obst
   if (n_goals == 0) return 0;
   mrp_map map = nullptr;
   if (int rc = mrp_map_create(dimx, dimy, obst_xy, n_obst, &map)) return rc;
+  // compact result: the free cells only (prefix sums of the free mask give their positions)
+  const int nWords = (dimx * dimy + 31) / 32;
+  std::vector<uint32_t> freeBits;
+  std::vector<int32_t> prefix;
+  size_t perField = (size_t)dimx * dimy;  // bytes of one field in the caller's array
+  if (compact) {
+    freeBits.resize(nWords);
+    prefix.resize(nWords + 1);
+    const int nFree = mrp_free_cell_index(dimx, dimy, obst_xy, n_obst, freeBits.data(), prefix.data());
+    if (nFree < 0) {
+      mrp_map_destroy(map);
+      return nFree;
+    }
+    perField = (size_t)nFree;
+  }
   int rc = 0, nOverflowed = 0;
   {
     std::lock_guard<std::mutex> lk(apiMutex());
@@ -770,7 +857,8 @@ int mrp_bfs_fields_packed(int dimx, int dimy, const int32_t* obst_xy, int n_obst
     const size_t wsBytes = (map->W == 1 && map->S == 1) ? 16 * batch + 256
                                                         : bfsLargeWorkspaceBytes(map, (int)batch);
     const size_t slotBytes = ((batch * cells + 255) & ~(size_t)255) + 256;
-    int32_t *d_goals = nullptr, *d_out = nullptr;
+    int32_t *d_goals = nullptr, *d_out = nullptr, *d_prefix = nullptr;
+    uint32_t* d_freeBits = nullptr;
     char *wsp = nullptr, *d_pack = nullptr;
     void* h_flags = nullptr;
     cudaEvent_t done[2] = {nullptr, nullptr}, copied[2] = {nullptr, nullptr};
@@ -781,6 +869,12 @@ int mrp_bfs_fields_packed(int dimx, int dimy, const int32_t* obst_xy, int n_obst
       if ((rc = scratch(3, wsBytes, &wsp))) break;
       if ((rc = scratch(4, 2 * slotBytes, &d_pack))) break;
       if ((rc = pinnedScratch(4, nBatches * sizeof(int), &h_flags))) break;
+      if (compact) {
+        if ((rc = scratch(13, (size_t)nWords, &d_freeBits))) break;
+        if ((rc = scratch(14, (size_t)nWords + 1, &d_prefix))) break;
+        cudaMemcpyAsync(d_freeBits, freeBits.data(), (size_t)nWords * 4, cudaMemcpyHostToDevice, c.stream);
+        cudaMemcpyAsync(d_prefix, prefix.data(), ((size_t)nWords + 1) * 4, cudaMemcpyHostToDevice, c.stream);
+      }
       cudaError_t e = cudaMemcpyAsync(d_goals, goalCell.data(), (size_t)n_goals * 4,
                                       cudaMemcpyHostToDevice, c.stream);
       if (e != cudaSuccess) {
@@ -802,7 +896,11 @@ int mrp_bfs_fields_packed(int dimx, int dimy, const int32_t* obst_xy, int n_obst
         cudaMemsetAsync(dflag, 0, sizeof(int), c.stream);
         const size_t total = n * cells;
         const int grid = (int)std::min<size_t>((total / 8 + 255) / 256 + 1, (size_t)c.smCount * 16);
-        if (map->dimx % 16 == 0)
+        if (compact)
+          pack_fields_compact_kernel<<<grid, 256, 0, c.stream>>>(
+              d_out, reinterpret_cast<uint8_t*>(dslot), (int)n, map->dimx, (int)cells, nWords, (int)perField,
+              d_freeBits, d_prefix, d_goals + g0, dflag);
+        else if (map->dimx % 16 == 0)
           pack_fields_u8_kernel<true><<<grid, 256, 0, c.stream>>>(
               d_out, reinterpret_cast<uint8_t*>(dslot), total, map->dimx, (int)cells, d_goals + g0, dflag);
         else
@@ -811,7 +909,8 @@ int mrp_bfs_fields_packed(int dimx, int dimy, const int32_t* obst_xy, int n_obst
         countLaunch();
         cudaEventRecord(done[sl], c.stream);
         cudaStreamWaitEvent(c.copyStream, done[sl], 0);
-        e = cudaMemcpyAsync(out + g0 * cells, dslot, total, cudaMemcpyDeviceToHost, c.copyStream);
+        const size_t wire = n * perField;
+        e = cudaMemcpyAsync(out + g0 * perField, dslot, wire, cudaMemcpyDeviceToHost, c.copyStream);
         if (e == cudaSuccess)
           e = cudaMemcpyAsync(static_cast<int*>(h_flags) + j, dflag, sizeof(int), cudaMemcpyDeviceToHost,
                               c.copyStream);
@@ -819,7 +918,7 @@ int mrp_bfs_fields_packed(int dimx, int dimy, const int32_t* obst_xy, int n_obst
           rc = fail(MRP_ERR_CUDA, "D2H copy failed: %s", cudaGetErrorString(e));
           break;
         }
-        g_bfsD2hBytes += (long long)total;
+        g_bfsD2hBytes += (long long)wire;
         cudaEventRecord(copied[sl], c.copyStream);
       }
       cudaError_t e1 = cudaStreamSynchronize(c.stream);

@@ -100,3 +100,23 @@ def test_product_does_not_import_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".cpp", ".hpp", ".h")):
                 text = open(os.path.join(dirpath, f), errors="ignore").read()
                 assert "oracle" not in text.lower().replace("# oracle", ""), f
+
+
+def test_free_cell_index_without_a_gpu():
+    """mrp_free_cell_index (the index of the compact field format) is host code: free mask,
+    prefix sums and the number of free cells against numpy, on a map whose cell count is not
+    a multiple of 32, obstacles outside the map ignored."""
+    import numpy as np
+    from libmultirobotplanning_b200 import capi
+    rng = np.random.default_rng(4)
+    dimx, dimy = 37, 21
+    blocked = rng.random((dimy, dimx)) < 0.3
+    ys, xs = np.nonzero(blocked)
+    obst = np.concatenate([np.stack([xs, ys], 1), [[-1, 3], [dimx, 0], [5, dimy]]]).astype(np.int32)
+    bits, prefix, n = capi.free_cell_index(dimx, dimy, obst)
+    free = (~blocked).ravel()
+    assert n == free.sum() == prefix[-1]
+    got = np.unpackbits(bits.view(np.uint8), bitorder="little")
+    assert (got[:dimx * dimy].astype(bool) == free).all() and not got[dimx * dimy:].any()
+    cs = np.concatenate([[0], np.cumsum(free)])
+    assert all(prefix[w] == cs[min(32 * w, dimx * dimy)] for w in range(len(prefix)))

@@ -281,3 +281,34 @@ def test_packed_result_mode(capi, orc):
     goals = [[0, 0], [dimx - 1, dimy - 1], [40, 20]]
     packed, ovf = capi.bfs_fields_packed(dimx, dimy, obst, goals)
     assert ovf.all()
+
+
+@pytest.mark.parametrize("batch", ["0", "3"])
+def test_compact_result_mode(capi, orc, batch):
+    """mrp_bfs_fields_compact: detour bytes of the free cells only, positions from
+    mrp_free_cell_index; read back with the numpy mirror of mrp_compact_value it must equal
+    the oracle's int fields on odd map shapes (cell counts that are no multiple of 32,
+    single-cell map, no obstacles, goals on obstacles); the D2H bytes are n_free per field;
+    a serpentine whose detours do not fit a byte is reported as overflowed."""
+    rng = np.random.default_rng(15)
+    for dimx, dimy, density, ng in [(300, 200, 0.2, 40), (33, 7, 0.1, 11), (1, 1, 0.0, 1),
+                                    (1024, 40, 0.2, 7), (48, 31, 0.0, 9), (64, 64, 0.45, 20)]:
+        obst = _rand_map(rng, dimx, dimy, density)
+        cells = rng.choice(dimx * dimy, ng, replace=False)
+        goals = np.stack([cells % dimx, cells // dimx], 1)
+        want = orc.bfs_fields(dimx, dimy, obst, goals)
+        bits, prefix, n_free = capi.free_cell_index(dimx, dimy, obst)
+        env = {} if batch == "0" else {"MRP_BFS_BATCH": batch}
+        got, ovf = _with_env(env, lambda: capi.bfs_fields_compact(dimx, dimy, obst, goals, n_free))
+        assert got.shape == (ng, n_free) and not ovf.any()
+        assert capi.bfs_d2h_bytes() == ng * n_free
+        assert np.array_equal(capi.unpack_compact(got, bits, dimx, dimy, goals), want)
+    dimx, dimy = 64, 33
+    obst = _serpentine(dimx, dimy)
+    goals = [[0, 0], [63, 32], [5, 16]]
+    bits, prefix, n_free = capi.free_cell_index(dimx, dimy, obst)
+    got, ovf = _with_env({"MRP_BFS_BATCH": "1"}, lambda: capi.bfs_fields_compact(dimx, dimy, obst, goals, n_free))
+    assert ovf[0] == 1
+    want = orc.bfs_fields(dimx, dimy, obst, goals)
+    ok = [k for k in range(3) if not ovf[k]]
+    assert np.array_equal(capi.unpack_compact(got[ok], bits, dimx, dimy, np.asarray(goals)[ok]), want[ok])
