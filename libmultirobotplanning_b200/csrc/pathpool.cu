@@ -176,6 +176,9 @@ int mrp_pathpool_reserve(mrp_pathpool pool, int n_slots) {
 int mrp_pathpool_reserve_states(mrp_pathpool pool, int n_states, int dimx, int dimy, int max_expanded) {
   MRP_CHECK(pool != nullptr && n_states >= 0 && max_expanded > 0 && dimx > 0 && dimy > 0, MRP_ERR_INVALID,
             "bad arguments");
+  // rows of the visited bitmap.  192 time steps: with 128 (six warps per SM instead of four) the
+  // 100-agent ECBS batch took 1.3-2.1 s instead of 1.0 s: searches that look past t = 128 are
+  // handed to the general kernel, which runs them to the end inside the launch
   const int TB = dimx * dimy <= 64 ? 64 : 192;
   const int maxNodes = 5 * max_expanded + 8;
   if (pool->blobBytes == 0) {
