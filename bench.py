@@ -386,6 +386,7 @@ def search_metrics(pkg, rank=0, world=1, dist=None, dev=None):
     out["cbs_ta_c4_cpu_instances_per_s_1core"] = sum(r["status"] == 0 for r in cres) / dt
     out["cbs_ta_c4_cost_mismatches_vs_oracle"] = sum(
         1 for a, b in zip(res[::25], cres) if a["status"] == 0 and b["status"] == 0 and a["cost"] != b["cost"])
+    out.update(c4_reference_binary(pkg, c4, res))
     cap_hl = 500
     c2runs = []
     for _ in range(2):  # the first run creates the pools and arenas of the 16 lanes small instances use
@@ -443,6 +444,44 @@ def c1_datapoint(pkg, s32):
                                        "highLevelExpanded": st["highLevelExpanded"],
                                        "lowLevelExpanded": st["lowLevelExpanded"]}
     return {"c1_ecbs_w1.3_agents10_ex1": d}
+
+
+def c4_reference_binary(pkg, c4, res):
+    """Config C4 next to the UNMODIFIED reference cbs_ta (oracle/_ref/cbs_ta, example/cbs_ta.cpp with
+    the reference's own headers against stand-in Boost headers): every answer of the batch against the
+    committed answers of that binary (tests/golden/ref_binary_golden_ta.json), and the binary itself
+    timed on a few instances on one host core (its time is mostly the Floyd-Warshall precompute over
+    all 1024 cells, example/shortest_path_heuristic.hpp:47-53, which its own timer leaves out)."""
+    import tempfile
+    import yaml
+    d = {}
+    gpath = os.path.join(ROOT, "tests", "golden", "ref_binary_golden_ta.json")
+    if os.path.exists(gpath):
+        g = json.load(open(gpath))["cbs_ta"]
+        pairs = [(g.get("all/" + i.name), r) for i, r in zip(c4, res)]
+        pairs = [(a, b) for a, b in pairs if a is not None and a["solved"] and b["status"] == 0]
+        d["cbs_ta_c4_compared_with_reference_binary"] = len(pairs)
+        d["cbs_ta_c4_cost_mismatches_vs_reference_binary"] = sum(1 for a, b in pairs if a["cost"] != b["cost"])
+    exe = os.path.join(ROOT, "oracle", "_ref", "cbs_ta")
+    if os.path.exists(exe):
+        walls, inner, same = [], [], 0
+        with tempfile.TemporaryDirectory() as td:
+            inp, outp = os.path.join(td, "i.yaml"), os.path.join(td, "o.yaml")
+            for k in range(0, len(c4), max(1, len(c4) // 4)):
+                pkg.instances.save_yaml(c4[k], inp)
+                t0 = time.perf_counter()
+                subprocess.run([exe, "-i", inp, "-o", outp], stdout=subprocess.DEVNULL,
+                               stderr=subprocess.DEVNULL, timeout=120, check=True, cwd=td)
+                walls.append(time.perf_counter() - t0)
+                with open(outp) as f:
+                    st = yaml.safe_load(f)["statistics"]
+                inner.append(st["runtime"])
+                same += int(res[k]["status"] == 0 and st["cost"] == res[k]["cost"])
+        d["cbs_ta_c4_reference_binary_1core"] = {
+            "instances": len(walls), "same_cost_as_this_path": same,
+            "seconds_per_instance_process": sum(walls) / len(walls),
+            "seconds_per_instance_search_only": sum(inner) / len(inner)}
+    return d
 
 
 def c3_scaled(pkg, s32, sizes=((120, 100), (160, 50), (200, 30)), seconds=30.0):

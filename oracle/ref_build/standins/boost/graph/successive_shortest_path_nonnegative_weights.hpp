@@ -1,0 +1,4 @@
+// Stand-in for <boost/graph/successive_shortest_path_nonnegative_weights.hpp> (TEST INFRASTRUCTURE): everything lives in
+// the adjacency_list.hpp next to this file.
+#pragma once
+#include "adjacency_list.hpp"

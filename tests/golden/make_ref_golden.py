@@ -37,9 +37,12 @@ def run(tool, inst, extra=(), timeout=10.0):
         with open(out) as f:
             y = yaml.safe_load(f)
         s = y["statistics"]
-        return {"solved": True, "cost": s["cost"], "makespan": s["makespan"],
-                "highLevelExpanded": s["highLevelExpanded"],
-                "lowLevelExpanded": s["lowLevelExpanded"], "runtime": s["runtime"]}
+        r = {"solved": True, "cost": s["cost"], "makespan": s["makespan"],
+             "highLevelExpanded": s["highLevelExpanded"],
+             "lowLevelExpanded": s["lowLevelExpanded"], "runtime": s["runtime"]}
+        if "numTaskAssignments" in s:  # cbs_ta / ecbs_ta (example/cbs_ta.cpp:599)
+            r["numTaskAssignments"] = s["numTaskAssignments"]
+        return r
 
 
 if __name__ == "__main__":

@@ -503,3 +503,62 @@ def test_total_expansion_budget_caps_an_instance(capi, set32):
     wide = solver.solve_batch(solver.ECBS, insts, w=1.3, max_hl=500, max_ll_total=10 ** 8)
     assert [(r["status"], r["cost"], r["ll_expanded"]) for r in wide] == \
         [(r["status"], r["cost"], r["ll_expanded"]) for r in ref]
+
+
+def _ta_reference_cases(set8, set32, prefix):
+    """(instance, answer of the unmodified reference cbs_ta binary) for the golden entries whose
+    key starts with `prefix` (tests/golden/make_ref_golden_ta.py)."""
+    import json
+    import sys
+    gdir = os.path.join(ROOT, "tests", "golden")
+    if gdir not in sys.path:
+        sys.path.insert(0, gdir)
+    import make_ref_golden_ta as T
+    g = json.load(open(os.path.join(gdir, "ref_binary_golden_ta.json")))["cbs_ta"]
+    out = []
+    for key, tool, inst, _, _ in T.selection(set8, set32):
+        ref = g.get(key) if tool == "cbs_ta" and key.startswith(prefix) else None
+        if ref is None or (ref["solved"] and ref["highLevelExpanded"] > 300):
+            continue
+        out.append((key, inst, ref))
+    return out
+
+
+def _solve_ta_by_shape(cases, max_hl):
+    from libmultirobotplanning_b200 import solver
+    res = [None] * len(cases)
+    for dim in sorted({c[1].dimx for c in cases}):  # one batch per map size
+        idx = [k for k, c in enumerate(cases) if c[1].dimx == dim]
+        for k, r in zip(idx, solver.solve_batch(solver.CBS_TA, [cases[k][1] for k in idx],
+                                                max_hl=max_hl)):
+            res[k] = r
+    return res
+
+
+def test_cbs_ta_config_c4_equals_reference_binary(capi, set8, set32):
+    """BASELINE config 4 (every goal of the file potential for every agent, 10-40 agents on
+    32x32_obst204 and the 8x8 set): the optimal sum of costs equals what the UNMODIFIED
+    reference cbs_ta prints (example/cbs_ta.cpp:589-600; golden made by
+    tests/golden/make_ref_golden_ta.py from oracle/_ref/cbs_ta)."""
+    cases = _ta_reference_cases(set8, set32, "all/")
+    assert len(cases) >= 300
+    for (key, inst, ref), r in zip(cases, _solve_ta_by_shape(cases, 20000)):
+        assert ref["solved"] and r["status"] == 0 and r["cost"] == ref["cost"], (key, r["status"])
+        if inst.n_agents <= 10:
+            check_solution(inst, r["paths"], 1)
+
+
+def test_cbs_ta_goal_subsets_equal_reference_binary(capi, set8, set32):
+    """Seeded subsets of the goals per agent: agents with few or no potential goals (unassigned
+    agents plan without a task, example/cbs_ta.cpp:283-319) and instances without any
+    assignment / solution (the reference prints "Planning NOT successful!")."""
+    cases = _ta_reference_cases(set8, set32, "sub/")
+    assert len(cases) >= 100
+    unsolved = 0
+    for (key, inst, ref), r in zip(cases, _solve_ta_by_shape(cases, 20000)):
+        if ref["solved"]:
+            assert r["status"] == 0 and r["cost"] == ref["cost"], (key, r["status"])
+        else:
+            assert r["status"] == 1, (key, r["status"])
+            unsolved += 1
+    assert unsolved >= 1
