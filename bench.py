@@ -349,6 +349,8 @@ def search_metrics(pkg, rank=0, world=1, dist=None, dev=None):
         t0 = time.perf_counter()
         fields = pkg.capi.bfs_fields_batch(sset)
         dt = time.perf_counter() - t0
+        if tag == "32x32":
+            fields32 = fields
         ncell = sum(f.size for f in fields)
         out["bfs_%s_e2e_cells_per_s" % tag] = ncell / dt
         out["bfs_%s_fields" % tag] = int(sum(len(f) for f in fields))
@@ -357,6 +359,20 @@ def search_metrics(pkg, rank=0, world=1, dist=None, dev=None):
     t0 = time.perf_counter()
     orc.floyd_warshall(32, 32, s32[0].obstacles)
     out["floyd_warshall_32x32_cpu_seconds_per_map"] = time.perf_counter() - t0
+    # ... and the reference's own class doing it (oracle/_ref/sph_fields: shortest_path_heuristic.hpp
+    # compiled unmodified, Boost.Graph calls resolved by the stand-in headers), process time included
+    sph = os.path.join(ROOT, "oracle", "_ref", "sph_fields")
+    if os.path.exists(sph):
+        import tempfile
+        i0 = s32[0]
+        txt = "%d %d %d %d\n" % (i0.dimx, i0.dimy, len(i0.obstacles), len(i0.goals))
+        txt += "".join("%d %d\n" % (x, y) for x, y in i0.obstacles) + "".join("%d %d\n" % (x, y) for x, y in i0.goals)
+        with tempfile.TemporaryDirectory() as td:
+            t0 = time.perf_counter()
+            raw = subprocess.run([sph], input=txt.encode(), stdout=subprocess.PIPE, check=True, cwd=td).stdout
+            out["floyd_warshall_32x32_reference_class_seconds_per_map"] = time.perf_counter() - t0
+        ref_f = np.frombuffer(raw, np.int32).reshape(len(i0.goals), -1)
+        out["bfs_32x32_fields_equal_reference_class"] = bool(np.array_equal(ref_f, fields32[0]))
     # config C4: CBS-TA with every goal of the instance potential for every agent
     # (all-agents x all-goals distance fields, cost matrix from the fields): the
     # 10- and 20-agent files of the 32x32 set, one batch, next to the oracle

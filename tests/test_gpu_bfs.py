@@ -312,3 +312,20 @@ def test_compact_result_mode(capi, orc, batch):
     want = orc.bfs_fields(dimx, dimy, obst, goals)
     ok = [k for k in range(3) if not ovf[k]]
     assert np.array_equal(capi.unpack_compact(got[ok], bits, dimx, dimy, np.asarray(goals)[ok]), want[ok])
+
+
+def test_fields_equal_reference_class(capi, set8, set32):
+    """The CUDA fields against the reference's OWN ShortestPathHeuristic class
+    (example/shortest_path_heuristic.hpp:12-62 compiled unmodified; CRCs committed by
+    tests/golden/make_sph_golden.py): benchmark maps and seeded odd shapes, bit for bit."""
+    import json
+    import os
+    import sys
+    gdir = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    if gdir not in sys.path:
+        sys.path.insert(0, gdir)
+    import make_sph_golden as S
+    g = json.load(open(os.path.join(gdir, "sph_fields_golden.json")))
+    for name, (dx, dy, obst, goals) in S.cases(set8, set32).items():
+        f = capi.bfs_fields(dx, dy, obst, goals)
+        assert S.crc(f) == g[name]["crc32"], name

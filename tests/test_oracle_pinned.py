@@ -380,3 +380,31 @@ def test_reference_ta_binaries_live(ref_fixtures, tmp_path):
                    stdout=subprocess.DEVNULL, cwd=str(tmp_path))
     y = yaml.safe_load(open(out))
     assert [s["cost"] for s in y["solutions"]] == [1, 2]
+
+
+def test_oracle_fields_equal_reference_class(orc, set8, set32):
+    """tests/golden/sph_fields_golden.json: CRC-32 of the distance fields that the reference's OWN
+    ShortestPathHeuristic class returns through getValue (example/shortest_path_heuristic.hpp:12-62,
+    compiled unmodified into oracle/_ref/sph_fields against the Boost.Graph stand-in) on benchmark
+    maps and seeded odd shapes (1-wide, non-square, goals on obstacles, closed pockets).  The
+    oracle's per-goal BFS must give the same bytes."""
+    import json
+    import os
+    import sys
+    gdir = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    if gdir not in sys.path:
+        sys.path.insert(0, gdir)
+    import make_sph_golden as S
+    g = json.load(open(os.path.join(gdir, "sph_fields_golden.json")))
+    cases = S.cases(set8, set32)
+    assert set(cases) == set(g) and len(g) >= 60
+    for name, (dx, dy, obst, goals) in cases.items():
+        f = orc.bfs_fields(dx, dy, obst, goals)
+        assert S.crc(f) == g[name]["crc32"], name
+        assert int((f == orc.INF).sum()) == g[name]["unreachable"], name
+    # live, where the binary was built: two cases straight from the class
+    if os.path.exists(S.EXE):
+        for name in ("odd_13x7_d20", "odd_64x5_d40"):
+            dx, dy, obst, goals = cases[name]
+            assert np.array_equal(S.reference_fields(dx, dy, obst, goals),
+                                  orc.bfs_fields(dx, dy, obst, goals)), name
