@@ -381,3 +381,27 @@ def test_hashed_sweep_with_parked_agents(capi, orc, monkeypatch):
             if N <= 700:
                 assert got == (orc.first_conflict(cell, ln, dimx, mode), orc.count_conflicts(cell, ln, mode))
             assert got[1] > 50
+
+
+def test_conflicts_equal_reference_environment(capi):
+    """The CUDA conflict kernels against the reference's OWN Environment methods (the example
+    files included unmodified into oracle/_ref/env_probe_*; answers committed by
+    tests/golden/make_env_golden.py): first conflict under both loop bounds
+    (example/cbs.cpp:335-386, cbs_ta.cpp:369-420), focalHeuristic's count (ecbs.cpp:315-350) and
+    focalState / focalTransition counts (ecbs.cpp:282-312) on 40 seeded tables."""
+    import json
+    import os
+    import sys
+    gdir = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    if gdir not in sys.path:
+        sys.path.insert(0, gdir)
+    import make_env_golden as E
+    g = json.load(open(os.path.join(gdir, "env_probe_golden.json")))
+    for k, (dimx, cell, ln, qs) in enumerate(E.tables()):
+        for mode, key in ((0, "first_mode0"), (1, "first_mode1")):
+            got = capi.first_conflict(cell, ln, dimx, mode)
+            assert (list(got) if got else None) == g[key][k], (k, mode)
+        assert capi.count_conflicts(cell, ln, 0) == g["count"][k], k
+        for q, want in zip(qs, g["focal_queries"][k]):
+            s, tr = capi.focal_counts(cell, ln, q[0], [q[1]], [q[2]], [q[3]])
+            assert [int(s[0]), int(tr[0])] == want, (k, q)

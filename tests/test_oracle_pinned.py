@@ -408,3 +408,32 @@ def test_oracle_fields_equal_reference_class(orc, set8, set32):
             dx, dy, obst, goals = cases[name]
             assert np.array_equal(S.reference_fields(dx, dy, obst, goals),
                                   orc.bfs_fields(dx, dy, obst, goals)), name
+
+
+def test_oracle_conflicts_equal_reference_environment(orc):
+    """tests/golden/env_probe_golden.json: what the reference's OWN Environment methods return
+    (example/cbs.cpp:335-386, cbs_ta.cpp:369-420, ecbs.cpp:282-350 — the example files included
+    unmodified into oracle/_ref/env_probe_*) on 40 seeded path tables: first conflict under both
+    loop bounds, conflict count, focalState / focalTransition counts of 240 candidate moves
+    (also past the ends of the paths).  The oracle must return the same tuples and counts."""
+    import json
+    import os
+    import sys
+    gdir = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    if gdir not in sys.path:
+        sys.path.insert(0, gdir)
+    import make_env_golden as E
+    g = json.load(open(os.path.join(gdir, "env_probe_golden.json")))
+    tabs = E.tables()
+    assert len(tabs) == len(g["count"]) == 40
+    for k, (dimx, cell, ln, qs) in enumerate(tabs):
+        for mode, key in ((0, "first_mode0"), (1, "first_mode1")):
+            got = orc.first_conflict(cell, ln, dimx, mode)
+            assert (list(got) if got else None) == g[key][k], (k, mode)
+        assert orc.count_conflicts(cell, ln, 0) == g["count"][k], k
+        for q, want in zip(qs, g["focal_queries"][k]):
+            s, tr = orc.focal_counts(cell, ln, q[0], [q[1]], [q[2]], [q[3]])
+            assert [int(s[0]), int(tr[0])] == want, (k, q)
+    if os.path.exists(os.path.join(E.REF, "env_probe_ecbs")):  # live, where the probes were built
+        live = E.probe("env_probe_ecbs", tabs[:8], True)
+        assert [r["count"] for r in live] == g["count"][:8]
