@@ -7,21 +7,30 @@
  * cpu_baseline / --impl reference legs of bench.py may load it.
  *
  * Parity status: the reference cannot be compiled as shipped in this image
- * (Boost and yaml-cpp are absent).  The oracle is pinned twice:
- *  (1) against the UNMODIFIED reference cbs / ecbs sources compiled with
- *      stand-in third-party headers (oracle/ref_build -> oracle/_ref/): 582 CBS
- *      instances with identical cost, makespan and expansion counts, 36 ECBS
- *      w=1.3 instances (tests/golden/ref_binary_golden.json,
- *      tests/test_oracle_pinned.py::test_oracle_equals_reference_binaries);
- *  (2) against the known answers held by the reference's own tests (test/test_cbs.py:24-34, test/test_ecbs.py:25-35,
- * test/test_cbs_ta.py:24-38, test/test_assignment.py:19-63,
- * test/test_next_best_assignment.py:19-110) — see tests/test_oracle_pinned.py.
- * Function-level outputs (distance fields, conflict tuples, focal counts) are
- * NOT pinned by any reference test; for those the oracle is cross-checked by
- * two independent restatements (Floyd–Warshall vs queue BFS) and by the
- * anchors recorded in BASELINE.md.  Tie-breaking among equal-cost optimal
- * paths / equal-cost tree nodes depends on Boost.Heap internals and is
- * "parity unpinned".
+ * (Boost and yaml-cpp are absent).  What can be compiled is its own source,
+ * UNMODIFIED, against small stand-in headers for those libraries
+ * (oracle/ref_build -> oracle/_ref/), and the oracle is pinned against that:
+ *  (1) whole searches: cbs / ecbs on 582 + 36 benchmark instances with identical
+ *      cost, makespan and expansion counts (tests/golden/ref_binary_golden.json);
+ *      cbs_ta / ecbs_ta (with a stand-in for the slice of Boost.Graph and
+ *      boost::bimap that assignment.hpp and shortest_path_heuristic.hpp use) on
+ *      594 task-assignment instances: every optimal sum of costs and every "no
+ *      solution" (tests/golden/ref_binary_golden_ta.json);
+ *  (2) functions: distance fields against getValue() of the reference's own
+ *      ShortestPathHeuristic class on 70 maps (oracle/_ref/sph_fields,
+ *      tests/golden/sph_fields_golden.json); getFirstConflict under both loop
+ *      bounds, focalHeuristic, focalStateHeuristic and focalTransitionHeuristic
+ *      against the reference's own Environment classes on 40 path tables
+ *      (oracle/_ref/env_probe_*, tests/golden/env_probe_golden.json);
+ *  (3) the known answers held by the reference's own tests (test/test_cbs.py:24-34,
+ *      test/test_ecbs.py:25-35, test/test_cbs_ta.py:24-38, test/test_assignment.py:19-63,
+ *      test/test_next_best_assignment.py:19-110) — the compiled binaries pass all
+ *      21 of those tests, and tests/test_oracle_pinned.py asserts the same values
+ *      for the oracle.
+ * Tie-breaking among equal-cost optimal paths / equal-cost tree nodes / equal-cost
+ * assignments depends on Boost.Heap and Boost.Graph internals and is "parity
+ * unpinned": only costs (and, for cbs / ecbs, the expansion counts the stand-in
+ * heap happens to reproduce) are compared.
  */
 #ifndef MRP_ORACLE_H
 #define MRP_ORACLE_H
