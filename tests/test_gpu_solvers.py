@@ -518,7 +518,7 @@ def _ta_reference_cases(set8, set32, prefix):
     out = []
     for key, tool, inst, _, _ in T.selection(set8, set32):
         ref = g.get(key) if tool == "cbs_ta" and key.startswith(prefix) else None
-        if ref is None or (ref["solved"] and ref["highLevelExpanded"] > 300):
+        if ref is None or (ref["solved"] and ref["highLevelExpanded"] > 100):
             continue
         out.append((key, inst, ref))
     return out
