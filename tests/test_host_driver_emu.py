@@ -1,0 +1,152 @@
+"""CPU tests of the batched host drivers (libmultirobotplanning_b200/host/hl_search.hpp: the CBS /
+ECBS / CBS-TA / ECBS-TA loops, flights, sliced replans, pool rows, lanes) on a machine without a
+GPU.  The driver code under test is the product's libmrp_host.so, unchanged; what it calls is a
+host emulation of the C ABI built from tests/emu/mrp_emu.cpp on top of the CPU oracle, loaded only
+inside the subprocess started here (tests/emu/run_driver.py).  The answers are compared with the
+committed answers of the unmodified reference binaries (tests/golden/ref_binary_golden*.json) and
+with the reference's own fixtures; the switches that must not change a single answer (slices,
+pool, lanes) are flipped against each other.  The same comparisons run against the CUDA library
+in tests/test_gpu_solvers.py."""
+import json
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+EMU_SRC = os.path.join(ROOT, "tests", "emu", "mrp_emu.cpp")
+EMU_LIB = os.path.join(ROOT, "tests", "emu", "_build", "libmrp_b200.so")
+HOST_LIB = os.path.join(ROOT, "libmultirobotplanning_b200", "libmrp_host.so")
+CBS, ECBS, CBS_TA, ECBS_TA = 0, 1, 2, 3
+
+
+@pytest.fixture(scope="module")
+def emu():
+    if not os.path.exists(HOST_LIB):
+        pytest.fail("libmrp_host.so is missing: run __graft_entry__.build()")
+    srcs = [EMU_SRC, os.path.join(ROOT, "oracle", "mrp_oracle.cpp"), os.path.join(ROOT, "oracle", "mrp_oracle.h"),
+            os.path.join(ROOT, "include", "mrp_b200.h")]
+    if not os.path.exists(EMU_LIB) or any(os.path.getmtime(s) > os.path.getmtime(EMU_LIB) for s in srcs):
+        os.makedirs(os.path.dirname(EMU_LIB), exist_ok=True)
+        cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+        subprocess.run([cxx, "-O2", "-std=c++17", "-fPIC", "-shared", "-Wall", EMU_SRC,
+                        os.path.join(ROOT, "oracle", "mrp_oracle.cpp"), "-o", EMU_LIB,
+                        "-Wl,-soname,libmrp_b200.so"], check=True)
+
+    def run(runs):
+        p = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "emu", "run_driver.py")],
+                           input=json.dumps({"emu": EMU_LIB, "runs": runs}).encode(),
+                           stdout=subprocess.PIPE, timeout=900)
+        assert p.returncode == 0
+        return json.loads(p.stdout)
+    return run
+
+
+def _agents(name):
+    return int(re.search(r"agents(\d+)_", name).group(1))
+
+
+def _check_paths(inst, paths, mode):
+    from libmultirobotplanning_b200 import validate
+    assert validate.validate_paths(inst, [np.array(p) for p in paths], mode) is None
+
+
+def test_cbs_costs_and_switches(emu, set8, set32):
+    """CBS through the driver: optimal sums of costs equal the unmodified reference binary's
+    (cbs.hpp:85-172); slices on / tiny / off, pool off and one lane give the same answers."""
+    g = json.load(open(os.path.join(ROOT, "tests", "golden", "ref_binary_golden.json")))["cbs"]
+    n8 = [n for n in sorted(g) if "8by8" in n and _agents(n) >= 4 and g[n]["highLevelExpanded"] <= 400][:120]
+    n32 = [n for n in sorted(g) if "32by32" in n and g[n]["highLevelExpanded"] <= 60][:12]
+    base = {"algo": CBS, "max_hl": 20000}
+    runs = [dict(base, set="bench_8x8", names=n8),
+            dict(base, set="bench_8x8", names=n8, env={"MRP_HOST_SLICE": "5", "MRP_HOST_LANES": "1"}),
+            dict(base, set="bench_8x8", names=n8, env={"MRP_HOST_SLICE": "0"}),
+            dict(base, set="bench_8x8", names=n8, env={"MRP_HOST_POOL": "0", "MRP_HOST_LANES": "3"}),
+            dict(base, set="bench_32x32", names=n32)]
+    out = emu(runs)
+    ref = [r for r in out[0]["results"]]
+    for names, o in ((n8, out[0]), (n8, out[1]), (n8, out[2]), (n8, out[3]), (n32, out[4])):
+        for n, r in zip(names, o["results"]):
+            assert r["status"] == 0 and r["cost"] == g[n]["cost"], n
+    for o in out[1:4]:  # the switches change nothing: same trees, node for node
+        for a, b in zip(ref, o["results"]):
+            assert (a["cost"], a["makespan"], a["hl_expanded"], a["ll_expanded"]) == \
+                   (b["cost"], b["makespan"], b["hl_expanded"], b["ll_expanded"])
+            assert a["paths"] == b["paths"]
+    # what the driver used: default = pool rows + sliced launches; tiny slices suspend and resume
+    assert out[0]["counters"][4] > 0 and out[0]["counters"][0] == 0
+    assert out[1]["counters"][5] > 0 and out[1]["counters"][6] == out[1]["counters"][5]
+    assert out[2]["counters"][4] == 0 and out[2]["counters"][3] > 0
+    assert out[3]["counters"][2] > 0 and out[3]["counters"][1] == 0
+    by = {i.name: i for i in set8 + set32}
+    for n, r in list(zip(n8, out[1]["results"]))[::10] + list(zip(n32, out[4]["results"]))[::4]:
+        _check_paths(by[n], r["paths"], 0)
+
+
+def test_ecbs_bound_and_switches(emu, set32):
+    """ECBS w = 1.3 (ecbs.hpp:109-288): solved, valid, cost <= w * lower bound, optimum <= cost;
+    sliced roots / flights against the lock-step driver: identical answers."""
+    g = json.load(open(os.path.join(ROOT, "tests", "golden", "ref_binary_golden.json")))
+    names = sorted(g["ecbs_w1.3"])
+    base = {"algo": ECBS, "w": 1.3, "max_hl": 2000, "set": "bench_32x32", "names": names}
+    out = emu([base, dict(base, env={"MRP_HOST_SLICE": "16", "MRP_HOST_LANES": "2"}),
+               dict(base, env={"MRP_HOST_SLICE": "0"}), dict(base, env={"MRP_HOST_POOL": "0"})])
+    by = {i.name: i for i in set32}
+    for n, r in zip(names, out[0]["results"]):
+        assert r["status"] == 0, n
+        assert np.float32(r["cost"]) <= np.float32(r["lower_bound"]) * np.float32(1.3), n
+        if n in g["cbs"]:
+            assert g["cbs"][n]["cost"] <= r["cost"], n
+        assert r["cost"] <= 1.3 * g["ecbs_w1.3"][n]["cost"] + 1e-6, n  # both within w of one optimum
+        _check_paths(by[n], r["paths"], 0)
+    for o in out[1:]:
+        for a, b in zip(out[0]["results"], o["results"]):
+            assert (a["cost"], a["lower_bound"], a["hl_expanded"], a["ll_expanded"], a["paths"]) == \
+                   (b["cost"], b["lower_bound"], b["hl_expanded"], b["ll_expanded"], b["paths"])
+    assert out[1]["counters"][5] > 0
+
+
+def test_cbs_ta_and_ecbs_ta(emu, set8, set32):
+    """CBS-TA (cbs_ta.hpp:87-214) on config-C4 files and goal subsets: the optimal sums of costs and
+    the "no solution" answers of the unmodified reference cbs_ta; ECBS-TA at w = 1.0 on the
+    reference's fixtures (test/test_ecbs_ta.py:25-39) and within w on C4 files."""
+    g = json.load(open(os.path.join(ROOT, "tests", "golden", "ref_binary_golden_ta.json")))["cbs_ta"]
+    keys = [k for k in sorted(g) if not g[k]["solved"] or g[k]["highLevelExpanded"] <= 40]
+    keys = [k for k in keys if "8by8" in k][::4] + [k for k in keys if "32by32" in k][::12]
+    keys8 = [k for k in keys if "8by8" in k]
+    keys32 = [k for k in keys if "32by32" in k]
+    fx = json.load(open(os.path.join(ROOT, "tests", "golden", "ref_fixtures.json")))
+    fnames = [n for n in sorted(fx) if "cbs_ta_cost" in fx[n]["expected"]]
+    out = emu([{"algo": CBS_TA, "ta": keys8, "max_hl": 20000}, {"algo": CBS_TA, "ta": keys32, "max_hl": 20000},
+               {"algo": ECBS_TA, "fixtures": fnames, "w": 1.0, "max_hl": 5000},
+               {"algo": CBS_TA, "fixtures": fnames, "max_hl": 5000},
+               {"algo": ECBS_TA, "ta": [k for k in keys32 if g[k]["solved"]][:6], "w": 1.3, "max_hl": 5000}])
+    unsolved = 0
+    for ks, o in ((keys8, out[0]), (keys32, out[1])):
+        # the runner returns the instances in the generator's order, not in the order of `ks`
+        order = [k for k in _ta_order(set8, set32) if k in set(ks)]
+        for k, r in zip(order, o["results"]):
+            if g[k]["solved"]:
+                assert r["status"] == 0 and r["cost"] == g[k]["cost"], k
+            else:
+                assert r["status"] == 1, k
+                unsolved += 1
+    assert unsolved >= 1 and len(keys8) >= 40 and len(keys32) >= 15
+    for o in out[2:4]:
+        for n, r in zip(fnames, o["results"]):
+            assert r["status"] == 0 and r["cost"] == fx[n]["expected"]["cbs_ta_cost"], n
+    order = [k for k in _ta_order(set8, set32) if k in set([k for k in keys32 if g[k]["solved"]][:6])]
+    for k, r in zip(order, out[4]["results"]):
+        assert r["status"] == 0 and g[k]["cost"] <= r["cost"] <= 1.3 * g[k]["cost"] + 1e-6, k
+
+
+def _ta_order(set8, set32):
+    """keys of the cbs_ta golden in the order the generator (and the runner) lists the instances"""
+    gdir = os.path.join(ROOT, "tests", "golden")
+    if gdir not in sys.path:
+        sys.path.insert(0, gdir)
+    import make_ref_golden_ta as T
+    return [j[0] for j in T.selection(set8, set32) if j[1] == "cbs_ta"]
