@@ -150,3 +150,105 @@ def _ta_order(set8, set32):
         sys.path.insert(0, gdir)
     import make_ref_golden_ta as T
     return [j[0] for j in T.selection(set8, set32) if j[1] == "cbs_ta"]
+
+
+def _emu_env():
+    env = dict(os.environ)
+    env["LD_LIBRARY_PATH"] = os.path.dirname(EMU_LIB) + os.pathsep + env.get("LD_LIBRARY_PATH", "")
+    return env
+
+
+def test_cli_binaries_on_the_emulation(emu, ref_fixtures, set8, tmp_path):
+    """bin/cbs, ecbs, cbs_ta, ecbs_ta (the drop-in command lines) with the emulation in front of
+    their library path: the reference's pinned answers, the layout of output.yaml
+    (example/cbs.cpp:637-661), "Planning NOT successful!" without an output file, option errors
+    -> usage on stderr and exit status 1 (example/cbs.cpp:585-596); bin/mapf_sweep over 40 files."""
+    import yaml
+    from libmultirobotplanning_b200 import instances as I
+    BIN = os.path.join(ROOT, "bin")
+    env = _emu_env()
+    for name, tool, extra, key in (("mapf_simple1", "cbs", [], "cbs_cost"),
+                                   ("mapf_circle", "cbs", [], "cbs_cost"),
+                                   ("mapf_atGoal", "ecbs", ["-w", "1.0"], "ecbs_w1_cost"),
+                                   ("mapf_simple1", "ecbs", ["--suboptimality=1.0"], "ecbs_w1_cost"),
+                                   ("mapfta_simple1_a2", "cbs_ta", [], "cbs_ta_cost"),
+                                   ("mapfta_simple1_a3", "cbs_ta", ["--maxTaskAssignments", "5"], "cbs_ta_cost"),
+                                   ("mapfta_simple1_a2", "ecbs_ta", ["-w", "1.0"], "cbs_ta_cost"),
+                                   ("mapfta_simple1_a1", "ecbs_ta", [], "cbs_ta_cost")):
+        d = ref_fixtures[name]
+        inst = I.Instance(name, d["dimx"], d["dimy"], np.array(d["obstacles"], np.int32).reshape(-1, 2),
+                          np.array(d["starts"], np.int32).reshape(-1, 2),
+                          np.array(d["goals"], np.int32).reshape(-1, 2) if "goals" in d else None,
+                          [np.array(p, np.int32).reshape(-1, 2) for p in d["potentialGoals"]]
+                          if "potentialGoals" in d else None)
+        inp, out = str(tmp_path / "in.yaml"), str(tmp_path / "out.yaml")
+        if os.path.exists(out):
+            os.remove(out)
+        I.save_yaml(inst, inp)
+        r = subprocess.run([os.path.join(BIN, tool), "-i", inp, "-o", out] + extra, capture_output=True,
+                           text=True, env=env)
+        assert r.returncode == 0, r.stderr
+        assert "Planning successful!" in r.stdout and "done; cost:" in r.stdout
+        text = open(out).read()
+        y = yaml.safe_load(text)
+        assert y["statistics"]["cost"] == d["expected"][key], (name, tool)
+        assert list(y["statistics"].keys())[:5] == ["cost", "makespan", "runtime", "highLevelExpanded",
+                                                    "lowLevelExpanded"]
+        assert ("numTaskAssignments" in y["statistics"]) == (tool in ("cbs_ta", "ecbs_ta"))
+        assert re.search(r"^schedule:\n  agent0:\n    - x: \d+\n      y: \d+\n      t: 0\n", text, re.M)
+        if "agent0_last" in d["expected"]:
+            assert y["schedule"]["agent0"][-1] == d["expected"]["agent0_last"]
+    # an agent walled in: no solution, no output file, exit status 0 like the reference
+    boxed = I.Instance("boxed", 3, 3, np.array([[1, 0], [0, 1], [1, 1]], np.int32), np.array([[0, 0]], np.int32),
+                       np.array([[2, 2]], np.int32))
+    inp, out = str(tmp_path / "boxed.yaml"), str(tmp_path / "boxed_out.yaml")
+    I.save_yaml(boxed, inp)
+    r = subprocess.run([os.path.join(BIN, "cbs"), "-i", inp, "-o", out], capture_output=True, text=True, env=env)
+    assert r.returncode == 0 and "Planning NOT successful!" in r.stdout and not os.path.exists(out)
+    r = subprocess.run([os.path.join(BIN, "cbs"), "-o", out], capture_output=True, text=True, env=env)
+    assert r.returncode == 1 and "Allowed options" in r.stderr and "--input" in r.stderr
+    r = subprocess.run([os.path.join(BIN, "ecbs"), "--help"], capture_output=True, text=True, env=env)
+    assert r.returncode == 0 and "suboptimality" in r.stdout
+    # the streaming sweep: same costs as the reference binary's golden
+    g = json.load(open(os.path.join(ROOT, "tests", "golden", "ref_binary_golden.json")))["cbs"]
+    insts = [i for i in set8 if i.name in g and g[i.name]["highLevelExpanded"] <= 200][:40]
+    files = []
+    for i in insts:
+        p = str(tmp_path / (i.name + ".yaml"))
+        I.save_yaml(i, p)
+        files.append(p)
+    (tmp_path / "files.txt").write_text("\n".join(files) + "\n")
+    (tmp_path / "out").mkdir()
+    r = subprocess.run([os.path.join(BIN, "mapf_sweep"), "--algo", "cbs", "--batch", "16", "--maxHighLevelExpansions",
+                        "5000", "--outputDir", str(tmp_path / "out"), "--csv", str(tmp_path / "res.csv"), "--list",
+                        str(tmp_path / "files.txt")], capture_output=True, text=True, timeout=600, env=env)
+    assert r.returncode == 0, r.stderr[-500:]
+    rows = [l.split(",") for l in (tmp_path / "res.csv").read_text().strip().splitlines()[1:]]
+    assert [row[0] for row in rows] == files
+    for row, i in zip(rows, insts):
+        assert int(row[1]) == 0 and int(row[2]) == g[i.name]["cost"], i.name
+        y = yaml.safe_load((tmp_path / "out" / (i.name + ".output.yaml")).read_text())
+        assert y["statistics"]["cost"] == g[i.name]["cost"]
+
+
+def test_reference_test_suite_on_our_binaries(emu, tmp_path):
+    """Where /root/reference exists (the build container): the reference's OWN python tests
+    (test/test_cbs.py, test_ecbs.py, test_cbs_ta.py, test_ecbs_ta.py: `./cbs -i ../test/... -o
+    output.yaml`, 12 tests) run unmodified against THIS repository's command lines — the drop-in
+    claim, checked by the reference's checker.  (PyYAML 6 needs an explicit Loader; the tests
+    call yaml.load(f), so the launcher passes SafeLoader as its default.)"""
+    ref = "/root/reference/test"
+    if not os.path.isdir(ref):
+        pytest.skip("the reference tree is not on this machine")
+    build = tmp_path / "build"
+    build.mkdir()
+    os.symlink(ref, str(tmp_path / "test"))
+    for b in ("cbs", "ecbs", "cbs_ta", "ecbs_ta"):
+        os.symlink(os.path.join(ROOT, "bin", b), str(build / b))
+    launcher = ("import yaml, functools, unittest\n"
+                "yaml.load = functools.partial(yaml.load, Loader=yaml.SafeLoader)\n"
+                "unittest.main(module=None, argv=['x', 'discover', '-s', '../test', '-p', 'test_*cbs*.py'])\n")
+    r = subprocess.run([sys.executable, "-c", launcher], cwd=str(build), env=_emu_env(), capture_output=True,
+                       text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert re.search(r"Ran 12 tests", r.stderr) and "OK" in r.stderr
