@@ -252,3 +252,36 @@ def test_reference_test_suite_on_our_binaries(emu, tmp_path):
                        text=True, timeout=600)
     assert r.returncode == 0, r.stderr[-2000:]
     assert re.search(r"Ran 12 tests", r.stderr) and "OK" in r.stderr
+
+
+def test_reference_templates_with_our_environment_on_the_emulation(emu, ref_fixtures, tmp_path):
+    """oracle/_ref/templates_gpuenv — the reference's UNMODIFIED CBS / ECBS / CBSTA templates
+    (include/libMultiRobotPlanning/cbs.hpp, ecbs.hpp, cbs_ta.hpp) instantiated with this
+    repository's Environment adapter (host/gpu_environment.hpp) — with the emulation behind the
+    adapter: the reference's own loops reach its pinned answers through our callbacks.  (The GPU
+    run of the same binary is tests/test_gpu_solvers.py::test_reference_templates_drive_gpu_environment.)"""
+    from libmultirobotplanning_b200 import instances as I
+    exe = os.path.join(ROOT, "oracle", "_ref", "templates_gpuenv")
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref not built (needs /root/reference)")
+    n = 0
+    for name, d in ref_fixtures.items():
+        exp = d["expected"]
+        inst = I.Instance(name, d["dimx"], d["dimy"], np.array(d["obstacles"], np.int32).reshape(-1, 2),
+                          np.array(d["starts"], np.int32).reshape(-1, 2),
+                          np.array(d["goals"], np.int32).reshape(-1, 2) if "goals" in d else None,
+                          [np.array(p, np.int32).reshape(-1, 2) for p in d["potentialGoals"]]
+                          if "potentialGoals" in d else None)
+        inp = str(tmp_path / (name + ".yaml"))
+        I.save_yaml(inst, inp)
+        runs = []
+        if "cbs_cost" in exp:
+            runs = [("cbs", [], exp["cbs_cost"]), ("ecbs", ["1.0"], exp["ecbs_w1_cost"])]
+        if "cbs_ta_cost" in exp:
+            runs = [("cbs_ta", [], exp["cbs_ta_cost"])]
+        for algo, extra, want in runs:
+            r = subprocess.run([exe, algo, inp] + extra, capture_output=True, text=True, env=_emu_env())
+            assert r.returncode == 0, (name, algo, r.stderr[-300:])
+            assert ("cost %d" % want) in r.stdout, (name, algo, r.stdout[-200:])
+            n += 1
+    assert n >= 9
