@@ -241,20 +241,33 @@ class BatchSolver {
   }
 
  private:
-  struct ConsList {
-    std::vector<int32_t> vc;  // (time, cell) pairs
-    std::vector<int32_t> ec;  // (time, from, to) triples
+  // A constraint-tree node does not own its paths or constraints (the reference deep-copies the
+  // whole node for every child, cbs.hpp:144,175-181; sharing is invisible in the results):
+  //  * a path is a PathRef: cost, fmin, length and either a row of the device pool (cbs / ecbs:
+  //    the cells never come to the host) or a shared host copy (cbs_ta / ecbs_ta, large maps).
+  //    Pool rows belong to the INSTANCE, not to the node: they are handed back in one piece when
+  //    the instance finishes, so copying a node is a flat copy without reference counts;
+  //  * the constraints of an agent are a parent-pointer chain in the instance's arena
+  //    (Inst::consArena): a node keeps the index of the newest entry per agent, a child adds one
+  //    entry whose `prev` is its parent's index (cbs.hpp:146-153 adds the new constraint to a
+  //    copy of the whole set);
+  //  * the task vector is shared by every node below one root.
+  struct PathRef {
+    std::shared_ptr<const AgentPath> host;  // cells / g-scores on the host (not in pool mode)
+    int32_t slot = -1, length = 0, cost = 0, fmin = 0;
+    bool set = false;  // false: this agent has no path yet (roots under construction)
+    explicit operator bool() const { return set; }
   };
-  // Children share every path / constraint list they do not change (the
-  // reference deep-copies the whole node, cbs.hpp:144; sharing is invisible in
-  // the results and removes the O(N*T) copy per child).
-  typedef std::shared_ptr<const AgentPath> PathPtr;
-  typedef std::shared_ptr<const ConsList> ConsPtr;
+  struct ConsEntry {
+    int32_t time, a, b;  // b < 0: vertex constraint (time, cell a); else edge (time, from a, to b)
+    int32_t prev;        // older constraint of the same agent on the way to the root, -1: none
+  };
+  typedef std::shared_ptr<const std::vector<int> > TaskPtr;
   struct Node {
     int inst = 0;
-    std::vector<PathPtr> paths;
-    std::vector<ConsPtr> cons;
-    std::vector<int> task;  // goal cell per agent (-1: none)
+    std::vector<PathRef> paths;
+    std::vector<int32_t> cons;  // per agent: newest entry of its chain in Inst::consArena, -1: none
+    TaskPtr task;               // goal cell per agent (-1: none)
     long cost = 0, LB = 0;
     int focal = 0;
     int id = 0;
@@ -290,7 +303,10 @@ class BatchSolver {
     std::unique_ptr<NextBestAssignment<int, int> > assignment;
     long nextRootNodeCost = 0;  // ecbs_ta (STYLE_MINROOT, ecbs_ta.hpp:142,345)
     SolveResult res;
-    std::vector<PathPtr> solution;  // pool mode: the rows of the solution until they are fetched
+    std::vector<PathRef> solution;  // pool mode: the rows of the solution until they are fetched
+    std::vector<ConsEntry> consArena;  // constraint chains of all nodes of this instance
+    std::vector<int32_t> rows;         // pool rows this instance holds (returned when it is done)
+    bool rowsQueued = false;
   };
   struct Pending {
     int inst = 0;
@@ -298,13 +314,13 @@ class BatchSolver {
   };
   struct JobSpec {
     int inst, agent, goal, field;
-    const ConsList* cons;
+    int cons;  // newest entry of the agent's constraint chain (Inst::consArena), -1: none
     int table, self;
   };
   struct JobOut {
     int status = 1;
     long expanded = 0;
-    PathPtr path;  // set iff status == 0
+    PathRef path;  // set iff status == 0
   };
 
   // Pools outlive their batch: creating one costs a dozen device allocations (tens of
@@ -362,35 +378,95 @@ class BatchSolver {
     std::lock_guard<std::mutex> lk(m_rowMutex);
     m_freeRows.push_back(row);
   }
-  // a path that owns a pool row gives it back when the last node drops it
-  PathPtr adopt(AgentPath&& p) {
-    if (p.slot < 0) return std::make_shared<const AgentPath>(std::move(p));
-    return PathPtr(new AgentPath(std::move(p)), [this](const AgentPath* q) {
-      giveRow(q->slot);
-      delete q;
-    });
+  // A finished replan becomes a PathRef.  In pool mode its row joins the rows of its instance
+  // (main thread only: the launches are absorbed there) and stays until the instance is done.
+  PathRef adopt(AgentPath&& p, int inst) {
+    PathRef r;
+    r.slot = p.slot;
+    r.length = p.length;
+    r.cost = p.cost;
+    r.fmin = p.fmin;
+    r.set = true;
+    if (p.slot < 0)
+      r.host = std::make_shared<const AgentPath>(std::move(p));
+    else
+      m_inst[inst].rows.push_back(p.slot);
+    return r;
+  }
+  // the rows of the instances that finished go back to the free list (main thread, after their
+  // solutions were read: fetchSolutions)
+  void releaseFinished() {
+    std::vector<int> done;
+    {
+      std::lock_guard<std::mutex> lk(m_rowMutex);
+      done.swap(m_doneQueue);
+    }
+    for (int k : done) {
+      Inst& I = m_inst[k];
+      {
+        std::lock_guard<std::mutex> lk(m_rowMutex);
+        m_freeRows.insert(m_freeRows.end(), I.rows.begin(), I.rows.end());
+      }
+      std::vector<int32_t>().swap(I.rows);
+      std::vector<ConsEntry>().swap(I.consArena);
+    }
+  }
+  // the constraints of one chain, oldest first, appended to the (time, cell) pairs / (time, from,
+  // to) triples of a launch
+  void appendCons(const Inst& I, int head, std::vector<int32_t>& vc, std::vector<int32_t>& ec) const {
+    const size_t v0 = vc.size(), e0 = ec.size();
+    for (int k = head; k >= 0; k = I.consArena[k].prev) {
+      const ConsEntry& c = I.consArena[k];
+      if (c.b < 0) {  // pushed back to front, reversed below
+        vc.push_back(c.a);
+        vc.push_back(c.time);
+      } else {
+        ec.push_back(c.b);
+        ec.push_back(c.a);
+        ec.push_back(c.time);
+      }
+    }
+    std::reverse(vc.begin() + v0, vc.end());
+    std::reverse(ec.begin() + e0, ec.end());
+  }
+  // createConstraintsFromConflict (example/cbs.cpp:388-406) for one side of a conflict: the new
+  // entry of `agent`'s chain below node P
+  int addConstraint(Inst& I, const Node& P, const mrp_conflict& c, int side, int agent) const {
+    const int c1 = c.x1 + m_dimx * c.y1;
+    const int c2 = c.type == 1 ? c.x2 + m_dimx * c.y2 : -1;
+    ConsEntry e;
+    e.time = c.time;
+    if (c.type == 0) {
+      e.a = c1;
+      e.b = -1;
+    } else {
+      e.a = side == 0 ? c1 : c2;
+      e.b = side == 0 ? c2 : c1;
+    }
+    e.prev = P.cons[agent];
+    I.consArena.push_back(e);
+    return (int)I.consArena.size() - 1;
   }
   // pool mode: the paths of the instances that finished since the last call come to
   // the host (one read for all of them; main thread only)
   void fetchSolutions() {
     if (!m_pool) return;
     std::vector<int32_t> rows;
-    std::vector<size_t> owner;
     for (size_t k = 0; k < m_inst.size(); ++k)
-      for (const PathPtr& p : m_inst[k].solution) {
-        rows.push_back(p->slot);
-        owner.push_back(k);
-      }
-    if (rows.empty()) return;
+      for (const PathRef& p : m_inst[k].solution) rows.push_back(p.slot);
+    if (rows.empty()) {
+      releaseFinished();
+      return;
+    }
     std::vector<int32_t> cells(rows.size() * (size_t)m_pathCap), len(rows.size());
     gpuCheck(mrp_pathpool_read(m_pool, rows.data(), (int)rows.size(), cells.data(), len.data()));
     size_t r = 0;
     for (size_t k = 0; k < m_inst.size(); ++k) {
       Inst& I = m_inst[k];
-      for (const PathPtr& p : I.solution) {
+      for (const PathRef& p : I.solution) {
         AgentPath out;
-        out.cost = p->cost;
-        out.fmin = p->fmin;
+        out.cost = p.cost;
+        out.fmin = p.fmin;
         out.length = len[r];
         out.cells.assign(cells.begin() + r * m_pathCap, cells.begin() + r * m_pathCap + len[r]);
         out.g.resize(len[r]);
@@ -400,6 +476,7 @@ class BatchSolver {
       }
       I.solution.clear();
     }
+    releaseFinished();
   }
 
   // ---------------------------------------------------------------------
@@ -459,15 +536,16 @@ class BatchSolver {
   }
 
   // nextTaskAssignment, example/cbs_ta.cpp:442-456
-  bool nextTasks(Inst& I, std::vector<int>& task) {
-    task.assign(I.in->numAgents(), -1);
+  bool nextTasks(Inst& I, TaskPtr& out) {
+    std::shared_ptr<std::vector<int> > task = std::make_shared<std::vector<int> >(I.in->numAgents(), -1);
+    out = task;
     if ((unsigned long)I.res.numTaskAssignments > (unsigned long)m_opt.maxTaskAssignments)
       return false;
     std::map<int, int> sol;
     I.assignment->nextSolution(sol);
     if (sol.empty()) return false;
     ++I.res.numTaskAssignments;
-    for (const auto& e : sol) task[e.first] = e.second;
+    for (const auto& e : sol) (*task)[e.first] = e.second;
     return true;
   }
 
@@ -482,18 +560,23 @@ class BatchSolver {
     I.res.status = status;
     I.res.runtime = t;
     if (n) {
-      for (const auto& p : n->paths) {  // example/cbs.cpp:630-635
-        if (p->slot >= 0)
+      for (const PathRef& p : n->paths) {  // example/cbs.cpp:630-635
+        if (p.slot >= 0)
           I.solution.push_back(p);  // cells follow in fetchSolutions()
         else
-          I.res.paths.push_back(*p);
-        I.res.cost += p->cost;
-        I.res.makespan = std::max<long>(I.res.makespan, p->cost);
-        I.res.lowerBound += p->fmin;
+          I.res.paths.push_back(*p.host);
+        I.res.cost += p.cost;
+        I.res.makespan = std::max<long>(I.res.makespan, p.cost);
+        I.res.lowerBound += p.fmin;
       }
     }
     for (Node* o : I.open) delete o;
     I.open.clear();
+    if (m_pool && !I.rowsQueued) {  // its rows go back once the solution has been read
+      I.rowsQueued = true;
+      std::lock_guard<std::mutex> lk(m_rowMutex);
+      m_doneQueue.push_back((int)(&I - m_inst.data()));
+    }
   }
 
   // pushes the evaluated nodes into the OPEN lists of their instances; `fresh`
@@ -580,10 +663,9 @@ class BatchSolver {
       j.goal_cell = s.goal;
       j.field = s.field;
       j.vc_begin = (int)vc.size() / 2;
-      if (s.cons) vc.insert(vc.end(), s.cons->vc.begin(), s.cons->vc.end());
-      j.vc_end = (int)vc.size() / 2;
       j.ec_begin = (int)ec.size() / 3;
-      if (s.cons) ec.insert(ec.end(), s.cons->ec.begin(), s.cons->ec.end());
+      appendCons(m_inst[s.inst], s.cons, vc, ec);
+      j.vc_end = (int)vc.size() / 2;
       j.ec_end = (int)ec.size() / 3;
       j.table = s.table;
       j.self = s.self;
@@ -622,7 +704,7 @@ class BatchSolver {
           ap.fmin = info[k].fmin;
           ap.slot = outRows[k];
           ap.length = info[k].length;
-          o.path = adopt(std::move(ap));
+          o.path = adopt(std::move(ap), specs[k].inst);
         } else {
           giveRow(outRows[k]);
         }
@@ -667,7 +749,7 @@ class BatchSolver {
         ap.cost = info[k].cost;
         ap.fmin = info[k].fmin;
         ap.length = L;
-        o.path = adopt(std::move(ap));
+        o.path = adopt(std::move(ap), specs[k].inst);
       }
     }
     prof.llUnpack += nowSeconds() - tUn;
@@ -685,10 +767,10 @@ class BatchSolver {
 #pragma omp parallel for schedule(static) if (nodes.size() >= kParallelMin)
     for (long b = 0; b < (long)nodes.size(); ++b)
       for (size_t a = 0; a < nodes[b]->paths.size(); ++a) {
-        const PathPtr& p = nodes[b]->paths[a];
+        const PathRef& p = nodes[b]->paths[a];
         if (!p) continue;
-        rows[b * N + a] = p->slot;
-        tmax[b] = std::max(tmax[b], p->length);
+        rows[b * N + a] = p.slot;
+        tmax[b] = std::max(tmax[b], p.length);
       }
     for (int t : tmax) Tpad = std::max(Tpad, t);
   }
@@ -699,8 +781,8 @@ class BatchSolver {
     Tpad = 1;
     for (const Node* n : nodes) {
       N = std::max(N, (int)n->paths.size());
-      for (const auto& p : n->paths)
-        if (p) Tpad = std::max(Tpad, (int)p->cells.size());
+      for (const PathRef& p : n->paths)
+        if (p) Tpad = std::max(Tpad, (int)p.host->cells.size());
     }
     // cells past a path's length are never read (the kernels clamp to len-1),
     // so the tables are not cleared: only the lengths are
@@ -710,7 +792,7 @@ class BatchSolver {
     for (long b = 0; b < (long)nodes.size(); ++b)
       for (size_t a = 0; a < nodes[b]->paths.size(); ++a) {
         if (!nodes[b]->paths[a]) continue;  // not planned yet (ECBS root construction)
-        const auto& c = nodes[b]->paths[a]->cells;
+        const auto& c = nodes[b]->paths[a].host->cells;
         std::copy(c.begin(), c.end(), tables.begin() + (b * N + a) * (size_t)Tpad);
         tlen[b * N + a] = (int)c.size();
       }
@@ -775,7 +857,7 @@ class BatchSolver {
       std::unique_ptr<Node> n(new Node());
       n->inst = (int)k;
       n->paths.resize(I.in->numAgents());
-      n->cons.assign(I.in->numAgents(), m_noCons);
+      n->cons.assign(I.in->numAgents(), -1);
       n->id = I.nextId++;
       n->isRoot = true;
       if (m_algo == Algo::CBSTA) {
@@ -786,7 +868,7 @@ class BatchSolver {
       } else if (m_algo == Algo::ECBSTA) {
         nextTasks(I, n->task);  // ecbs_ta.hpp:104 plans even without an assignment
       } else {
-        n->task.assign(I.in->goals.begin(), I.in->goals.end());
+        n->task = std::make_shared<const std::vector<int> >(I.in->goals.begin(), I.in->goals.end());
       }
       roots[k] = std::move(n);
     }
@@ -818,9 +900,9 @@ class BatchSolver {
       for (size_t k = 0; k < m_inst.size(); ++k) {
         if (!roots[k]) continue;
         for (size_t a = 0; a < m_inst[k].in->numAgents(); ++a) {
-          const int goal = roots[k]->task[a];
+          const int goal = (*roots[k]->task)[a];
           specs.push_back({(int)k, (int)a, goal, fieldFor(m_inst[k], (int)a, goal),
-                           roots[k]->cons[a].get(), -1, (int)a});
+                           roots[k]->cons[a], -1, (int)a});
         }
       }
       std::vector<JobOut> outs;
@@ -845,9 +927,9 @@ class BatchSolver {
       std::vector<const Node*> tabs;
       for (size_t k = 0; k < nodes.size(); ++k) {
         if (!nodes[k] || a >= m_inst[k].in->numAgents()) continue;
-        const int goal = nodes[k]->task[a];
+        const int goal = (*nodes[k]->task)[a];
         specs.push_back({(int)k, (int)a, goal, fieldFor(m_inst[k], (int)a, goal),
-                         nodes[k]->cons[a].get(), (int)tabs.size(), (int)a});
+                         nodes[k]->cons[a], (int)tabs.size(), (int)a});
         tabs.push_back(nodes[k].get());
       }
       std::vector<JobOut> outs;
@@ -866,8 +948,8 @@ class BatchSolver {
       return;
     }
     Node& n = *roots[s.inst];
-    n.cost += o.path->cost;
-    n.LB += o.path->fmin;
+    n.cost += o.path.cost;
+    n.LB += o.path.fmin;
     n.paths[s.agent] = std::move(o.path);
   }
 
@@ -887,7 +969,7 @@ class BatchSolver {
       if (!nextTasks(I, r->task)) continue;
       r->inst = (int)k;
       r->paths.resize(I.in->numAgents());
-      r->cons.assign(I.in->numAgents(), m_noCons);
+      r->cons.assign(I.in->numAgents(), -1);
       r->isRoot = true;
       roots[k] = std::move(r);
       any = true;
@@ -936,7 +1018,7 @@ class BatchSolver {
     if ((size_t)f.nextAgent >= I.in->numAgents()) return false;
     const int a = f.nextAgent;
     FlightJob j;
-    j.spec = {f.pd.inst, a, f.root->task[a], fieldFor(I, a, f.root->task[a]), f.root->cons[a].get(), -1, a};
+    j.spec = {f.pd.inst, a, (*f.root->task)[a], fieldFor(I, a, (*f.root->task)[a]), f.root->cons[a], -1, a};
     f.jobs.clear();
     f.jobs.push_back(std::move(j));
     return true;
@@ -955,7 +1037,7 @@ class BatchSolver {
   void dropFlight(Flight& f) {
     for (FlightJob& j : f.jobs) {
       if (j.state >= 0) m_freeStates.push_back(j.state);
-      if (j.outRow >= 0 && !j.out.path) giveRow(j.outRow);
+      if (j.outRow >= 0 && !j.out.path) giveRow(j.outRow);  // (an adopted row belongs to the instance)
       j.state = j.outRow = -1;
     }
     m_inst[f.pd.inst].busy = false;
@@ -972,26 +1054,15 @@ class BatchSolver {
       Inst& I = m_inst[pending[pi].inst];
       const Node& P = *pending[pi].parent;
       const mrp_conflict& c = P.conflict;
-      const int c1 = c.x1 + m_dimx * c.y1;
-      const int c2 = c.type == 1 ? c.x2 + m_dimx * c.y2 : -1;
       for (int side = 0; side < 2; ++side) {
         const int agent = side == 0 ? c.agent1 : c.agent2;
-        std::unique_ptr<Node> n(new Node(P));  // shares paths / constraint lists
-        std::shared_ptr<ConsList> cl = std::make_shared<ConsList>(*P.cons[agent]);
-        if (c.type == 0) {
-          cl->vc.push_back(c.time);
-          cl->vc.push_back(c1);
-        } else {
-          cl->ec.push_back(c.time);
-          cl->ec.push_back(side == 0 ? c1 : c2);
-          cl->ec.push_back(side == 0 ? c2 : c1);
-        }
-        n->cons[agent] = cl;
-        n->cost -= n->paths[agent]->cost;
-        n->LB -= n->paths[agent]->fmin;
+        std::unique_ptr<Node> n(new Node(P));  // a flat copy: rows and chain heads
+        n->cons[agent] = addConstraint(I, P, c, side, agent);
+        n->cost -= n->paths[agent].cost;
+        n->LB -= n->paths[agent].fmin;
         FlightJob j;
-        j.spec = {pending[pi].inst, agent, n->task[agent], fieldFor(I, agent, n->task[agent]),
-                  n->cons[agent].get(), -1, agent};
+        j.spec = {pending[pi].inst, agent, (*n->task)[agent], fieldFor(I, agent, (*n->task)[agent]),
+                  n->cons[agent], -1, agent};
         f->jobs.push_back(std::move(j));
         FlightChild k;
         k.agent = agent;
@@ -1040,10 +1111,9 @@ class BatchSolver {
         mj.goal_cell = sp.goal;
         mj.field = sp.field;
         mj.vc_begin = (int)vc.size() / 2;
-        vc.insert(vc.end(), sp.cons->vc.begin(), sp.cons->vc.end());
-        mj.vc_end = (int)vc.size() / 2;
         mj.ec_begin = (int)ec.size() / 3;
-        ec.insert(ec.end(), sp.cons->ec.begin(), sp.cons->ec.end());
+        appendCons(m_inst[sp.inst], sp.cons, vc, ec);
+        mj.vc_end = (int)vc.size() / 2;
         mj.ec_end = (int)ec.size() / 3;
         mj.table = table;
         mj.self = sp.self;
@@ -1096,7 +1166,7 @@ class BatchSolver {
         ap.fmin = info[k].fmin;
         ap.slot = j.outRow;
         ap.length = info[k].length;
-        j.out.path = adopt(std::move(ap));
+        j.out.path = adopt(std::move(ap), j.spec.inst);
       } else {
         giveRow(j.outRow);
       }
@@ -1132,8 +1202,8 @@ class BatchSolver {
           m_flights[i].reset();
           continue;
         }
-        f.root->cost += j.out.path->cost;
-        f.root->LB += j.out.path->fmin;
+        f.root->cost += j.out.path.cost;
+        f.root->LB += j.out.path.fmin;
         f.root->paths[f.nextAgent] = std::move(j.out.path);
         ++f.nextAgent;
         if (nextRootJob(f)) {  // the next agent of this root
@@ -1157,8 +1227,8 @@ class BatchSolver {
         FlightJob& j = f.jobs[q];
         if (j.out.status != 0) continue;  // no path under these constraints: the child is dropped
         Node& n = *f.kids[q].node;
-        n.cost += j.out.path->cost;
-        n.LB += j.out.path->fmin;
+        n.cost += j.out.path.cost;
+        n.LB += j.out.path.fmin;
         n.paths[f.kids[q].agent] = std::move(j.out.path);
         n.id = I.nextId++;
         made[i][q] = f.kids[q].node.release();
@@ -1209,7 +1279,7 @@ class BatchSolver {
         if (nextTasks(I, r->task)) {
           r->inst = pending[pi].inst;
           r->paths.resize(I.in->numAgents());
-          r->cons.assign(I.in->numAgents(), m_noCons);
+          r->cons.assign(I.in->numAgents(), -1);
           r->isRoot = true;
           ChildPlan cp;
           cp.pendingIdx = (int)pi;
@@ -1217,8 +1287,8 @@ class BatchSolver {
           cp.firstJob = specs.size();
           cp.nJobs = I.in->numAgents();
           for (size_t a = 0; a < I.in->numAgents(); ++a)
-            specs.push_back({pending[pi].inst, (int)a, r->task[a],
-                             fieldFor(I, (int)a, r->task[a]), r->cons[a].get(), -1, (int)a});
+            specs.push_back({pending[pi].inst, (int)a, (*r->task)[a],
+                             fieldFor(I, (int)a, (*r->task)[a]), r->cons[a], -1, (int)a});
           cp.node = std::move(r);
           plans.push_back(std::move(cp));
         }
@@ -1226,31 +1296,20 @@ class BatchSolver {
       // createConstraintsFromConflict, example/cbs.cpp:388-406: children in
       // ascending agent order (agent1 < agent2)
       const mrp_conflict& c = P.conflict;
-      const int c1 = c.x1 + m_dimx * c.y1;
-      const int c2 = c.type == 1 ? c.x2 + m_dimx * c.y2 : -1;
       for (int side = 0; side < 2; ++side) {
         const int agent = side == 0 ? c.agent1 : c.agent2;
-        std::unique_ptr<Node> n(new Node(P));  // shares paths / constraint lists
+        std::unique_ptr<Node> n(new Node(P));  // a flat copy: path references and chain heads
         n->isRoot = P.isRoot;
-        std::shared_ptr<ConsList> cl = std::make_shared<ConsList>(*P.cons[agent]);
-        if (c.type == 0) {
-          cl->vc.push_back(c.time);
-          cl->vc.push_back(c1);
-        } else {
-          cl->ec.push_back(c.time);
-          cl->ec.push_back(side == 0 ? c1 : c2);
-          cl->ec.push_back(side == 0 ? c2 : c1);
-        }
-        n->cons[agent] = cl;
-        n->cost -= n->paths[agent]->cost;
-        n->LB -= n->paths[agent]->fmin;
+        n->cons[agent] = addConstraint(I, P, c, side, agent);
+        n->cost -= n->paths[agent].cost;
+        n->LB -= n->paths[agent].fmin;
         ChildPlan cp;
         cp.pendingIdx = (int)pi;
         cp.agent = agent;
         cp.firstJob = specs.size();
         cp.nJobs = 1;
-        specs.push_back({pending[pi].inst, agent, n->task[agent],
-                         fieldFor(I, agent, n->task[agent]), n->cons[agent].get(), tableIdx, agent});
+        specs.push_back({pending[pi].inst, agent, (*n->task)[agent],
+                         fieldFor(I, agent, (*n->task)[agent]), n->cons[agent], tableIdx, agent});
         cp.node = std::move(n);
         plans.push_back(std::move(cp));
       }
@@ -1293,8 +1352,8 @@ class BatchSolver {
         if (!ok) continue;  // no path under these constraints: the child is dropped
         for (size_t j = cp.firstJob; j < cp.firstJob + cp.nJobs; ++j) {
           const int a = specs[j].agent;
-          n.cost += outs[j].path->cost;
-          n.LB += outs[j].path->fmin;
+          n.cost += outs[j].path.cost;
+          n.LB += outs[j].path.fmin;
           n.paths[a] = std::move(outs[j].path);
         }
         n.id = I.nextId++;
@@ -1330,7 +1389,7 @@ class BatchSolver {
   int m_slice = 256;  // expansions per replan and launch (MRP_HOST_SLICE)
   bool m_sliced = false;
   std::mutex m_rowMutex;
-  const ConsPtr m_noCons = std::make_shared<const ConsList>();
+  std::vector<int> m_doneQueue;  // finished instances whose rows are still to be returned (m_rowMutex)
   HostProfile m_prof;
   // staging buffers reused across lock-step iterations
   mutable std::vector<int32_t> m_evTables, m_evTlen;

@@ -48,11 +48,44 @@ int fail(int code, const char* fmt, ...) {
 
 struct Counters {
   std::mutex mu;
-  long calls[8] = {0, 0, 0, 0, 0, 0, 0, 0};  // conflicts, conflicts_pool, ll_fs, ll_pool, ll_sliced, suspended, resumed, jobs
+  // conflicts, conflicts_pool, ll_fs, ll_pool, ll_sliced, suspended, resumed, jobs, then the sum of
+  // the content hashes of all calls (what the device would have been given, row numbers and state
+  // ids left out: two drivers with equal sums made the same calls up to their order)
+  long calls[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
 } g_cnt;
 void bump(int k, long n = 1) {
   std::lock_guard<std::mutex> lk(g_cnt.mu);
   g_cnt.calls[k] += n;
+}
+struct Fnv {
+  unsigned long long h = 1469598103934665603ull;
+  void add(const void* p, size_t n) {
+    const unsigned char* b = (const unsigned char*)p;
+    for (size_t i = 0; i < n; ++i) h = (h ^ b[i]) * 1099511628211ull;
+  }
+  template <class T>
+  void val(const T& v) { add(&v, sizeof v); }
+};
+void bumpHash(const Fnv& f) {
+  std::lock_guard<std::mutex> lk(g_cnt.mu);
+  g_cnt.calls[8] = (long)((unsigned long long)g_cnt.calls[8] + f.h);
+}
+// content of dense tables [B][N][Tpad] / len[B][N]: the cells up to each path's end
+void hashTables(Fnv& f, const int32_t* cell, const int32_t* len, int B, int N, int Tpad) {
+  for (size_t k = 0; k < (size_t)B * N; ++k) {
+    f.val(len[k]);
+    f.add(cell + k * Tpad, (size_t)len[k] * 4);
+  }
+}
+void hashJob(Fnv& f, const mrp_job& q, const int32_t* vc, const int32_t* ec) {
+  f.val(q.map);
+  f.val(q.start_cell);
+  f.val(q.goal_cell);
+  f.val(q.field);
+  f.val(q.table);
+  f.val(q.self);
+  f.add(vc + 2 * (size_t)q.vc_begin, (size_t)(q.vc_end - q.vc_begin) * 8);
+  f.add(ec + 3 * (size_t)q.ec_begin, (size_t)(q.ec_end - q.ec_begin) * 12);
 }
 
 }  // namespace
@@ -184,9 +217,9 @@ long long mrp_launch_count(void) { return 0; }
 
 // what the driver did, for the tests: calls of conflicts, conflicts_pool, lowlevel_fs, lowlevel_pool,
 // lowlevel_sliced; SUSPENDED answers, resumed jobs, jobs finished
-void mrp_emu_counters(long* out8) {
+void mrp_emu_counters(long* out9) {
   std::lock_guard<std::mutex> lk(g_cnt.mu);
-  for (int k = 0; k < 8; ++k) out8[k] = g_cnt.calls[k];
+  for (int k = 0; k < 9; ++k) out9[k] = g_cnt.calls[k];
 }
 
 int mrp_map_create(int dimx, int dimy, const int32_t* obst_xy, int n_obst, mrp_map* out) {
@@ -260,6 +293,13 @@ int mrp_count_conflicts(const int32_t* cell, const int32_t* len, int N, int Tpad
 int mrp_conflicts_batch(const int32_t* cell, const int32_t* len, int B, int N, int Tpad, int dimx, int mode,
                         int32_t* found, mrp_conflict* conflicts, int32_t* counts) {
   bump(0);
+  {
+    Fnv f;
+    f.val(B); f.val(N); f.val(dimx); f.val(mode);
+    for (size_t k = 0; k < (size_t)B * N; ++k) EMU_CHECK(len[k] >= 0 && len[k] <= Tpad, "len %d, Tpad %d", len[k], Tpad);
+    hashTables(f, cell, len, B, N, Tpad);
+    bumpHash(f);
+  }
   for (int b = 0; b < B; ++b) {
     const int32_t* c = cell + (size_t)b * N * Tpad;
     const int32_t* l = len + (size_t)b * N;
@@ -280,6 +320,13 @@ int mrp_lowlevel_batch_fs(const mrp_map* maps, int n_maps, mrp_fieldset fs, cons
   bump(2);
   bump(7, n_jobs);
   if (int rc = checkJobs(jobs, n_jobs, n_maps, fs ? (int)fs->goalCell.size() : 0, n_vc, n_ec, n_tables, N)) return rc;
+  {
+    Fnv f;
+    f.val(prm->variant); f.val(prm->w); f.val(prm->max_expanded); f.val(n_jobs);
+    if (n_tables > 0) hashTables(f, tables, table_len, n_tables, N, Tpad);
+    for (int j = 0; j < n_jobs; ++j) hashJob(f, jobs[j], vc, ec);
+    bumpHash(f);
+  }
   std::vector<int32_t> cells, gs;
   for (int j = 0; j < n_jobs; ++j) {
     if (int rc = runJob(maps, fs, vc, ec, tables, table_len, N, Tpad, jobs[j], *prm, info[j], cells, gs)) return rc;
@@ -344,6 +391,12 @@ int mrp_conflicts_batch_pool(mrp_pathpool pool, const int32_t* table_slots, int 
   bump(1);
   std::vector<int32_t> cell, len;
   if (int rc = gather(pool, table_slots, B, N, Tpad, cell, len)) return rc;
+  {
+    Fnv f;
+    f.val(B); f.val(N); f.val(dimx); f.val(mode);
+    hashTables(f, cell.data(), len.data(), B, N, Tpad);
+    bumpHash(f);
+  }
   for (int b = 0; b < B; ++b) {
     const int32_t* c = cell.data() + (size_t)b * N * Tpad;
     const int32_t* l = len.data() + (size_t)b * N;
@@ -367,6 +420,17 @@ int mrp_lowlevel_batch_pool_sliced(const mrp_map* maps, int n_maps, mrp_fieldset
   if (int rc = checkJobs(jobs, n_jobs, n_maps, fs ? (int)fs->goalCell.size() : 0, n_vc, n_ec, n_tables, N)) return rc;
   std::vector<int32_t> cell, len;
   if (int rc = gather(pool, table_slots, n_tables, N, Tpad, cell, len)) return rc;
+  {
+    Fnv f;
+    f.val(prm->variant); f.val(prm->w); f.val(prm->max_expanded); f.val(n_jobs); f.val(slice_expanded);
+    hashTables(f, cell.data(), len.data(), n_tables, N, Tpad);
+    for (int j = 0; j < n_jobs; ++j) {
+      hashJob(f, jobs[j], vc, ec);
+      const int r = resume ? resume[j] : 0;
+      f.val(r);
+    }
+    bumpHash(f);
+  }
   std::vector<char> blobSeen(pool->blobs.size(), 0);
   std::vector<int32_t> cells, gs;
   for (int j = 0; j < n_jobs; ++j) {

@@ -21,7 +21,8 @@ def main():
     from libmultirobotplanning_b200 import instances as I
     from libmultirobotplanning_b200 import solver
     os.environ.setdefault("OMP_WAIT_POLICY", "PASSIVE")
-    solver._lib = ctypes.CDLL(solver.LIB_PATH)  # its NEEDED libmrp_b200.so is the emulation
+    # its NEEDED libmrp_b200.so is the emulation ("host": another build of the driver, for A/B runs)
+    solver._lib = ctypes.CDLL(spec.get("host", solver.LIB_PATH))
     solver._lib.mrph_last_error.restype = ctypes.c_char_p
     assert b"host emulation" in ctypes.cast(emu.mrp_device_info, ctypes.CFUNCTYPE(ctypes.c_char_p))()
     sets = {}
@@ -55,16 +56,18 @@ def main():
         else:
             by = load(run["set"])
             insts = [by[n] for n in run["names"]]
-        before = (ctypes.c_long * 8)()
+        before = (ctypes.c_long * 9)()
         emu.mrp_emu_counters(before)
         res = solver.solve_batch(run["algo"], insts, w=run.get("w", 1.0), max_hl=run.get("max_hl", 0),
                                  max_ll=run.get("max_ll", 12000), max_ll_total=run.get("max_ll_total", 0))
-        after = (ctypes.c_long * 8)()
+        after = (ctypes.c_long * 9)()
         emu.mrp_emu_counters(after)
         for r in res:
             if "paths" in r:
                 r["paths"] = [p.tolist() for p in r["paths"]]
-        out.append({"results": res, "counters": [a - b for a, b in zip(after, before)]})
+        cnt = [a - b for a, b in zip(after, before)]
+        cnt[8] &= (1 << 64) - 1  # a sum of hashes modulo 2^64
+        out.append({"results": res, "counters": cnt})
         for k in run.get("env", {}):
             os.environ.pop(k, None)
     json.dump(out, sys.stdout)
