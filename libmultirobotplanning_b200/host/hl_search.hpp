@@ -128,7 +128,10 @@ class BatchSolver {
   ~BatchSolver() {
     m_flights.clear();
     for (Inst& I : m_inst) {
-      for (Node* n : I.open) delete n;
+      for (Node* n : I.open) freeNode(n);
+      I.open.clear();
+      for (const auto& h : I.heap) freeNode(h.node);
+      I.heap.clear();
       I.solution.clear();
     }
     if (m_pool) poolCache(m_pathCap, m_dimx, m_dimy, m_opt.maxLlExpanded, m_pool);
@@ -170,14 +173,14 @@ class BatchSolver {
       const double tPop = nowSeconds();
       const bool timeUp = m_opt.maxSeconds > 0 && elapsed() > m_opt.maxSeconds;
       const double tNow = elapsed();
-      std::vector<std::unique_ptr<Node> > popped(m_inst.size());
+      std::vector<NodeUP> popped(m_inst.size());
       // instances are independent: the per-instance bookkeeping of a lock-step
       // iteration runs on all host cores
 #pragma omp parallel for schedule(dynamic, 16) if (m_inst.size() >= kParallelMin)
       for (long k = 0; k < (long)m_inst.size(); ++k) {
         Inst& I = m_inst[k];
         if (I.done || I.busy) continue;
-        if (I.open.empty()) {
+        if (I.openEmpty()) {
           finish(I, kNoSolution, nullptr, tNow);
           continue;
         }
@@ -186,7 +189,7 @@ class BatchSolver {
           finish(I, kCapped, nullptr, tNow);
           continue;
         }
-        std::unique_ptr<Node> P = popBest(I);
+        NodeUP P = popBest(I);
         ++I.res.hlExpanded;  // onExpandHighLevelNode, cbs.hpp:121
         if (!P->found) {
           finish(I, kSolved, P.get(), tNow);
@@ -263,10 +266,16 @@ class BatchSolver {
     int32_t prev;        // older constraint of the same agent on the way to the root, -1: none
   };
   typedef std::shared_ptr<const std::vector<int> > TaskPtr;
+  // A node and its two per-agent arrays are ONE block of its instance's pool (Inst::nodePool:
+  // all nodes of an instance have the same size, an instance is only ever touched by one thread
+  // at a time, so creating / dropping a node costs no malloc, no lock and no arena growth; the
+  // slabs go back in one piece when the instance is done).  Nodes are made by newNode /
+  // cloneNode and owned through NodeUP or, inside OPEN / `fresh`, as plain pointers that end in
+  // freeNode.
   struct Node {
-    int inst = 0;
-    std::vector<PathRef> paths;
-    std::vector<int32_t> cons;  // per agent: newest entry of its chain in Inst::consArena, -1: none
+    int inst = 0, nAgents = 0;
+    PathRef* paths = nullptr;   // [nAgents], behind the node in its block
+    int32_t* cons = nullptr;    // [nAgents]: newest entry of the agent's chain in Inst::consArena, -1: none
     TaskPtr task;               // goal cell per agent (-1: none)
     long cost = 0, LB = 0;
     int focal = 0;
@@ -275,6 +284,104 @@ class BatchSolver {
     int found = 0;
     mrp_conflict conflict;
   };
+  struct BlockPool {  // equal-sized blocks cut from slabs; not thread-safe (one instance, one thread)
+    size_t blockSize = 0, left = 0;
+    char* cur = nullptr;
+    void* freeList = nullptr;
+    std::vector<char*> slabs;
+    BlockPool() {}
+    BlockPool(const BlockPool&) = delete;
+    BlockPool& operator=(const BlockPool&) = delete;
+    BlockPool(BlockPool&& o) noexcept
+        : blockSize(o.blockSize), left(o.left), cur(o.cur), freeList(o.freeList), slabs(std::move(o.slabs)) {
+      o.left = 0;
+      o.cur = nullptr;
+      o.freeList = nullptr;
+    }
+    ~BlockPool() { release(); }
+    // -DMRP_HOST_DEBUG_MALLOC: one malloc per block, so that AddressSanitizer sees a node that is
+    // used after it was dropped (tests/test_host_driver_emu.py builds that variant when asked to)
+#ifdef MRP_HOST_DEBUG_MALLOC
+    void* alloc() { return std::malloc(blockSize); }
+    void free(void* p) { std::free(p); }
+    void release() {}
+#else
+    void* alloc() {
+      if (freeList) {
+        void* p = freeList;
+        freeList = *(void**)p;
+        return p;
+      }
+      if (left < blockSize) {
+        const size_t n = std::max<size_t>(blockSize * 16, (size_t)64 << 10);
+        cur = (char*)std::malloc(n);
+        if (!cur) throw std::bad_alloc();
+        slabs.push_back(cur);
+        left = n;
+      }
+      void* p = cur;
+      cur += blockSize;
+      left -= blockSize;
+      return p;
+    }
+    void free(void* p) {
+      *(void**)p = freeList;
+      freeList = p;
+    }
+    void release() {
+      for (char* sl : slabs) std::free(sl);
+      slabs.clear();
+      left = 0;
+      cur = nullptr;
+      freeList = nullptr;
+    }
+#endif
+  };
+  struct NodeDeleter {
+    BatchSolver* solver;
+    NodeDeleter() : solver(nullptr) {}
+    explicit NodeDeleter(BatchSolver* s) : solver(s) {}
+    void operator()(Node* n) const { solver->freeNode(n); }
+  };
+  typedef std::unique_ptr<Node, NodeDeleter> NodeUP;
+  NodeUP own(Node* n) { return NodeUP(n, NodeDeleter(this)); }
+  static size_t nodeHeaderBytes() { return (sizeof(Node) + 15) & ~(size_t)15; }
+  // an empty node of instance k: no paths, no constraints
+  Node* newNode(int k) {
+    Inst& I = m_inst[k];
+    const int N = (int)I.in->numAgents();
+    if (!I.nodePool.blockSize)
+      I.nodePool.blockSize = (nodeHeaderBytes() + (size_t)N * (sizeof(PathRef) + sizeof(int32_t)) + 15) & ~(size_t)15;
+    char* b = (char*)I.nodePool.alloc();
+    Node* n = new (b) Node();
+    n->inst = k;
+    n->nAgents = N;
+    n->paths = reinterpret_cast<PathRef*>(b + nodeHeaderBytes());
+    n->cons = reinterpret_cast<int32_t*>(b + nodeHeaderBytes() + (size_t)N * sizeof(PathRef));
+    for (int a = 0; a < N; ++a) {
+      new (&n->paths[a]) PathRef();
+      n->cons[a] = -1;
+    }
+    return n;
+  }
+  // HighLevelNode newNode = P (cbs.hpp:144): a flat copy of path references and chain heads
+  Node* cloneNode(const Node& P) {
+    Inst& I = m_inst[P.inst];
+    char* b = (char*)I.nodePool.alloc();
+    Node* n = new (b) Node(P);
+    n->paths = reinterpret_cast<PathRef*>(b + nodeHeaderBytes());
+    n->cons = reinterpret_cast<int32_t*>(b + nodeHeaderBytes() + (size_t)P.nAgents * sizeof(PathRef));
+    for (int a = 0; a < P.nAgents; ++a) new (&n->paths[a]) PathRef(P.paths[a]);
+    std::memcpy(n->cons, P.cons, (size_t)P.nAgents * sizeof(int32_t));
+    return n;
+  }
+  void freeNode(Node* n) {
+    if (!n) return;
+    BlockPool& pool = m_inst[n->inst].nodePool;
+    for (int a = 0; a < n->nAgents; ++a) n->paths[a].~PathRef();
+    n->~Node();
+    pool.free(n);
+  }
   // batches smaller than this stay on the calling thread (a single instance from
   // the command-line binaries must not wake a thread team per iteration)
   static constexpr size_t kParallelMin = 64;
@@ -293,7 +400,19 @@ class BatchSolver {
   };
   struct Inst {
     const MapfInstance* in = nullptr;
-    std::set<Node*, OpenOrder> open;  // owning
+    std::set<Node*, OpenOrder> open;  // owning; ecbs / ecbs_ta (FOCAL walks it in cost order)
+    // cbs / cbs_ta only ever take the best node: a binary heap of (cost, focal, id, node) with the
+    // keys inline — the same total order as OpenOrder (ids are unique), no tree node per entry
+    struct HeapItem {
+      long cost;
+      int focal, id;
+      Node* node;
+      bool operator<(const HeapItem& o) const {  // std::*_heap keep the LARGEST on top: invert
+        return std::make_tuple(cost, focal, id) > std::make_tuple(o.cost, o.focal, o.id);
+      }
+    };
+    std::vector<HeapItem> heap;  // owning
+    bool openEmpty() const { return open.empty() && heap.empty(); }
     int nextId = 0;
     bool done = false;
     bool busy = false;       // sliced replans of its current expansion are still running
@@ -307,10 +426,11 @@ class BatchSolver {
     std::vector<ConsEntry> consArena;  // constraint chains of all nodes of this instance
     std::vector<int32_t> rows;         // pool rows this instance holds (returned when it is done)
     bool rowsQueued = false;
+    BlockPool nodePool;                // the blocks of this instance's nodes
   };
   struct Pending {
     int inst = 0;
-    std::unique_ptr<Node> parent;
+    NodeUP parent;
   };
   struct JobSpec {
     int inst, agent, goal, field;
@@ -409,6 +529,7 @@ class BatchSolver {
       }
       std::vector<int32_t>().swap(I.rows);
       std::vector<ConsEntry>().swap(I.consArena);
+      I.nodePool.release();  // every node of a finished instance is gone by now (see run())
     }
   }
   // the constraints of one chain, oldest first, appended to the (time, cell) pairs / (time, from,
@@ -450,7 +571,10 @@ class BatchSolver {
   // pool mode: the paths of the instances that finished since the last call come to
   // the host (one read for all of them; main thread only)
   void fetchSolutions() {
-    if (!m_pool) return;
+    if (!m_pool) {
+      releaseFinished();
+      return;
+    }
     std::vector<int32_t> rows;
     for (size_t k = 0; k < m_inst.size(); ++k)
       for (const PathRef& p : m_inst[k].solution) rows.push_back(p.slot);
@@ -560,7 +684,8 @@ class BatchSolver {
     I.res.status = status;
     I.res.runtime = t;
     if (n) {
-      for (const PathRef& p : n->paths) {  // example/cbs.cpp:630-635
+      for (int a = 0; a < n->nAgents; ++a) {  // example/cbs.cpp:630-635
+        const PathRef& p = n->paths[a];
         if (p.slot >= 0)
           I.solution.push_back(p);  // cells follow in fetchSolutions()
         else
@@ -570,9 +695,11 @@ class BatchSolver {
         I.res.lowerBound += p.fmin;
       }
     }
-    for (Node* o : I.open) delete o;
+    for (Node* o : I.open) freeNode(o);
     I.open.clear();
-    if (m_pool && !I.rowsQueued) {  // its rows go back once the solution has been read
+    for (const auto& h : I.heap) freeNode(h.node);
+    I.heap.clear();
+    if (!I.rowsQueued) {  // its rows and node slabs go back once the solution has been read
       I.rowsQueued = true;
       std::lock_guard<std::mutex> lk(m_rowMutex);
       m_doneQueue.push_back((int)(&I - m_inst.data()));
@@ -591,10 +718,24 @@ class BatchSolver {
     }
 #pragma omp parallel for schedule(dynamic, 16) if (runs.size() >= kParallelMin)
     for (long r = 0; r < (long)runs.size(); ++r)
-      for (size_t i = runs[r].first; i < runs[r].second; ++i) m_inst[fresh[i]->inst].open.insert(fresh[i]);
+      for (size_t i = runs[r].first; i < runs[r].second; ++i) openInsert(m_inst[fresh[i]->inst], fresh[i]);
   }
 
-  std::unique_ptr<Node> popBest(Inst& I) {
+  void openInsert(Inst& I, Node* n) {
+    if (isFocal()) {
+      I.open.insert(n);
+      return;
+    }
+    I.heap.push_back({n->cost, n->focal, n->id, n});
+    std::push_heap(I.heap.begin(), I.heap.end());
+  }
+  NodeUP popBest(Inst& I) {
+    if (!isFocal()) {  // lowest (cost, focal, id): cbs.hpp:187-191 orders by cost only
+      std::pop_heap(I.heap.begin(), I.heap.end());
+      NodeUP n = own(I.heap.back().node);
+      I.heap.pop_back();
+      return n;
+    }
     auto best = I.open.begin();
     if (m_algo == Algo::ECBSTA) {
       // FOCAL rebuilt every iteration: cost <= nextRootNodeCost, best by
@@ -634,7 +775,7 @@ class BatchSolver {
           }
       }
     }
-    std::unique_ptr<Node> n(*best);
+    NodeUP n = own(*best);
     I.open.erase(best);
     return n;
   }
@@ -761,12 +902,12 @@ class BatchSolver {
                   int& Tpad) const {
     N = 0;
     Tpad = 1;
-    for (const Node* n : nodes) N = std::max(N, (int)n->paths.size());
+    for (const Node* n : nodes) N = std::max(N, n->nAgents);
     rows.assign(nodes.size() * (size_t)N, -1);
     std::vector<int> tmax(nodes.size(), 1);
 #pragma omp parallel for schedule(static) if (nodes.size() >= kParallelMin)
     for (long b = 0; b < (long)nodes.size(); ++b)
-      for (size_t a = 0; a < nodes[b]->paths.size(); ++a) {
+      for (int a = 0; a < nodes[b]->nAgents; ++a) {
         const PathRef& p = nodes[b]->paths[a];
         if (!p) continue;
         rows[b * N + a] = p.slot;
@@ -780,9 +921,9 @@ class BatchSolver {
     N = 0;
     Tpad = 1;
     for (const Node* n : nodes) {
-      N = std::max(N, (int)n->paths.size());
-      for (const PathRef& p : n->paths)
-        if (p) Tpad = std::max(Tpad, (int)p.host->cells.size());
+      N = std::max(N, n->nAgents);
+      for (int a = 0; a < n->nAgents; ++a)
+        if (n->paths[a]) Tpad = std::max(Tpad, (int)n->paths[a].host->cells.size());
     }
     // cells past a path's length are never read (the kernels clamp to len-1),
     // so the tables are not cleared: only the lengths are
@@ -790,7 +931,7 @@ class BatchSolver {
     tlen.assign(nodes.size() * (size_t)N, 0);
 #pragma omp parallel for schedule(static) if (nodes.size() >= kParallelMin)
     for (long b = 0; b < (long)nodes.size(); ++b)
-      for (size_t a = 0; a < nodes[b]->paths.size(); ++a) {
+      for (int a = 0; a < nodes[b]->nAgents; ++a) {
         if (!nodes[b]->paths[a]) continue;  // not planned yet (ECBS root construction)
         const auto& c = nodes[b]->paths[a].host->cells;
         std::copy(c.begin(), c.end(), tables.begin() + (b * N + a) * (size_t)Tpad);
@@ -851,13 +992,10 @@ class BatchSolver {
 
   // ---- roots -----------------------------------------------------------------
   void buildRoots(std::vector<Node*>& fresh) {
-    std::vector<std::unique_ptr<Node> > roots(m_inst.size());
+    std::vector<NodeUP> roots(m_inst.size());
     for (size_t k = 0; k < m_inst.size(); ++k) {
       Inst& I = m_inst[k];
-      std::unique_ptr<Node> n(new Node());
-      n->inst = (int)k;
-      n->paths.resize(I.in->numAgents());
-      n->cons.assign(I.in->numAgents(), -1);
+      NodeUP n = own(newNode((int)k));
       n->id = I.nextId++;
       n->isRoot = true;
       if (m_algo == Algo::CBSTA) {
@@ -918,7 +1056,7 @@ class BatchSolver {
   // ecbs_ta.hpp:107-126,318-330); nodes[k] belongs to instance k (may be null).
   // initial == true: a failing search ends the instance (first root);
   // otherwise the node is just dropped (later roots of ecbs_ta).
-  void planSequential(std::vector<std::unique_ptr<Node> >& nodes, bool initial) {
+  void planSequential(std::vector<NodeUP>& nodes, bool initial) {
     size_t maxN = 0;
     for (size_t k = 0; k < nodes.size(); ++k)
       if (nodes[k]) maxN = std::max(maxN, m_inst[k].in->numAgents());
@@ -938,7 +1076,7 @@ class BatchSolver {
     }
   }
 
-  void absorbRoot(std::vector<std::unique_ptr<Node> >& roots, const JobSpec& s, JobOut& o,
+  void absorbRoot(std::vector<NodeUP>& roots, const JobSpec& s, JobOut& o,
                   bool initial) {
     if (!roots[s.inst]) return;
     if (o.status != 0) {  // cbs.hpp:96-100: a failing root search ends the search
@@ -957,7 +1095,7 @@ class BatchSolver {
   // exceeds nextRootNodeCost the next-best assignment becomes a new root, then
   // the bound is reset from the cheapest node's LB.
   void spawnMinRoots() {
-    std::vector<std::unique_ptr<Node> > roots(m_inst.size());
+    std::vector<NodeUP> roots(m_inst.size());
     std::vector<char> triggered(m_inst.size(), 0);
     bool any = false;
     for (size_t k = 0; k < m_inst.size(); ++k) {
@@ -965,11 +1103,8 @@ class BatchSolver {
       if (I.done || I.open.empty()) continue;
       if (!((*I.open.begin())->cost > I.nextRootNodeCost)) continue;
       triggered[k] = 1;
-      std::unique_ptr<Node> r(new Node());
+      NodeUP r = own(newNode((int)k));
       if (!nextTasks(I, r->task)) continue;
-      r->inst = (int)k;
-      r->paths.resize(I.in->numAgents());
-      r->cons.assign(I.in->numAgents(), -1);
       r->isRoot = true;
       roots[k] = std::move(r);
       any = true;
@@ -983,7 +1118,7 @@ class BatchSolver {
           fresh.push_back(roots[k].release());
         }
       evaluate(fresh);
-      for (Node* n : fresh) m_inst[n->inst].open.insert(n);
+      for (Node* n : fresh) openInsert(m_inst[n->inst], n);
     }
     for (size_t k = 0; k < m_inst.size(); ++k) {
       Inst& I = m_inst[k];
@@ -1001,7 +1136,7 @@ class BatchSolver {
   };
   struct FlightChild {
     int agent = 0;
-    std::unique_ptr<Node> node;
+    NodeUP node;
   };
   // one high-level expansion in progress: the parent, its two children and their replans
   struct Flight {
@@ -1010,7 +1145,7 @@ class BatchSolver {
     std::vector<FlightJob> jobs;
     // a root under construction (ecbs): its agents are planned one by one, jobs[0] is
     // the replan of agent nextAgent and sees the agents planned so far
-    std::unique_ptr<Node> root;
+    NodeUP root;
     int nextAgent = 0;
   };
   bool nextRootJob(Flight& f) {
@@ -1056,7 +1191,7 @@ class BatchSolver {
       const mrp_conflict& c = P.conflict;
       for (int side = 0; side < 2; ++side) {
         const int agent = side == 0 ? c.agent1 : c.agent2;
-        std::unique_ptr<Node> n(new Node(P));  // a flat copy: rows and chain heads
+        NodeUP n = own(cloneNode(P));  // a flat copy: rows and chain heads
         n->cons[agent] = addConstraint(I, P, c, side, agent);
         n->cost -= n->paths[agent].cost;
         n->LB -= n->paths[agent].fmin;
@@ -1255,7 +1390,7 @@ class BatchSolver {
     struct ChildPlan {
       int pendingIdx;
       int agent;        // replanned agent; -1: a whole new root (cbs_ta)
-      std::unique_ptr<Node> node;
+      NodeUP node;
       size_t firstJob, nJobs;
       bool failed = false;
     };
@@ -1275,11 +1410,8 @@ class BatchSolver {
         // an expanded root with a conflict spawns the next-best assignment as
         // a new root (cbs_ta.hpp:142-172).  The reference copies isRoot into
         // every child (cbs_ta.hpp:180), so this fires on every expansion.
-        std::unique_ptr<Node> r(new Node());
+        NodeUP r = own(newNode(pending[pi].inst));
         if (nextTasks(I, r->task)) {
-          r->inst = pending[pi].inst;
-          r->paths.resize(I.in->numAgents());
-          r->cons.assign(I.in->numAgents(), -1);
           r->isRoot = true;
           ChildPlan cp;
           cp.pendingIdx = (int)pi;
@@ -1298,7 +1430,7 @@ class BatchSolver {
       const mrp_conflict& c = P.conflict;
       for (int side = 0; side < 2; ++side) {
         const int agent = side == 0 ? c.agent1 : c.agent2;
-        std::unique_ptr<Node> n(new Node(P));  // a flat copy: path references and chain heads
+        NodeUP n = own(cloneNode(P));  // a flat copy: path references and chain heads
         n->isRoot = P.isRoot;
         n->cons[agent] = addConstraint(I, P, c, side, agent);
         n->cost -= n->paths[agent].cost;
@@ -1367,7 +1499,7 @@ class BatchSolver {
     size_t keep = 0;
     for (size_t i = 0; i < fresh.size(); ++i) {
       if (m_inst[fresh[i]->inst].done)
-        delete fresh[i];
+        freeNode(fresh[i]);
       else
         fresh[keep++] = fresh[i];
     }
