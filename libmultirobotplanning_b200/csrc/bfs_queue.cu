@@ -443,7 +443,7 @@ constexpr int kQueueSlack = 128;  // words behind each queue (see the kernel)
 
 static QueueGeom queueGeometry(const mrp_map_s* map) {
   QueueGeom q;
-  q.WPR = ((map->dimx + 2 + 31) / 32) | 1;
+  q.WPR = bitmapRowWords(map->dimx);
   q.nOpenWords = (map->dimy + 4) * q.WPR;  // border rows + two zero rows (dummy cell)
   const int span = map->dimx + map->dimy;
   // 12 warps serve a 1024x1024 map as fast as 32 (the level loop is bound by

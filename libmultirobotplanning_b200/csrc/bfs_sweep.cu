@@ -497,7 +497,7 @@ int launchBfsSweep(const mrp_map_s* map, const int32_t* d_goal_cell, int n_goals
   p.n_goals = n_goals;
   p.dimx = map->dimx;
   p.dimy = map->dimy;
-  p.WPR = ((map->dimx + 2 + 31) / 32) | 1;
+  p.WPR = bitmapRowWords(map->dimx);
   p.dbg = getenv("MRP_SWEEP_DBG") ? atoi(getenv("MRP_SWEEP_DBG")) : 0;
   MRP_CUDA(cudaMemsetAsync(d_ws, 0, 64 * 4, st));
   const bool vec = (map->dimx & 3) == 0 && (reinterpret_cast<uintptr_t>(d_out) & 15) == 0;

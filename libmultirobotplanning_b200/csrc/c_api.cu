@@ -305,7 +305,7 @@ int mrp_map_create(int dimx, int dimy, const int32_t* obst_xy, int n_obst,
     const int TW8 = (dimx + 7) / 8, TH4 = (dimy + 3) / 4;
     std::vector<uint32_t> bits84((size_t)TW8 * TH4, 0u);
     // third layout: row-major with a zero border for the queue BFS kernel
-    const int WPR = ((dimx + 2 + 31) / 32) | 1;
+    const int WPR = bitmapRowWords(dimx);
     // (+ 4 words: the queue kernel's bulk copy moves whole 16-byte granules)
     std::vector<uint32_t> rowbits((size_t)(dimy + 4) * WPR + 4, 0u);
     for (int y = 0; y < dimy; ++y)

@@ -14,6 +14,17 @@
 
 namespace mrp {
 
+// Words per row of the bordered row-major bitmap (`d_rowbits`: bit x + 1 of row y + 1 = cell (x, y) is
+// free): the columns plus a zero border on both sides, rounded to an ODD number of words (the cells of
+// a diagonal wavefront then fall into distinct banks) and never fewer than three: the kernels divide
+// word indices by this stride with a 32-bit multiply-shift whose constant 2^32 / stride does not exist
+// for a stride of one (narrow maps, dimx <= 30, used to get one word per row and with it a zero
+// constant: every cell was filed under row 0).
+inline int bitmapRowWords(int dimx) {
+  const int w = ((dimx + 2 + 31) / 32) | 1;
+  return w < 3 ? 3 : w;
+}
+
 constexpr int kTile = 32;  // maps are tiled in 32x32-cell tiles, one bit per cell
 
 // ---- error handling (thread-local message, never throws across the ABI) ----

@@ -41,6 +41,9 @@ def test_golden_crcs(capi, set8, set32, oracle_golden):
     (32, 32, 0.2), (33, 32, 0.2), (32, 33, 0.2), (40, 50, 0.3), (64, 64, 0.2),
     (100, 37, 0.35), (129, 65, 0.2), (257, 300, 0.25), (1100, 70, 0.2),
     (70, 1100, 0.2),
+    # narrow and more than one tile high (dimx <= 30): used to get one bitmap word per row, for which the
+    # queue kernel's multiply-shift division has no constant (found by test_fields_equal_reference_class)
+    (17, 45, 0.0), (30, 33, 0.2), (8, 100, 0.3), (3, 64, 0.0), (29, 1000, 0.2), (1, 40, 0.0),
     # the queue kernel's compile-time instances (widths 256, 512, 1024, 2048)
     (256, 90, 0.2), (512, 300, 0.25), (1024, 130, 0.2), (2048, 75, 0.3)])
 def test_random_maps(capi, orc, dimx, dimy, density):
