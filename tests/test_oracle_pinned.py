@@ -437,3 +437,30 @@ def test_oracle_conflicts_equal_reference_environment(orc):
     if os.path.exists(os.path.join(E.REF, "env_probe_ecbs")):  # live, where the probes were built
         live = E.probe("env_probe_ecbs", tabs[:8], True)
         assert [r["count"] for r in live] == g["count"][:8]
+
+
+def test_oracle_replans_equal_reference_astar(orc, set8, set32):
+    """tests/golden/astar_probe_golden.json: cost and number of states of 140 constrained low-level
+    replans from the reference's OWN AStar::search (a_star.hpp:63-161) driven through its own
+    Environments (example/cbs.cpp and example/cbs_ta.cpp included unmodified into
+    oracle/_ref/astar_probe_*): vertex / edge constraints on the agent's shortest path, constraints
+    on the goal after arrival, cbs_ta's free waiting on the goal and agents without a task.  The
+    oracle's A* must find the same costs (paths of equal cost are not unique)."""
+    import json
+    import os
+    import sys
+    gdir = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    if gdir not in sys.path:
+        sys.path.insert(0, gdir)
+    import make_astar_golden as A
+    g = json.load(open(os.path.join(gdir, "astar_probe_golden.json")))
+    n = 0
+    for (dx, dy, obst, lst), gold in zip(A.jobs(orc, set8, set32), g):
+        assert len(lst) == len(gold)
+        for (variant, s, goal, vc, ec), (cost, length) in zip(lst, gold):
+            r = orc.lowlevel(dx, dy, obst, variant, s, goal, vc, ec)
+            assert r["status"] == 0 and r["cost"] == cost, (variant, s, goal, vc, ec)
+            if variant == 0:
+                assert len(r["path"]) == length == cost + 1
+            n += 1
+    assert n == 140
