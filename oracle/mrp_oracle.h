@@ -21,7 +21,10 @@
  *      tests/golden/sph_fields_golden.json); getFirstConflict under both loop
  *      bounds, focalHeuristic, focalStateHeuristic and focalTransitionHeuristic
  *      against the reference's own Environment classes on 40 path tables
- *      (oracle/_ref/env_probe_*, tests/golden/env_probe_golden.json);
+ *      (oracle/_ref/env_probe_*, tests/golden/env_probe_golden.json); the costs of 140
+ *      constrained low-level replans against the reference's AStar::search through
+ *      its cbs / cbs_ta Environments (oracle/_ref/astar_probe_*,
+ *      tests/golden/astar_probe_golden.json);
  *  (3) the known answers held by the reference's own tests (test/test_cbs.py:24-34,
  *      test/test_ecbs.py:25-35, test/test_cbs_ta.py:24-38, test/test_assignment.py:19-63,
  *      test/test_next_best_assignment.py:19-110) — the compiled binaries pass all
