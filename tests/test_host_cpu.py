@@ -217,3 +217,27 @@ def test_validate_paths_agrees_with_the_oracle_conflict_count():
     I.obstacles = np.array([[1, 0]], np.int32)
     assert "obstacle" in validate.validate_paths(I, [np.array([(0, 0, 0), (1, 0, 1)])])
     assert "goal" in validate.validate_paths(I, [np.array([(0, 0, 0), (0, 1, 1)])], goals=[[3, 3]])
+
+
+def test_host_assignment_equals_reference_next_best_assignment(orc):
+    """tests/golden/nba_golden.json: the complete cost sequences that the reference's OWN
+    NextBestAssignment enumerates (next_best_assignment.hpp:37-201 over assignment.hpp, compiled
+    unmodified into oracle/_ref/next_best_assignment) on 48 seeded cost tables (square, rectangular,
+    sparse, many ties; 637 solutions).  The host module (host/assignment.hpp) and the oracle's
+    restatement must enumerate the same costs in the same order."""
+    import json
+    import os
+    import sys
+    from libmultirobotplanning_b200 import solver
+    gdir = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    if gdir not in sys.path:
+        sys.path.insert(0, gdir)
+    import make_nba_golden as N
+    g = json.load(open(os.path.join(gdir, "nba_golden.json")))
+    probs = N.problems()
+    assert len(probs) == len(g) == 48
+    for (A, T, E), want in zip(probs, g):
+        edges = [list(e) for e in E]
+        c1, _ = solver.next_best_assignments(edges, A, T, 500)
+        c2, _ = orc.next_best_assignments(edges, A, T, 500)
+        assert list(c1) == want and list(c2) == want, (A, T, E)
