@@ -123,7 +123,10 @@ def test_cbs_ta_and_ecbs_ta(emu, set8, set32):
     out = emu([{"algo": CBS_TA, "ta": keys8, "max_hl": 20000}, {"algo": CBS_TA, "ta": keys32, "max_hl": 20000},
                {"algo": ECBS_TA, "fixtures": fnames, "w": 1.0, "max_hl": 5000},
                {"algo": CBS_TA, "fixtures": fnames, "max_hl": 5000},
-               {"algo": ECBS_TA, "ta": [k for k in keys32 if g[k]["solved"]][:6], "w": 1.3, "max_hl": 5000}])
+               {"algo": ECBS_TA, "ta": [k for k in keys32 if g[k]["solved"]][:6], "w": 1.3, "max_hl": 5000},
+               # at w = 1.0 ecbs_ta must return the optimum the reference cbs_ta found (test_ecbs_ta.py:25-39
+               # asserts exactly that on the three fixtures)
+               {"algo": ECBS_TA, "ta": [k for k in keys8 if g[k]["solved"]][:25], "w": 1.0, "max_hl": 20000}])
     unsolved = 0
     for ks, o in ((keys8, out[0]), (keys32, out[1])):
         # the runner returns the instances in the generator's order, not in the order of `ks`
@@ -141,6 +144,9 @@ def test_cbs_ta_and_ecbs_ta(emu, set8, set32):
     order = [k for k in _ta_order(set8, set32) if k in set([k for k in keys32 if g[k]["solved"]][:6])]
     for k, r in zip(order, out[4]["results"]):
         assert r["status"] == 0 and g[k]["cost"] <= r["cost"] <= 1.3 * g[k]["cost"] + 1e-6, k
+    order = [k for k in _ta_order(set8, set32) if k in set([k for k in keys8 if g[k]["solved"]][:25])]
+    for k, r in zip(order, out[5]["results"]):
+        assert r["status"] == 0 and r["cost"] == g[k]["cost"], k
 
 
 def _ta_order(set8, set32):
