@@ -399,6 +399,12 @@ int mrp_conflicts_sharded_dev(const int32_t* d_cell, const int32_t* d_len, int N
 /* number of kernel launches issued by this library since mrp_init (bench.py's
  * `gpu_launches`) */
 long long mrp_launch_count(void);
+/* The geometry of the bordered row-major bitmap the queue BFS kernel keeps in shared memory for a map
+ * of `dimx` columns: words per row (odd, at least 3) and the multiply-shift constants with which the
+ * kernel turns a word index into a row (row = umulhi(word, magic) >> shift).  Host code, needs no
+ * device: exported so that the CPU tests can check the constants for every width (a width of at most 30
+ * columns once got a stride of one word, for which no 32-bit constant exists). */
+int mrp_bitmap_row_division(int dimx, int32_t* row_words, uint32_t* magic, int32_t* shift);
 
 #ifdef __cplusplus
 }

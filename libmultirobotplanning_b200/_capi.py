@@ -61,7 +61,7 @@ EXPORTS = [
     "mrp_pathpool_create", "mrp_pathpool_destroy", "mrp_pathpool_reserve", "mrp_pathpool_write",
     "mrp_pathpool_read", "mrp_conflicts_batch_pool", "mrp_lowlevel_batch_pool",
     "mrp_pathpool_reserve_states", "mrp_lowlevel_batch_pool_sliced",
-    "mrp_free_cell_index", "mrp_bfs_fields_compact",
+    "mrp_free_cell_index", "mrp_bfs_fields_compact", "mrp_bitmap_row_division",
 ]
 COMM_ID_BYTES = 128
 

@@ -524,10 +524,7 @@ int launchBfsQueue(const mrp_map_s* map, const int32_t* d_goal_cell, int n_goals
   p.nOpenWords = q.nOpenWords;
   p.cap = q.cap;
   // w / WPR for w < 2^27 (exact): magic = ceil(2^(32+s) / WPR), s = floor(log2 WPR)
-  int sh = 0;
-  while ((2 << sh) <= q.WPR) ++sh;
-  p.wprShift = sh;
-  p.wprMagic = (uint32_t)((((unsigned long long)1 << (32 + sh)) + (unsigned)q.WPR - 1) / (unsigned)q.WPR);
+  bitmapRowDivision(q.WPR, &p.wprMagic, &p.wprShift);
   const char* tma = getenv("MRP_BFS_TMA");
   p.tma = tma ? atoi(tma) : 1;
   if ((reinterpret_cast<uintptr_t>(map->d_rowbits) & 15) != 0) p.tma = 0;

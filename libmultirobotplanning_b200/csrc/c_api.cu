@@ -272,6 +272,15 @@ const char* mrp_device_info(void) {
 
 long long mrp_launch_count(void) { return g_launches.load(); }
 
+int mrp_bitmap_row_division(int dimx, int32_t* row_words, uint32_t* magic, int32_t* shift) {
+  MRP_CHECK(dimx > 0 && row_words && magic && shift, MRP_ERR_INVALID, "bad arguments");
+  *row_words = bitmapRowWords(dimx);
+  int sh = 0;
+  bitmapRowDivision(*row_words, magic, &sh);
+  *shift = sh;
+  return 0;
+}
+
 // ---- maps ------------------------------------------------------------------
 int mrp_map_create(int dimx, int dimy, const int32_t* obst_xy, int n_obst,
                    mrp_map* out) {

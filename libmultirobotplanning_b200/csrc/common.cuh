@@ -24,6 +24,15 @@ inline int bitmapRowWords(int dimx) {
   const int w = ((dimx + 2 + 31) / 32) | 1;
   return w < 3 ? 3 : w;
 }
+// word index -> bitmap row without a division: row = umulhi(word, magic) >> shift, exact for words
+// below 2^27 (magic = ceil(2^(32 + shift) / stride), shift = floor(log2 stride); the stride is odd and
+// at least 3, so the constant fits 32 bits).  Exported for the CPU tests (mrp_bitmap_row_division).
+inline void bitmapRowDivision(int rowWords, uint32_t* magic, int* shift) {
+  int sh = 0;
+  while ((2 << sh) <= rowWords) ++sh;
+  *shift = sh;
+  *magic = (uint32_t)((((unsigned long long)1 << (32 + sh)) + (unsigned)rowWords - 1) / (unsigned)rowWords);
+}
 
 constexpr int kTile = 32;  // maps are tiled in 32x32-cell tiles, one bit per cell
 

@@ -120,3 +120,33 @@ def test_free_cell_index_without_a_gpu():
     assert (got[:dimx * dimy].astype(bool) == free).all() and not got[dimx * dimy:].any()
     cs = np.concatenate([[0], np.cumsum(free)])
     assert all(prefix[w] == cs[min(32 * w, dimx * dimy)] for w in range(len(prefix)))
+
+
+def test_bitmap_row_division_constants():
+    """The queue BFS kernel turns a bitmap word index into a row with a 32-bit multiply-shift
+    (bfs_queue.cu: umulhi(word, magic) >> shift).  For every map width: the row stride is odd, at
+    least three words and covers the columns plus the border, and the constants divide exactly for
+    every word index the kernel can form (< 2^27).  (Maps at most 30 columns wide once got a stride of
+    one word, for which no 32-bit constant exists: narrow maps of more than one tile came out wrong.)
+    Host code only: no device needed."""
+    import ctypes as C
+    import numpy as np
+    from libmultirobotplanning_b200 import _capi
+    lib = _capi.lib()
+    rng = np.random.default_rng(0)
+    widths = list(range(1, 200)) + [255, 256, 257, 511, 512, 513, 1023, 1024, 1025, 2047, 2048, 2049, 4096,
+                                    30000, 65533]
+    for dimx in widths:
+        rw, mg, sh = C.c_int32(), C.c_uint32(), C.c_int32()
+        assert lib.mrp_bitmap_row_division(dimx, C.byref(rw), C.byref(mg), C.byref(sh)) == 0
+        W = rw.value
+        assert W % 2 == 1 and W >= 3 and 32 * W >= dimx + 2, dimx
+        k = np.concatenate([np.arange(0, 100000, dtype=np.uint64),
+                            rng.integers(0, 1 << 27, 100000).astype(np.uint64),
+                            np.array([(1 << 27) - 1], np.uint64)])
+        m = (k // np.uint64(W)) * np.uint64(W)  # both sides of every row boundary
+        w = np.unique(np.concatenate([k, m, np.maximum(m, np.uint64(1)) - np.uint64(1), m + np.uint64(W - 1)]))
+        w = w[w < (1 << 27)]
+        got = ((w * np.uint64(mg.value)) >> np.uint64(32)) >> np.uint64(sh.value)
+        assert np.array_equal(got, w // np.uint64(W)), dimx
+    assert lib.mrp_bitmap_row_division(0, C.byref(rw), C.byref(mg), C.byref(sh)) < 0
