@@ -59,7 +59,8 @@ def main():
         before = (ctypes.c_long * 9)()
         emu.mrp_emu_counters(before)
         res = solver.solve_batch(run["algo"], insts, w=run.get("w", 1.0), max_hl=run.get("max_hl", 0),
-                                 max_ll=run.get("max_ll", 12000), max_ll_total=run.get("max_ll_total", 0))
+                                 max_ll=run.get("max_ll", 12000), max_ll_total=run.get("max_ll_total", 0),
+                                 max_seconds=run.get("max_seconds", 0.0))
         after = (ctypes.c_long * 9)()
         emu.mrp_emu_counters(after)
         for r in res:

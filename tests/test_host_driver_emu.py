@@ -291,3 +291,27 @@ def test_reference_templates_with_our_environment_on_the_emulation(emu, ref_fixt
             assert ("cost %d" % want) in r.stdout, (name, algo, r.stdout[-200:])
             n += 1
     assert n >= 9
+
+
+def test_caps_end_an_instance_as_capped(emu, set8, set32):
+    """The reference's searches are unbounded; the drivers' caps (high-level expansions, expansions
+    per replan, low-level expansions per instance, wall clock) must end an instance as CAPPED (2),
+    never as "no solution", in the sliced, lock-step and table drivers — including flights that
+    are dropped while their replans are suspended."""
+    e100 = [i.name for i in set32 if i.n_agents == 100][:8]
+    n8 = [i.name for i in set8 if i.n_agents >= 12][:40]
+    out = emu([
+        {"algo": ECBS, "set": "bench_32x32", "names": e100, "w": 1.3, "max_hl": 2000, "max_ll_total": 15000,
+         "env": {"MRP_HOST_SLICE": "64", "MRP_HOST_LANES": "2", "MRP_HOST_LANE_SIZE": "4"}},
+        {"algo": ECBS, "set": "bench_32x32", "names": e100, "w": 1.3, "max_hl": 3, "env": {"MRP_HOST_SLICE": "0"}},
+        {"algo": CBS, "set": "bench_8x8", "names": n8, "max_hl": 40, "max_ll": 200},
+        {"algo": CBS, "set": "bench_8x8", "names": n8, "max_hl": 40, "max_ll": 200,
+         "env": {"MRP_HOST_SLICE": "0", "MRP_HOST_POOL": "0"}},
+        {"algo": ECBS, "set": "bench_32x32", "names": e100, "w": 1.3, "max_hl": 2000, "max_seconds": 0.05,
+         "env": {"MRP_HOST_SLICE": "64"}},
+    ])
+    for o in out:
+        st = [r["status"] for r in o["results"]]
+        assert set(st) <= {0, 2} and 2 in st
+    # the same instances under the same caps: the sliced pool driver and the lock-step table driver agree
+    assert [(r["status"], r["cost"]) for r in out[2]["results"]] == [(r["status"], r["cost"]) for r in out[3]["results"]]
