@@ -1,5 +1,5 @@
 """Distance fields of narrow maps (dimx <= 30, more than one tile high: one bitmap word per row before the
-fix of bitmapRowWords) against the oracle.  usage: python tools/narrow_check.py"""
+fix of bitmapRowWords) against the oracle.  usage: python tests/narrow_check.py  (a checker script, not a pytest file: it uses the oracle, hence it lives under tests/)"""
 import os
 import sys
 import time
