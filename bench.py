@@ -320,6 +320,14 @@ def search_metrics(pkg, rank=0, world=1, dist=None, dev=None):
         out["ecbs_reference_binary_instances_per_s_1core"] = ref
         out["ecbs_reference_binary"] = ("unmodified example/ecbs.cpp + stand-in Boost/yaml-cpp "
                                         "headers (oracle/_ref), statistics.runtime convention")
+    try:  # the same binary on every host core at once (a side measurement: never fatal)
+        n_all = max(8, min(32, 2 * (os.cpu_count() or 4)))
+        allc = reference_binary_rate_all_cores("ecbs", insts[:n_all], ("-w", "1.3"), timeout=20.0)
+        if allc and allc[0]:
+            out["ecbs_reference_binary_instances_per_s_all_cores"] = allc[0]
+            out["ecbs_reference_binary_all_cores_sample"] = "%d instances, one process per core, %d cores" % (allc[2], allc[1])
+    except Exception as e:  # noqa: BLE001
+        out["ecbs_reference_binary_all_cores_error"] = repr(e)[:200]
     out["ecbs_cost_gpu_vs_cpu"] = [[a["cost"], b["cost"]] for a, b in zip(res, cres)]
     if world == 1:
         # throughput against batch size: the batch above plus three more of the same kind (the
@@ -560,6 +568,40 @@ def reference_binary_rate(tool, insts, extra, timeout=60.0):
                     total += float(yaml.safe_load(f)["statistics"]["runtime"])
                 solved += 1
     return solved / total if total > 0 else None
+
+
+def reference_binary_rate_all_cores(tool, insts, extra, timeout=60.0):
+    """Throughput of the reference's own binary with one process per host core (the reference is
+    single-threaded: this is all the host can do with it): `insts` are written out first, then run
+    concurrently; instances per second = solved / wall time of the whole set, process start and YAML
+    parsing included.  Returns (rate, cores, n) or None."""
+    import tempfile
+    from concurrent.futures import ThreadPoolExecutor
+    from libmultirobotplanning_b200 import instances as I
+    exe = os.path.join(ROOT, "oracle", "_ref", tool)
+    if not os.path.exists(exe) or not insts:
+        return None
+    allowed = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    cores = max(1, allowed)
+    with tempfile.TemporaryDirectory() as d:
+        files = []
+        for k, inst in enumerate(insts):
+            inp = os.path.join(d, "i%d.yaml" % k)
+            I.save_yaml(inst, inp)
+            files.append((inp, os.path.join(d, "o%d.yaml" % k)))
+
+        def one(io):
+            try:
+                subprocess.run([exe, "-i", io[0], "-o", io[1], *extra], stdout=subprocess.DEVNULL,
+                               stderr=subprocess.DEVNULL, timeout=timeout, check=True, cwd=d)
+            except Exception:
+                return 0
+            return int(os.path.exists(io[1]))
+        t0 = time.perf_counter()
+        with ThreadPoolExecutor(max_workers=cores) as ex:
+            solved = sum(ex.map(one, files))
+        dt = time.perf_counter() - t0
+    return (solved / dt if dt > 0 else None), cores, len(files)
 
 
 def reference_on_unsolved(tool, insts, extra, wall):
