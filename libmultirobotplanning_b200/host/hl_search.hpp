@@ -11,6 +11,13 @@
 // focalHeuristic), and ALL low-level replans they trigger run in one launch
 // (mrp_lowlevel_batch_fs: AStar / AStarEpsilon).  The per-goal distance fields
 // are computed once per batch and stay resident in HBM (mrp_fieldset).
+// cbs / ecbs batches keep the paths of all constraint-tree nodes in a device pool
+// (mrp_pathpool_*) and advance per instance: an expansion is a "flight" whose
+// replans run in slices (mrp_lowlevel_batch_pool_sliced), so a launch never lasts
+// as long as the slowest search.  A node is one flat block of its instance's
+// slab: pool rows, heads of parent-pointer constraint chains, a shared task
+// vector (see Node below).  The host logic is tested without a device on an
+// emulation of the C ABI (tests/emu, tests/test_host_driver_emu.py).
 //
 // Deviations from the reference, all result-preserving:
 //   * cbs/ecbs use the exact BFS distance field instead of the Manhattan
